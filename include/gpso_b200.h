@@ -1,0 +1,117 @@
+/*
+ * gpso_b200.h -- C ABI of the B200-native Gaussian-process surrogate hot path of pyGPSO.
+ *
+ * One opaque handle = one GPR surrogate on one GPU (training data, Cholesky factor L, inverse factor L^-1, alpha and
+ * all workspaces live in that GPU's HBM for the life of the handle).  Plain C: pointers, sizes, status codes; no
+ * C++ / torch types cross this boundary.  A handle is not thread-safe; use one per surrogate per GPU.
+ *
+ * The reference (jajcayn/pygpso, pure Python) has no FFI for this path; the seam is the Python attribute
+ * GPSurrogate.gpflow_model (gpso/gp_surrogate.py:163).  Each entry point below names the reference call it replaces.
+ *
+ * Conventions
+ *   - all matrices are row-major (C-contiguous) fp64, exactly like the numpy arrays the reference passes around;
+ *   - "_host"  : the pointer is host memory (pageable or pinned); the call does its own H2D/D2H and returns when the
+ *                outputs are valid;
+ *     "_dev"   : device memory of the handle's GPU; the call is enqueued on `stream` (a cudaStream_t passed as void*,
+ *                NULL = default stream) and is asynchronous unless stated;
+ *   - return value: 0 = GPSO_OK; >0 = LAPACK-style info, the Gram matrix is not positive definite at column `info`
+ *                (1-based); <0 = GPSO_E_* below.  No exception crosses the ABI; gpso_last_error() gives the text.
+ *   - hyper-parameter vectors are packed in GPflow's trainable_variables order:
+ *         [ lengthscale(s) (1, or d when ard) , kernel variance , likelihood (noise) variance , mean constant (if any) ]
+ *     `u`     = unconstrained (softplus pre-image; noise variance has the 1e-6 floor of gpflow.likelihoods.Gaussian),
+ *     `theta` = constrained values.
+ */
+#ifndef GPSO_B200_H
+#define GPSO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gpso_handle gpso_handle;
+
+enum {
+    GPSO_OK = 0,
+    GPSO_E_BADARG = -1,   /* null pointer, size <= 0, wrong length ...            */
+    GPSO_E_CUDA = -2,     /* a CUDA runtime call failed (text in gpso_last_error) */
+    GPSO_E_STATE = -3,    /* call order violated (e.g. predict before factorize)  */
+    GPSO_E_NOGPU = -4,    /* no usable sm_100 device                              */
+    GPSO_E_NOMEM = -5
+};
+
+/* gpflow.kernels.* accepted by GPRSurrogate(gp_kernel=...), gp_surrogate.py:393-402, default Matern52 (:424) */
+enum { GPSO_KERNEL_MATERN12 = 0, GPSO_KERNEL_MATERN32 = 1, GPSO_KERNEL_MATERN52 = 2, GPSO_KERNEL_SE = 3 };
+/* gpflow.mean_functions.*: None/Zero or Constant (:167, :427) */
+enum { GPSO_MEAN_ZERO = 0, GPSO_MEAN_CONSTANT = 1 };
+
+/* ---- library ------------------------------------------------------------------------------------------------- */
+int gpso_version(void);                 /* ABI version, currently 1 */
+const char* gpso_last_error(void);      /* thread-local text of the last failure */
+int gpso_device_count(void);            /* number of CUDA devices, or GPSO_E_* */
+
+/* ---- life cycle: replaces gpflow.models.GPR(...) construction, gp_surrogate.py:490-495 ----------------------- */
+int gpso_create(int device, int kernel_id, int ard, int mean_id, gpso_handle** out);
+int gpso_destroy(gpso_handle* h);
+
+/* model.data = (x, y), gp_surrogate.py:498.  X_host[N,d], y_host[N] are copied to the device. */
+int gpso_set_data(gpso_handle* h, const double* X_host, const double* y_host, int N, int d);
+
+/* ---- fit: the closure scipy's L-BFGS-B calls, i.e. model.training_loss + TF autodiff, gp_surrogate.py:500-503 -- */
+/* f = -log marginal likelihood at unconstrained u[p]; grad[p] = df/du.  Host in, host out, synchronous.            */
+int gpso_neg_lml_grad(gpso_handle* h, const double* u_host, int p, double* f_host, double* grad_host);
+
+/* Fix the hyper-parameters used by the predict calls: Gram -> Cholesky -> L^-1 -> alpha, cached on the device.
+ * (GPflow re-factorises inside every predict_y call; here it is done once per parameter change.) */
+int gpso_factorize(gpso_handle* h, const double* theta_host, int p);
+/* -LML at the factorised theta (valid after gpso_factorize). */
+int gpso_factor_lml(gpso_handle* h, double* lml_host);
+
+/* ---- predict: model.predict_y(Xnew), gp_surrogate.py:298 (noise variance included) ---------------------------- */
+int gpso_predict_y_host(gpso_handle* h, const double* Xc_host, int64_t M, double* mean_host, double* var_host);
+int gpso_predict_y_dev(gpso_handle* h, const double* Xc_dev, int64_t M, double* mean_dev, double* var_dev,
+                       void* stream);
+
+/* ---- exploitation step: gp_eval_best_ucb(normed_coords), gp_surrogate.py:313-328 ------------------------------ */
+/* ucb = mean + varsigma * var ; winner = FIRST index of the maximum (np.argmax; a NaN wins like in numpy).
+ * result_host[4] = { (double)index, mean, var, ucb }.  The cross-covariance is never materialised beyond a
+ * rolling window of candidates; mean/var of the non-winners are not written anywhere. */
+int gpso_ucb_argmax_host(gpso_handle* h, const double* Xc_host, int64_t M, double varsigma, double* result_host);
+/* Device-resident candidates.  Synchronous on `stream` at return (the 4 result doubles are copied back). */
+int gpso_ucb_argmax_dev(gpso_handle* h, const double* Xc_dev, int64_t M, double varsigma, double* result_host,
+                        void* stream);
+
+/* ---- leaf-coordinate batching: LeafNode.grow(depth), param_space.py:175-200 (+ ternary_split :257-307) -------- */
+/* bounds_host[d,2] = (lo,hi) per dimension of the leaf; out[(3^depth-1)/2, d] = centres in the reference's order
+ * (level by level, parents in order, children l,c,r), bit-identical to the Python arithmetic (no FMA contraction). */
+int64_t gpso_grow_count(int depth);
+int gpso_grow_leaves_host(int device, const double* bounds_host, int d, int depth, double* out_host);
+int gpso_grow_leaves_dev(int device, const double* bounds_host, int d, int depth, double* out_dev, void* stream);
+/* child.grow(depth) fused with gp_eval_best_ucb: optimisation.py:379-381.  Leaves never leave the device. */
+int gpso_grow_ucb_argmax(gpso_handle* h, const double* bounds_host, int d, int depth, double varsigma,
+                         double* result_host);
+
+/* ---- multi-GPU: share one fit with the ranks that score candidate shards -------------------------------------- */
+/* The fitted state (theta, scaled training inputs, alpha, L^-1) is exposed as ONE contiguous device buffer so the host
+ * side can broadcast it with a single NCCL call (torch.distributed.broadcast) and import it on the other ranks. */
+int gpso_state_bytes(gpso_handle* h, int N, int d, int64_t* bytes);   /* size for a given problem shape */
+int gpso_export_state_dev(gpso_handle* h, void* dst_dev, int64_t bytes, void* stream);
+int gpso_import_state_dev(gpso_handle* h, const void* src_dev, int64_t bytes, int N, int d, void* stream);
+
+/* ---- introspection for benchmarks / tests ---------------------------------------------------------------------- */
+/* kernel launches issued by this handle since creation (our own kernels only; memcpy/memset not counted) */
+int64_t gpso_launch_count(gpso_handle* h);
+/* copy device-side intermediates to the host for parity tests: which = 0 Gram+noise (N*N), 1 L (N*N, lower),
+ * 2 L^-1 (N*N, lower), 3 alpha (N), 4 K_y^-1 (N*N, lower; valid after gpso_neg_lml_grad) */
+int gpso_debug_fetch(gpso_handle* h, int which, double* out_host, int64_t count);
+/* elapsed device time in ms of the last gpso_ucb_argmax_* / gpso_predict_y_* / gpso_neg_lml_grad call, split per stage:
+ * out[0]=total, out[1]=cross-covariance generation, out[2]=triangular product+reduction, out[3]=finalise/argmax */
+int gpso_last_timing(gpso_handle* h, double* out_ms4);
+/* tuning knob: candidates per rolling window (0 = automatic) */
+int gpso_set_window(gpso_handle* h, int64_t candidates);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPSO_B200_H */

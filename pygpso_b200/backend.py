@@ -1,0 +1,291 @@
+"""
+ctypes binding of the C-ABI library ``libgpso_b200.so`` (declared in ``include/gpso_b200.h``).
+
+This is the only compute backend of the package.  If the shared library is missing, cannot be loaded, or no sm_100
+GPU is visible, every entry point raises ``GpsoBackendError`` -- there is deliberately no CPU fallback (the numpy
+oracle under ``oracle/`` is test infrastructure and is never imported from here).
+
+A *session* is one ``gpso_handle``: the device-resident state of one GPR surrogate on one GPU.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+KERNEL_IDS = {"Matern12": 0, "Matern32": 1, "Matern52": 2, "SquaredExponential": 3}
+_LIB_NAME = "libgpso_b200.so"
+_ABI_VERSION = 1
+
+_c_double_p = ctypes.POINTER(ctypes.c_double)
+
+
+class GpsoBackendError(RuntimeError):
+    """The CUDA library is unavailable or a device call failed."""
+
+
+class NotPositiveDefiniteError(np.linalg.LinAlgError):
+    """Cholesky of K + noise*I broke down (the C ABI returned a LAPACK-style info > 0)."""
+
+
+def _dptr(a):
+    return a.ctypes.data_as(_c_double_p)
+
+
+def library_path():
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), _LIB_NAME)
+
+
+_lib = None
+
+
+def load_library():
+    """dlopen the in-tree library and declare the prototypes.  Raises GpsoBackendError when it is not there."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not os.path.exists(path):
+        raise GpsoBackendError(
+            f"{path} not found: build it with `python -m pygpso_b200._build` (needs nvcc). "
+            "pygpso_b200 has no CPU fallback."
+        )
+    try:
+        lib = ctypes.CDLL(path)
+    except OSError as err:
+        raise GpsoBackendError(f"cannot load {path}: {err}") from err
+    H = ctypes.c_void_p
+    i32, i64, dbl = ctypes.c_int, ctypes.c_int64, ctypes.c_double
+    protos = {
+        "gpso_version": (i32, []),
+        "gpso_last_error": (ctypes.c_char_p, []),
+        "gpso_device_count": (i32, []),
+        "gpso_create": (i32, [i32, i32, i32, i32, ctypes.POINTER(H)]),
+        "gpso_destroy": (i32, [H]),
+        "gpso_set_data": (i32, [H, _c_double_p, _c_double_p, i32, i32]),
+        "gpso_neg_lml_grad": (i32, [H, _c_double_p, i32, _c_double_p, _c_double_p]),
+        "gpso_factorize": (i32, [H, _c_double_p, i32]),
+        "gpso_factor_lml": (i32, [H, _c_double_p]),
+        "gpso_predict_y_host": (i32, [H, _c_double_p, i64, _c_double_p, _c_double_p]),
+        "gpso_predict_y_dev": (i32, [H, ctypes.c_void_p, i64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+        "gpso_ucb_argmax_host": (i32, [H, _c_double_p, i64, dbl, _c_double_p]),
+        "gpso_ucb_argmax_dev": (i32, [H, ctypes.c_void_p, i64, dbl, _c_double_p, ctypes.c_void_p]),
+        "gpso_grow_count": (i64, [i32]),
+        "gpso_grow_leaves_host": (i32, [i32, _c_double_p, i32, i32, _c_double_p]),
+        "gpso_grow_leaves_dev": (i32, [i32, _c_double_p, i32, i32, ctypes.c_void_p, ctypes.c_void_p]),
+        "gpso_grow_ucb_argmax": (i32, [H, _c_double_p, i32, i32, dbl, _c_double_p]),
+        "gpso_state_bytes": (i32, [H, i32, i32, ctypes.POINTER(i64)]),
+        "gpso_export_state_dev": (i32, [H, ctypes.c_void_p, i64, ctypes.c_void_p]),
+        "gpso_import_state_dev": (i32, [H, ctypes.c_void_p, i64, i32, i32, ctypes.c_void_p]),
+        "gpso_launch_count": (i64, [H]),
+        "gpso_debug_fetch": (i32, [H, i32, _c_double_p, i64]),
+        "gpso_last_timing": (i32, [H, _c_double_p]),
+        "gpso_set_window": (i32, [H, i64]),
+    }
+    for name, (restype, argtypes) in protos.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as err:
+            raise GpsoBackendError(f"{path} does not export {name}") from err
+        fn.restype = restype
+        fn.argtypes = argtypes
+    if lib.gpso_version() != _ABI_VERSION:
+        raise GpsoBackendError(f"{path}: ABI version {lib.gpso_version()} != expected {_ABI_VERSION}")
+    _lib = lib
+    return lib
+
+
+EXPORTED_SYMBOLS = (
+    "gpso_version gpso_last_error gpso_device_count gpso_create gpso_destroy gpso_set_data gpso_neg_lml_grad "
+    "gpso_factorize gpso_factor_lml gpso_predict_y_host gpso_predict_y_dev gpso_ucb_argmax_host gpso_ucb_argmax_dev "
+    "gpso_grow_count gpso_grow_leaves_host gpso_grow_leaves_dev gpso_grow_ucb_argmax gpso_state_bytes "
+    "gpso_export_state_dev gpso_import_state_dev gpso_launch_count gpso_debug_fetch gpso_last_timing gpso_set_window"
+).split()
+
+
+def _check(lib, rc, what):
+    if rc == 0:
+        return
+    text = lib.gpso_last_error().decode("utf-8", "replace")
+    if rc > 0:
+        raise NotPositiveDefiniteError(f"{what}: {text}")
+    raise GpsoBackendError(f"{what} failed (status {rc}): {text}")
+
+
+def default_device():
+    """GPU index for this process: LOCAL_RANK under torchrun, else GPSO_DEVICE, else 0."""
+    for var in ("GPSO_DEVICE", "LOCAL_RANK"):
+        if var in os.environ:
+            return int(os.environ[var])
+    return 0
+
+
+class CudaSession:
+    """One gpso_handle."""
+
+    def __init__(self, lib, device, kernel, n_lengthscales, has_mean):
+        if kernel not in KERNEL_IDS:
+            raise ValueError(f"unsupported kernel {kernel!r}; choose from {sorted(KERNEL_IDS)}")
+        self._lib = lib
+        self.device = device
+        self.kernel = kernel
+        self.ard = n_lengthscales > 1
+        self.has_mean = bool(has_mean)
+        handle = ctypes.c_void_p()
+        _check(lib, lib.gpso_create(device, KERNEL_IDS[kernel], int(self.ard), int(self.has_mean), ctypes.byref(handle)),
+               "gpso_create")
+        self._h = handle
+        self.N = self.d = 0
+
+    # -- fit ----------------------------------------------------------------------------------------------------------
+    def set_data(self, x, y):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.ascontiguousarray(y, dtype=np.float64).reshape(-1)
+        _check(self._lib, self._lib.gpso_set_data(self._h, _dptr(x), _dptr(y), x.shape[0], x.shape[1]), "gpso_set_data")
+        self.N, self.d = x.shape
+
+    def neg_lml_and_grad(self, u):
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        f = ctypes.c_double()
+        grad = np.empty_like(u)
+        _check(self._lib, self._lib.gpso_neg_lml_grad(self._h, _dptr(u), u.size, ctypes.byref(f), _dptr(grad)),
+               "gpso_neg_lml_grad")
+        return float(f.value), grad
+
+    def factorize(self, theta):
+        theta = np.ascontiguousarray(theta, dtype=np.float64)
+        _check(self._lib, self._lib.gpso_factorize(self._h, _dptr(theta), theta.size), "gpso_factorize")
+
+    def log_marginal_likelihood(self):
+        v = ctypes.c_double()
+        _check(self._lib, self._lib.gpso_factor_lml(self._h, ctypes.byref(v)), "gpso_factor_lml")
+        return float(v.value)
+
+    # -- predict ------------------------------------------------------------------------------------------------------
+    def predict_y(self, xnew):
+        xnew = np.ascontiguousarray(xnew, dtype=np.float64)
+        m = xnew.shape[0]
+        mean = np.empty(m)
+        var = np.empty(m)
+        if m:
+            _check(self._lib, self._lib.gpso_predict_y_host(self._h, _dptr(xnew), m, _dptr(mean), _dptr(var)),
+                   "gpso_predict_y_host")
+        return mean, var
+
+    def ucb_argmax(self, xnew, varsigma):
+        xnew = np.ascontiguousarray(xnew, dtype=np.float64)
+        out = np.empty(4)
+        _check(self._lib, self._lib.gpso_ucb_argmax_host(self._h, _dptr(xnew), xnew.shape[0], float(varsigma), _dptr(out)),
+               "gpso_ucb_argmax_host")
+        return int(out[0]), float(out[1]), float(out[2]), float(out[3])
+
+    def grow_ucb_argmax(self, bounds, depth, varsigma):
+        bounds = np.ascontiguousarray(bounds, dtype=np.float64)
+        out = np.empty(4)
+        _check(self._lib, self._lib.gpso_grow_ucb_argmax(self._h, _dptr(bounds), bounds.shape[0], int(depth), float(varsigma),
+                                                         _dptr(out)), "gpso_grow_ucb_argmax")
+        return int(out[0]), float(out[1]), float(out[2]), float(out[3])
+
+    # -- device-pointer variants (benchmarks, multi-GPU sharding): pointers are ints (e.g. torch.Tensor.data_ptr()) -----
+    def predict_y_dev(self, xc_ptr, m, mean_ptr, var_ptr, stream=0):
+        _check(self._lib, self._lib.gpso_predict_y_dev(self._h, xc_ptr, m, mean_ptr, var_ptr, stream), "gpso_predict_y_dev")
+
+    def ucb_argmax_dev(self, xc_ptr, m, varsigma, stream=0):
+        out = np.empty(4)
+        _check(self._lib, self._lib.gpso_ucb_argmax_dev(self._h, xc_ptr, m, float(varsigma), _dptr(out), stream),
+               "gpso_ucb_argmax_dev")
+        return int(out[0]), float(out[1]), float(out[2]), float(out[3])
+
+    def state_bytes(self, n=None, d=None):
+        v = ctypes.c_int64()
+        _check(self._lib, self._lib.gpso_state_bytes(self._h, n or self.N, d or self.d, ctypes.byref(v)), "gpso_state_bytes")
+        return int(v.value)
+
+    def export_state_dev(self, dst_ptr, nbytes, stream=0):
+        _check(self._lib, self._lib.gpso_export_state_dev(self._h, dst_ptr, nbytes, stream), "gpso_export_state_dev")
+
+    def import_state_dev(self, src_ptr, nbytes, n, d, stream=0):
+        _check(self._lib, self._lib.gpso_import_state_dev(self._h, src_ptr, nbytes, n, d, stream), "gpso_import_state_dev")
+        self.N, self.d = n, d
+
+    # -- introspection ------------------------------------------------------------------------------------------------
+    def launch_count(self):
+        return int(self._lib.gpso_launch_count(self._h))
+
+    def last_timing_ms(self):
+        out = np.zeros(4)
+        _check(self._lib, self._lib.gpso_last_timing(self._h, _dptr(out)), "gpso_last_timing")
+        return out
+
+    def set_window(self, candidates):
+        _check(self._lib, self._lib.gpso_set_window(self._h, int(candidates)), "gpso_set_window")
+
+    def debug_fetch(self, which):
+        n = self.N
+        out = np.empty(n if which == 3 else n * n)
+        _check(self._lib, self._lib.gpso_debug_fetch(self._h, which, _dptr(out), out.size), "gpso_debug_fetch")
+        return out if which == 3 else out.reshape(n, n)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.gpso_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class CudaBackend:
+    """Factory of sessions on one GPU plus the handle-free entry points (leaf generation)."""
+
+    name = "cuda-sm100a"
+
+    def __init__(self, device=None):
+        self._lib = load_library()
+        n = self._lib.gpso_device_count()
+        if n <= 0:
+            raise GpsoBackendError(
+                "no CUDA device visible: pygpso_b200 runs its surrogate on a B200 GPU and has no CPU fallback "
+                f"({self._lib.gpso_last_error().decode('utf-8', 'replace')})"
+            )
+        self.device = default_device() if device is None else int(device)
+
+    def open_session(self, kernel, n_lengthscales, has_mean):
+        return CudaSession(self._lib, self.device, kernel, n_lengthscales, has_mean)
+
+    def grow_count(self, depth):
+        return int(self._lib.gpso_grow_count(int(depth)))
+
+    def grow_leaves(self, bounds, depth):
+        """``LeafNode.grow(depth)`` coordinates for the box ``bounds[d,2]``, generated on the GPU, returned as numpy."""
+        bounds = np.ascontiguousarray(bounds, dtype=np.float64)
+        rows = self.grow_count(depth)
+        if rows <= 0:
+            raise ValueError(f"bad depth {depth}")
+        out = np.empty((rows, bounds.shape[0]))
+        _check(self._lib, self._lib.gpso_grow_leaves_host(self.device, _dptr(bounds), bounds.shape[0], int(depth), _dptr(out)),
+               "gpso_grow_leaves_host")
+        return out
+
+    def grow_leaves_dev(self, bounds, depth, out_ptr, stream=0):
+        bounds = np.ascontiguousarray(bounds, dtype=np.float64)
+        _check(self._lib, self._lib.gpso_grow_leaves_dev(self.device, _dptr(bounds), bounds.shape[0], int(depth), out_ptr, stream),
+               "gpso_grow_leaves_dev")
+
+
+_default = None
+
+
+def default_backend():
+    """The process-wide CUDA backend (created on first use; raises GpsoBackendError when unavailable)."""
+    global _default
+    if _default is None:
+        _default = CudaBackend()
+    return _default
+
+
+def reset_default_backend():
+    global _default
+    _default = None

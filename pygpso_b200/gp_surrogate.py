@@ -1,0 +1,434 @@
+"""
+Gaussian-process surrogate of the objective function -- the reference's ``gpso/gp_surrogate.py`` with the
+GPflow/TensorFlow arithmetic replaced by the B200 library.
+
+Kept API (reference file:line): ``GPPoint`` (:24-36), ``GPListOfPoints`` (:39-118), ``GPSurrogate`` (:121-385:
+``append``, ``gp_predict``, ``gp_eval_best_ucb``, ``gp_update``, ``_gp_train``, the ``num_*`` / ``highest_*`` /
+``current_training_data`` / ``gp_based_coords`` properties, optimiser (de)serialisation, ``save`` / ``from_saved``) and
+``GPRSurrogate`` (:388-533, incl. ``default()``).  ``fit`` / ``predict_y`` are thin aliases named by the build brief.
+``surrogate.gpflow_model`` is a :class:`pygpso_b200.gpmodel.GPR`.
+
+Two reference conventions that parity depends on are kept verbatim: the UCB uses the *variance*
+(``ucb = mean + varsigma * var``; ``score_sigma`` stores a variance, :305-308, :326) and ``predict_y`` includes the
+noise variance.
+
+Host-side change: the point list keeps a dense coordinate matrix next to the list so the duplicate test of
+``append`` / ``find_by_coords`` (tolerance 1e-12, :20, :68-101) is one vectorised distance computation instead of a
+Python loop over all points; order, replace-in-place and "evaluated wins" semantics are unchanged.
+"""
+import json
+import logging
+import os
+from collections import namedtuple
+
+import dill
+import numpy as np
+from scipy.special import erfcinv
+
+from . import gpmodel
+from .param_space import NORM_PARAMS_BOUNDS
+from .utils import JSON_EXT, PKL_EXT, PointLabels, load_json, make_dirs
+
+GP_TRAIN_MAX_ITER = 100
+DUPLICATE_TOLERANCE = 1.0e-12
+
+
+class GPPoint(namedtuple("GPPoint", ["normed_coord", "score_mu", "score_sigma", "score_ucb", "label"])):
+    """One point of the surrogate: normalised coordinates, mean, variance (sic), UCB and label."""
+
+    def __eq__(self, other):
+        if not isinstance(other, tuple) or len(other) != len(self):
+            return False
+        return all(np.array_equal(mine, theirs) for mine, theirs in zip(self, other))
+
+    def __ne__(self, other):
+        return not self.__eq__(other)
+
+    __hash__ = None
+
+
+class GPListOfPoints(list):
+    """List of :class:`GPPoint` whose ``append`` de-duplicates on coordinates (Euclidean distance < 1e-12)."""
+
+    @classmethod
+    def from_file(cls, filename):
+        if not filename.endswith(JSON_EXT):
+            filename += JSON_EXT
+        points = []
+        for item in load_json(filename):
+            item["normed_coord"] = np.array(item["normed_coord"])
+            item["label"] = PointLabels[item["label"]]
+            points.append(GPPoint(**item))
+        return cls(points)
+
+    def __init__(self, *args, **kwargs):
+        if args:
+            assert all(isinstance(it, GPPoint) for it in args[0])
+        super().__init__(*args, **kwargs)
+        self._coords = None  # [capacity, d] mirror of the coordinates of self[0:len(self)]
+        self._count = 0
+
+    # -- coordinate mirror --------------------------------------------------------------------------------------------
+    def _mirror(self):
+        n = len(self)
+        if self._coords is None or self._count != n:
+            if n == 0:
+                self._coords, self._count = None, 0
+                return None
+            d = np.size(self[0].normed_coord)
+            cap = max(64, 2 * n)
+            coords = np.empty((cap, d))
+            for i, point in enumerate(self):
+                coords[i] = point.normed_coord
+            self._coords, self._count = coords, n
+        return self._coords[: self._count]
+
+    def _invalidate(self):
+        self._coords, self._count = None, 0
+
+    def _matches(self, coords):
+        """Indices (ascending) of the points closer than the tolerance to ``coords``."""
+        mirror = self._mirror()
+        if mirror is None:
+            return ()
+        diff = mirror - np.asarray(coords, dtype=np.float64)
+        dist2 = np.einsum("ij,ij->i", diff, diff)
+        hits = np.flatnonzero(np.sqrt(dist2) < DUPLICATE_TOLERANCE)
+        return hits
+
+    # -- list protocol ------------------------------------------------------------------------------------------------
+    def append(self, object):
+        assert isinstance(object, GPPoint)
+        hits = self._matches(object.normed_coord)
+        if len(hits) == 0:
+            n = len(self)
+            super().append(object)
+            if self._coords is not None and self._count == n and n < self._coords.shape[0]:
+                self._coords[n] = object.normed_coord
+                self._count = n + 1
+            else:
+                self._invalidate()
+            return
+        for idx in hits:
+            # an evaluated point is never overwritten; a GP-based one is replaced in place
+            if self[idx].label == PointLabels.evaluated:
+                continue
+            list.__setitem__(self, int(idx), object)
+            self._coords[int(idx)] = object.normed_coord
+
+    def find_by_coords(self, coords):
+        """First point (list order) within the tolerance of ``coords``, or None."""
+        hits = self._matches(coords)
+        return self[int(hits[0])] if len(hits) else None
+
+    def index_by_coords(self, coords):
+        hits = self._matches(coords)
+        return int(hits[0]) if len(hits) else None
+
+    def _mutating(name):
+        def method(self, *args, **kwargs):
+            self._invalidate()
+            return getattr(list, name)(self, *args, **kwargs)
+
+        method.__name__ = name
+        return method
+
+    for _name in ("__setitem__", "__delitem__", "__iadd__", "__imul__", "insert", "extend", "pop", "remove", "clear",
+                  "sort", "reverse"):
+        locals()[_name] = _mutating(_name)
+    del _name, _mutating
+
+    def save(self, filename):
+        if not filename.endswith(JSON_EXT):
+            filename += JSON_EXT
+        serialised = []
+        for point in self:
+            item = point._asdict()
+            item["normed_coord"] = np.asarray(item["normed_coord"]).tolist()
+            item["label"] = item["label"].name
+            serialised.append(item)
+        with open(filename, "w") as handle:
+            handle.write(json.dumps(serialised))
+
+
+class GPSurrogate:
+    """Bookkeeping of evaluated / GP-predicted points around a GP model; subclasses supply the model and its training."""
+
+    POINTS_FILE = f"points{JSON_EXT}"
+    GPR_FILE = f"GPRmodel{PKL_EXT}"
+    GPR_INFO = f"GPRinfo{JSON_EXT}"
+
+    @classmethod
+    def from_saved(cls, folder):
+        raise NotImplementedError
+
+    def __init__(
+        self,
+        gp_kernel,
+        gp_meanf=None,
+        optimiser=None,
+        varsigma=erfcinv(0.01),
+        points=None,
+        gpflow_model=None,
+        backend=None,
+    ):
+        """
+        :param gp_kernel: covariance function (``pygpso_b200.gpmodel.kernels.*``)
+        :param gp_meanf: mean function (``gpmodel.mean_functions.Constant`` / ``Zero``) or None
+        :param optimiser: object with ``minimize(closure, variables)``; default ``gpmodel.optimizers.Scipy()``
+        :param varsigma: UCB multiplier, ``ucb = mean + varsigma * var``
+        :param points: initial list of :class:`GPPoint`
+        :param gpflow_model: an initialised model (only used when loading a saved surrogate)
+        :param backend: compute backend; None = the CUDA library (tests inject a checker backend here)
+        """
+        self.gpflow_model = gpflow_model
+        self.gp_varsigma = varsigma
+        assert isinstance(gp_kernel, gpmodel.Kernel)
+        self.gp_kernel = gp_kernel
+        assert gp_meanf is None or isinstance(gp_meanf, gpmodel.MeanFunction)
+        self.gp_meanf = gp_meanf
+        optimiser = gpmodel.Scipy() if optimiser is None else optimiser
+        assert hasattr(optimiser, "minimize")
+        self.optimiser = optimiser
+        self.backend = backend
+        self.points = GPListOfPoints(points or list())
+
+    # -- views on the point list --------------------------------------------------------------------------------------
+    def _with_label(self, label):
+        return [point for point in self.points if point.label == label]
+
+    @property
+    def num_evaluated(self):
+        return sum(1 for point in self.points if point.label == PointLabels.evaluated)
+
+    @property
+    def num_gp_based(self):
+        return sum(1 for point in self.points if point.label == PointLabels.gp_based)
+
+    @property
+    def highest_score(self):
+        """Evaluated point with the highest score (first one on ties), or None."""
+        best = None
+        for point in self.points:
+            if point.label == PointLabels.evaluated and (best is None or point.score_mu > best.score_mu):
+                best = point
+        return best
+
+    @property
+    def highest_ucb(self):
+        """GP-based point with the highest UCB (first one on ties), or None."""
+        best = None
+        for point in self.points:
+            if point.label == PointLabels.gp_based and (best is None or point.score_ucb > best.score_ucb):
+                best = point
+        return best
+
+    @property
+    def current_training_data(self):
+        evaluated = self._with_label(PointLabels.evaluated)
+        x = np.array([point.normed_coord for point in evaluated])
+        y = np.array([point.score_mu for point in evaluated])
+        return x, y
+
+    @property
+    def gp_based_coords(self):
+        return np.array([point.normed_coord for point in self._with_label(PointLabels.gp_based)])
+
+    # -- to be provided by the concrete surrogate ---------------------------------------------------------------------
+    def _gp_train(self, x, y):
+        raise NotImplementedError
+
+    def save(self, folder):
+        raise NotImplementedError
+
+    # -- data ---------------------------------------------------------------------------------------------------------
+    def append(self, coords, scores):
+        """Add objective evaluations (normalised ``coords[n,d]``, ``scores[n]``) as training points."""
+        assert coords.ndim == 2
+        assert scores.ndim == 1
+        assert coords.shape[0] == scores.shape[0]
+        for idx in range(coords.shape[0]):
+            self.points.append(
+                GPPoint(
+                    normed_coord=coords[idx, :],
+                    score_mu=scores[idx],
+                    score_sigma=0.0,
+                    score_ucb=0.0,
+                    label=PointLabels.evaluated,
+                )
+            )
+
+    # -- prediction ---------------------------------------------------------------------------------------------------
+    def _require_model(self):
+        assert isinstance(self.gpflow_model, gpmodel.GPModel), "train the surrogate (gp_update / _gp_train) first"
+        return self.gpflow_model
+
+    def predict_y(self, normed_coords):
+        """Posterior mean and variance (noise included), both ``[M,1]``; alias of ``gpflow_model.predict_y``."""
+        return self._require_model().predict_y(normed_coords)
+
+    def gp_predict(self, normed_coords):
+        """Predict at ``normed_coords[M,d]`` and store one GP-based point per row (duplicates replace in place)."""
+        mean, var = self._require_model().predict_y(normed_coords)
+        mean = np.asarray(mean).reshape(-1)
+        var = np.asarray(var).reshape(-1)
+        for idx in range(normed_coords.shape[0]):
+            self.points.append(
+                GPPoint(
+                    normed_coord=normed_coords[idx, :],
+                    score_mu=float(mean[idx]),
+                    score_sigma=float(var[idx]),
+                    score_ucb=float(mean[idx] + self.gp_varsigma * var[idx]),
+                    label=PointLabels.gp_based,
+                )
+            )
+
+    def gp_eval_best_ucb(self, normed_coords):
+        """(mean, var, ucb) of the candidate with the highest ``mean + varsigma*var`` (first one on ties)."""
+        _, mean, var, ucb = self._require_model().ucb_argmax(normed_coords, self.gp_varsigma)
+        return mean, var, ucb
+
+    def gp_eval_best_ucb_in_leaf(self, leaf, depth):
+        """
+        ``gp_eval_best_ucb(leaf.grow(depth))`` without the round trip through the host: the leaf-centre batch is
+        generated on the device and scored in place (reference optimisation.py:379-381).
+        """
+        _, mean, var, ucb = self._require_model().grow_ucb_argmax(leaf.bounds_array(), depth, self.gp_varsigma)
+        return mean, var, ucb
+
+    def gp_update(self):
+        """Re-train on all evaluated points, then refresh every GP-based point with the new posterior."""
+        x_train, y_train = self.current_training_data
+        logging.debug(f"Retraining GPR with x data: {x_train}; y data: {y_train}")
+        self._gp_train(x=x_train, y=y_train[:, np.newaxis])
+        if self.num_gp_based > 0:
+            self.gp_predict(self.gp_based_coords)
+
+    def fit(self, x=None, y=None):
+        """Alias: train on (x, y[:,None]) or, without arguments, on the evaluated points."""
+        if x is None:
+            x, y = self.current_training_data
+            y = y[:, np.newaxis]
+        return self._gp_train(x=x, y=y)
+
+    # -- optimiser (de)serialisation ----------------------------------------------------------------------------------
+    def _serialise_optimiser(self):
+        name = self.optimiser.__class__.__name__
+        if name == "Scipy":
+            return tuple([name])
+        raise ValueError(f"{name} not currently supported.")
+
+    @staticmethod
+    def _deserialse_optimiser(from_json):
+        if from_json[0] == "Scipy":
+            return gpmodel.Scipy()
+        raise ValueError(f"{from_json[0]} not currently supported.")
+
+
+class GPRSurrogate(GPSurrogate):
+    """Surrogate on exact GP regression with a Gaussian likelihood."""
+
+    def __init__(
+        self,
+        gp_kernel,
+        gp_meanf=None,
+        optimiser=None,
+        varsigma=erfcinv(0.01),
+        gauss_likelihood_sigma=1.0e-3,
+        points=None,
+        gpflow_model=None,
+        backend=None,
+    ):
+        """:param gauss_likelihood_sigma: initial noise *variance* of the Gaussian likelihood (normalised units)"""
+        super().__init__(
+            gp_kernel=gp_kernel,
+            gp_meanf=gp_meanf,
+            optimiser=optimiser,
+            varsigma=varsigma,
+            points=points,
+            gpflow_model=gpflow_model,
+            backend=backend,
+        )
+        self.gp_lik_sigma = gauss_likelihood_sigma
+
+    @classmethod
+    def default(cls, backend=None):
+        """Matern-5/2 with lengthscale 0.25, unit variance, constant mean 0, noise variance 1e-3, SciPy L-BFGS-B."""
+        return cls(
+            gp_kernel=gpmodel.Matern52(lengthscales=np.sum(NORM_PARAMS_BOUNDS) * 0.25, variance=1.0),
+            gp_meanf=gpmodel.Constant(0.0),
+            optimiser=gpmodel.Scipy(),
+            varsigma=erfcinv(0.01),
+            gauss_likelihood_sigma=1.0e-3,
+            points=None,
+            gpflow_model=None,
+            backend=backend,
+        )
+
+    def _gp_train(self, x, y):
+        assert x.shape[0] == y.shape[0]
+        assert x.ndim == 2 and y.ndim == 2
+        if self.gpflow_model is None:
+            self.gpflow_model = gpmodel.GPR(
+                data=(x, y),
+                kernel=self.gp_kernel,
+                mean_function=self.gp_meanf,
+                noise_variance=self.gp_lik_sigma,
+                backend=self.backend,
+            )
+        else:
+            self.gpflow_model.data = (x, y)  # hyper-parameters warm-start from the previous optimum
+        return self.optimiser.minimize(self.gpflow_model.training_loss, self.gpflow_model.trainable_variables)
+
+    # -- persistence: same file names and JSON keys as the reference (:505-533 / :436-482) -----------------------------
+    def save(self, folder):
+        make_dirs(folder)
+        self.points.save(filename=os.path.join(folder, self.POINTS_FILE))
+        model = self._require_model()
+        params = {key: np.asarray(p).copy() for key, p in gpmodel.parameter_dict(model).items()}
+        with open(os.path.join(folder, self.GPR_FILE), "wb") as handle:
+            dill.dump(params, handle)
+        meanf = model.mean_function
+        save_info = {
+            "gpr_kernel": model.kernel.__class__.__name__,
+            "gpr_kernel_shape": model.kernel.lengthscales.shape.as_list(),
+            "gpr_meanf": meanf.__class__.__name__,
+            "gpr_meanf_shape": meanf.parameters[0].shape.as_list() if meanf.parameters else [],
+            "gp_varsigma": self.gp_varsigma,
+            "gp_likelihood": self.gp_lik_sigma,
+            "optimiser": self._serialise_optimiser(),
+        }
+        with open(os.path.join(folder, self.GPR_INFO), "w") as handle:
+            handle.write(json.dumps(save_info))
+
+    @classmethod
+    def from_saved(cls, folder, backend=None):
+        points = GPListOfPoints.from_file(os.path.join(folder, cls.POINTS_FILE))
+        evaluated = [point for point in points if point.label == PointLabels.evaluated]
+        x = np.array([point.normed_coord for point in evaluated])
+        y = np.array([point.score_mu for point in evaluated])[:, np.newaxis]
+
+        info = load_json(os.path.join(folder, cls.GPR_INFO))
+        assert hasattr(gpmodel.kernels, info["gpr_kernel"])
+        gp_kernel = getattr(gpmodel.kernels, info["gpr_kernel"])(lengthscales=np.ones(info["gpr_kernel_shape"]))
+        assert hasattr(gpmodel.mean_functions, info["gpr_meanf"])
+        meanf_cls = getattr(gpmodel.mean_functions, info["gpr_meanf"])
+        gp_meanf = meanf_cls(np.zeros(info["gpr_meanf_shape"])) if meanf_cls is gpmodel.Constant else meanf_cls()
+        optimiser = cls._deserialse_optimiser(info["optimiser"])
+
+        model = gpmodel.GPR(
+            data=(x, y), kernel=gp_kernel, mean_function=gp_meanf, noise_variance=info["gp_likelihood"], backend=backend
+        )
+        with open(os.path.join(folder, cls.GPR_FILE), "rb") as handle:
+            params = dill.load(handle)
+        gpmodel.multiple_assign(model, params)
+        return cls(
+            gp_kernel=gp_kernel,
+            gp_meanf=gp_meanf,
+            optimiser=optimiser,
+            gauss_likelihood_sigma=info["gp_likelihood"],
+            varsigma=info["gp_varsigma"],
+            points=points,
+            gpflow_model=model,
+            backend=backend,
+        )

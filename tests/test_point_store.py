@@ -1,0 +1,83 @@
+"""GPListOfPoints keeps the reference's de-duplication semantics (gpso/gp_surrogate.py:68-101) -- CPU only."""
+import numpy as np
+
+from pygpso_b200.gp_surrogate import DUPLICATE_TOLERANCE, GPListOfPoints, GPPoint
+from pygpso_b200.utils import PointLabels
+
+
+def point(coord, mu=0.0, label=PointLabels.gp_based, ucb=0.0):
+    return GPPoint(normed_coord=np.asarray(coord, dtype=float), score_mu=mu, score_sigma=0.0, score_ucb=ucb, label=label)
+
+
+def literal_append(items, obj):
+    """The reference's loop, statement for statement in behaviour, on a plain list."""
+    add = True
+    for idx in range(len(items)):
+        if np.linalg.norm(items[idx].normed_coord - obj.normed_coord) < DUPLICATE_TOLERANCE:
+            add = False
+            if items[idx].label == PointLabels.evaluated:
+                continue
+            items[idx] = obj
+    if add:
+        items.append(obj)
+
+
+def test_append_matches_literal_semantics():
+    rng = np.random.default_rng(1)
+    base = rng.random((40, 3))
+    fast, slow = GPListOfPoints(), []
+    for step in range(400):
+        coord = base[rng.integers(40)] + (rng.random(3) < 0.3) * rng.normal(0, 3e-13, 3)
+        label = PointLabels.evaluated if rng.random() < 0.4 else PointLabels.gp_based
+        obj = point(coord, mu=float(step), label=label)
+        fast.append(obj)
+        literal_append(slow, obj)
+        assert len(fast) == len(slow)
+    for a, b in zip(fast, slow):
+        assert a == b and a.label == b.label and a.score_mu == b.score_mu
+
+
+def test_evaluated_is_never_overwritten_and_gp_is_replaced():
+    pts = GPListOfPoints()
+    pts.append(point([0.5, 0.5], 1.0, PointLabels.gp_based))
+    pts.append(point([0.5, 0.5], 2.0, PointLabels.gp_based))
+    assert len(pts) == 1 and pts[0].score_mu == 2.0
+    pts.append(point([0.5, 0.5], 3.0, PointLabels.evaluated))
+    assert len(pts) == 1 and pts[0].label == PointLabels.evaluated and pts[0].score_mu == 3.0
+    pts.append(point([0.5, 0.5], 4.0, PointLabels.gp_based))
+    assert len(pts) == 1 and pts[0].score_mu == 3.0
+    pts.append(point([0.5, 0.5 + 5e-13], 5.0, PointLabels.gp_based))  # inside the tolerance
+    assert len(pts) == 1
+    pts.append(point([0.5, 0.5 + 2e-12], 6.0, PointLabels.gp_based))  # outside
+    assert len(pts) == 2
+
+
+def test_find_by_coords_and_mutation_keeps_index_fresh():
+    pts = GPListOfPoints([point([0.1 * i, 0.2]) for i in range(10)])
+    assert pts.find_by_coords(np.array([0.3, 0.2])) is pts[3]
+    assert pts.find_by_coords(np.array([0.35, 0.2])) is None
+    assert pts.index_by_coords(np.array([0.9, 0.2])) == 9
+    del pts[3]
+    assert pts.find_by_coords(np.array([0.3, 0.2])) is None
+    pts.insert(0, point([0.3, 0.2], 9.0))
+    assert pts.find_by_coords(np.array([0.3, 0.2])).score_mu == 9.0
+    pts[1] = point([0.77, 0.77])
+    assert pts.find_by_coords(np.array([0.77, 0.77])) is pts[1]
+    pts.clear()
+    assert pts.find_by_coords(np.array([0.77, 0.77])) is None and len(pts) == 0
+
+
+def test_save_load(tmp_path):
+    pts = GPListOfPoints([point([0.1, 0.9], 1.5, PointLabels.evaluated, 0.3), point([0.4, 0.2], -2.0, PointLabels.gp_based, 7.0)])
+    path = str(tmp_path / "points")
+    pts.save(path)
+    loaded = GPListOfPoints.from_file(path)
+    assert isinstance(loaded, GPListOfPoints) and list(loaded) == list(pts)
+    assert loaded[0].label == PointLabels.evaluated and isinstance(loaded[0].normed_coord, np.ndarray)
+
+
+def test_gppoint_equality():
+    a = point([0.1, 0.2], 1.0)
+    assert a == point([0.1, 0.2], 1.0)
+    assert a != point([0.1, 0.2], 1.5)
+    assert a != point([0.1, 0.25], 1.0)
