@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""
+Benchmark of the hot path: predict_y + UCB + arg-max over leaf candidates (BASELINE.json metric, config C3:
+N=4096 training points, d=10, 1e7 candidates, Matern-5/2, fp64).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+One "step" = one full scoring pass over the candidate set (a `gp_eval_best_ucb` call at C3 size).  With N > 1 GPUs
+the candidates are sharded contiguously over the ranks (total work fixed -> "scaling": "strong"); the fit state is
+broadcast once with NCCL before the timed region (reported as broadcast_ms), and every step ends with the all-gather
+of one 32-byte record per rank.  Prints ONE JSON line on rank 0 (keys described in DESIGN.md section "Measurement").
+
+--impl reference times the CPU restatement of the reference's own path (oracle/gpr_oracle.py, GPflow op order incl.
+the Cholesky inside every predict_y call) on the box's host cores, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SEED = 20240517
+WORKLOADS = {
+    # name: (N, d, M, description)
+    "c3": (4096, 10, 10_000_000, "C3: UCB scoring, N=4096 train, d=10, 1e7 leaf candidates, Matern-5/2 fp64"),
+    "c2": (512, 2, 100_000, "C2: predict_y+UCB microbench, N=512 train, d=2, 1e5 candidates, Matern-5/2 fp64"),
+}
+FP64_PEAK_TFLOPS = 37.03  # measured DMMA.8x8x4 issue peak of this pool's B200 (profiles/r01_fp64_probe.txt)
+CPU_SAMPLE = 8192         # candidates per CPU-baseline step (bounded sample of the same workload)
+
+
+def synthetic_training(N, d):
+    rng = np.random.default_rng(SEED)
+    X = rng.random((N, d))
+    y = np.sin(3.0 * X.sum(axis=1)) + 0.01 * rng.standard_normal(N)
+    return X, y[:, None]
+
+
+def fixed_theta(d):
+    return np.array([0.25 * np.sqrt(d), 1.0, 1.0e-3, 0.0])
+
+
+def blas_threads():
+    try:
+        from threadpoolctl import threadpool_info
+
+        infos = [i for i in threadpool_info() if i.get("user_api") == "blas"]
+        if infos:
+            return int(max(i["num_threads"] for i in infos)), infos[0].get("internal_api", "blas")
+    except Exception:
+        pass
+    return os.cpu_count() or 1, "unknown"
+
+
+def cpu_reference_step(X, y, theta, Xc, varsigma):
+    """The reference path on the CPU: predict_y (Cholesky inside, Kmn materialised, two TRSMs) + UCB + argmax."""
+    from oracle import gpr_oracle as go
+
+    h = go.Hyper(theta[0], theta[1], theta[2], theta[3])
+    mean, var = go.predict_y("Matern52", X, y, h, Xc, chunk=65536)
+    return go.ucb_argmax(mean, var, varsigma)
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU with nvidia-smi while the timed region runs."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu_index = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        self.join(timeout=2)
+        sm, smax, reasons = [], 0.0, set()
+        for row in self.rows:
+            try:
+                sm.append(float(row[0]))
+                smax = max(smax, float(row[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), row[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def run_reference(args, rank):
+    """--impl reference: the CPU path on the host cores (rank 0 only)."""
+    if rank != 0:
+        return
+    from oracle import gpr_oracle as go
+
+    N, d, M, desc = WORKLOADS[args.workload]
+    X, y = synthetic_training(N, d)
+    theta = fixed_theta(d)
+    sample = min(M, CPU_SAMPLE)
+    Xc = np.random.default_rng([SEED, 0]).random((sample, d))
+    for _ in range(args.warmup):
+        cpu_reference_step(X, y, theta, Xc, go.VARSIGMA_DEFAULT)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_reference_step(X, y, theta, Xc, go.VARSIGMA_DEFAULT)
+    dt = time.perf_counter() - t0
+    cores, blas = blas_threads()
+    value = sample * args.steps / dt
+    line = {
+        "impl": "reference", "metric": "predict_y+UCB candidates/sec", "value": value, "unit": "candidates/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": desc, "N": N, "d": d, "M": M, "kernel": "Matern52", "theta": theta.tolist()},
+        "cpu_baseline": {"value": value, "unit": "candidates/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample} of the {M} candidates per step (numpy/scipy restatement of GPflow's predict_y op "
+                                   f"sequence incl. the per-call Cholesky; {blas} BLAS, {cores} threads; GPflow itself is not "
+                                   "installable here)"},
+        "e2e": {"value": value, "unit": "candidates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--candidates", type=int, default=0, help="override the number of candidates (smoke runs only)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from oracle import gpr_oracle as go  # checker + cpu_baseline leg only
+    from pygpso_b200 import backend, gpmodel
+    from pygpso_b200.distributed import ShardedScorer, gather_records, pick_best, shard_bounds
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (pygpso_b200 has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    os.environ.setdefault("GPSO_DEVICE", str(local_rank))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    N, d, M, desc = WORKLOADS[args.workload]
+    if args.candidates:
+        M = args.candidates
+    varsigma = go.VARSIGMA_DEFAULT
+    X, y = synthetic_training(N, d)
+    theta = fixed_theta(d)
+
+    # the model object of the public API (GPR == the reference's gpflow_model); rank 0 fits, the others import
+    kernel = gpmodel.Matern52(lengthscales=theta[0], variance=theta[1])
+    model = gpmodel.GPR(data=(X, y), kernel=kernel, mean_function=gpmodel.Constant(theta[3]), noise_variance=theta[2],
+                        backend=backend.CudaBackend(device=local_rank))
+    session = model._session
+    t0 = time.perf_counter()
+    if rank == 0:
+        model._ensure_factor()  # Gram -> Cholesky -> L^-1 -> alpha on rank 0 only
+    factor_ms = (time.perf_counter() - t0) * 1e3
+    broadcast_ms = None
+    scorer = None
+    if world > 1:
+        scorer = ShardedScorer(session)
+        torch.cuda.synchronize()
+        dist.barrier()
+        t0 = time.perf_counter()
+        scorer.broadcast_fit(N, d, src=0)  # one NCCL broadcast of (scaled X, alpha, L^-1, theta) per fit
+        torch.cuda.synchronize()
+        dist.barrier()
+        broadcast_ms = (time.perf_counter() - t0) * 1e3
+        model._factor_key = model._theta().tobytes()
+
+    # this rank's shard of the candidates, in pinned host memory (for the end-to-end leg) and resident in HBM
+    start, stop = shard_bounds(M, world, rank)
+    m_local = stop - start
+    host = torch.empty((max(m_local, 1), d), dtype=torch.float64, pin_memory=True)
+    xc_host = host.numpy()[:m_local]
+    np.random.default_rng([SEED, rank]).random(out=xc_host)
+    xc_dev = host[:m_local].to("cuda", non_blocking=False)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step_device():
+        rec = [-np.inf, -1.0, 0.0, 0.0]
+        if m_local:
+            idx, mean, var, ucb = session.ucb_argmax_dev(xc_dev.data_ptr(), m_local, varsigma, stream)
+            rec = [ucb, float(start + idx), mean, var]
+        return pick_best(gather_records(rec)) if world > 1 else (int(rec[1]), rec[2], rec[3], rec[0])
+
+    def step_e2e():
+        # public API with HOST buffers: H2D of the candidates + D2H of the result inside the call
+        if world > 1:
+            return scorer.ucb_argmax(xc_host, start, varsigma)
+        return model.ucb_argmax(xc_host, varsigma)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident measurement -------------------------------------------------------------------------------
+    for _ in range(args.warmup):
+        result = step_device()
+    session.set_profile(True)
+    sync_all()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = session.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stage_ms = np.zeros(4)
+    windows = 0
+    ev0.record()
+    for _ in range(args.steps):
+        result = step_device()
+        stage_ms += session.last_timing_ms()
+        windows += session.last_windows()
+    ev1.record()
+    sync_all()
+    dev_ms = max_over_ranks(ev0.elapsed_time(ev1))
+    launches = session.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    session.set_profile(False)
+
+    # ---- end-to-end measurement (host buffers through the public API) ------------------------------------------------
+    for _ in range(min(args.warmup, 1)):
+        step_e2e()
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        result_e2e = step_e2e()
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    if world > 1:
+        dist.barrier()
+
+    if rank == 0:
+        assert result_e2e[0] == result[0], "end-to-end and device-resident passes selected different candidates"
+        value = M * args.steps / (dev_ms * 1e-3)
+        e2e_value = M * args.steps / e2e_s
+        trmm_ms = stage_ms[2]
+        flops = float(N) * N * m_local * args.steps  # algorithmic: N^2 per candidate
+        achieved = flops / (trmm_ms * 1e-3) / 1e12 if trmm_ms > 0 else None
+        traffic = None
+        prof_json = os.path.join(ROOT, "profiles", "predict_trmm_traffic.json")
+        if os.path.exists(prof_json):
+            try:
+                traffic = json.load(open(prof_json)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        line = {
+            "metric": "predict_y+UCB candidates/sec", "value": value, "unit": "candidates/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": desc, "N": N, "d": d, "M": M, "kernel": "Matern52", "theta": theta.tolist(),
+                       "varsigma": varsigma, "parallelism": f"candidates sharded over {world} GPU(s)",
+                       "l2": "inputs larger than L2: 80 B/candidate x M candidates in HBM plus a 2 GiB rolling "
+                             "cross-covariance window per GPU vs 126 MB L2"},
+            "e2e": {"value": e2e_value, "unit": "candidates/s", "h2d_bytes_per_step": int(M) * d * 8,
+                    "d2h_bytes_per_step": 32 * world, "ms_per_step": e2e_s / args.steps * 1e3},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {
+                "bound": "tensor", "kernel": "predict_trmm_kernel (FP64 DMMA triangular product + column sum of squares)",
+                "achieved": achieved, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
+                "frac": (achieved / FP64_PEAK_TFLOPS) if achieved else None, "traffic": traffic,
+                "peak_source": "measured DMMA.8x8x4 issue peak on this pool's B200 (profiles/r01_fp64_probe.txt; cuBLAS dgemm "
+                               "8192^3 reaches 36.06); MEASURED_PEAKS.json has no FP64 entry",
+                "launches": int(windows), "avg_launch_ms": trmm_ms / windows if windows else None,
+                "algorithmic_flops_per_launch": flops / windows if windows else None,
+                "whole_step_tflops": float(N) * N * M * args.steps / (dev_ms * 1e-3) / 1e12 / world,
+                "hbm_algorithmic_gbs": (80.0 * M * args.steps / (dev_ms * 1e-3)) / 1e9,
+                "stage_ms_per_step": {"crosscov": stage_ms[1] / args.steps, "trmm": stage_ms[2] / args.steps,
+                                      "finalize": stage_ms[3] / args.steps},
+            },
+            "setup": {"factorize_ms": factor_ms, "broadcast_ms": broadcast_ms, "state_bytes": session.state_bytes(N, d)},
+            "result": {"index": int(result[0]), "mean": result[1], "var": result[2], "ucb": result[3]},
+        }
+        # ---- CPU baseline beside it (bounded sample, rank 0, single GPU runs only) -----------------------------------
+        if world == 1 and not args.no_cpu_baseline:
+            sample = min(M, CPU_SAMPLE)
+            xs = xc_host[:sample]
+            cpu_reference_step(X, y, theta, xs[:256], varsigma)
+            t0 = time.perf_counter()
+            ref = cpu_reference_step(X, y, theta, xs, varsigma)
+            cpu_s = time.perf_counter() - t0
+            cores, blas = blas_threads()
+            # the same sample through the CUDA path must select the same candidate
+            got = session.ucb_argmax(xs, varsigma)
+            line["cpu_baseline"] = {
+                "value": sample / cpu_s, "unit": "candidates/s", "cores": cores, "kind": "port",
+                "sample": f"first {sample} of the {M} candidates, one pass (numpy/scipy restatement of GPflow's predict_y op "
+                          f"sequence incl. the per-call Cholesky; {blas} BLAS, {cores} threads)",
+                "same_argmax_as_gpu": bool(got[0] == ref[0]),
+            }
+        print(json.dumps(line), flush=True)
+    model.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -102,12 +102,16 @@ int gpso_import_state_dev(gpso_handle* h, const void* src_dev, int64_t bytes, in
 /* ---- introspection for benchmarks / tests ---------------------------------------------------------------------- */
 /* kernel launches issued by this handle since creation (our own kernels only; memcpy/memset not counted) */
 int64_t gpso_launch_count(gpso_handle* h);
-/* copy device-side intermediates to the host for parity tests: which = 0 Gram+noise (N*N), 1 L (N*N, lower),
- * 2 L^-1 (N*N, lower), 3 alpha (N), 4 K_y^-1 (N*N, lower; valid after gpso_neg_lml_grad) */
+/* copy device-side intermediates to the host for parity tests: which = 1 L (N*N, lower), 2 L^-1 (N*N, lower),
+ * 3 alpha (N), 4 K_y^-1 (N*N, lower; valid after gpso_neg_lml_grad) */
 int gpso_debug_fetch(gpso_handle* h, int which, double* out_host, int64_t count);
-/* elapsed device time in ms of the last gpso_ucb_argmax_* / gpso_predict_y_* / gpso_neg_lml_grad call, split per stage:
- * out[0]=total, out[1]=cross-covariance generation, out[2]=triangular product+reduction, out[3]=finalise/argmax */
+/* elapsed device time in ms of the last gpso_ucb_argmax_* / gpso_predict_y_* / gpso_neg_lml_grad call (CUDA events on
+ * the launching stream): out[0]=total; with gpso_set_profile(h,1) also the per-stage sums over all windows:
+ * out[1]=cross-covariance generation, out[2]=triangular product + reduction (the dominant kernel, one launch per
+ * window), out[3]=finalise/argmax.  gpso_last_windows = number of windows (= launches of each stage) of that call. */
 int gpso_last_timing(gpso_handle* h, double* out_ms4);
+int gpso_set_profile(gpso_handle* h, int enabled);
+int64_t gpso_last_windows(gpso_handle* h);
 /* tuning knob: candidates per rolling window (0 = automatic) */
 int gpso_set_window(gpso_handle* h, int64_t candidates);
 

@@ -80,6 +80,8 @@ def load_library():
         "gpso_debug_fetch": (i32, [H, i32, _c_double_p, i64]),
         "gpso_last_timing": (i32, [H, _c_double_p]),
         "gpso_set_window": (i32, [H, i64]),
+        "gpso_set_profile": (i32, [H, i32]),
+        "gpso_last_windows": (i64, [H]),
     }
     for name, (restype, argtypes) in protos.items():
         try:
@@ -98,7 +100,8 @@ EXPORTED_SYMBOLS = (
     "gpso_version gpso_last_error gpso_device_count gpso_create gpso_destroy gpso_set_data gpso_neg_lml_grad "
     "gpso_factorize gpso_factor_lml gpso_predict_y_host gpso_predict_y_dev gpso_ucb_argmax_host gpso_ucb_argmax_dev "
     "gpso_grow_count gpso_grow_leaves_host gpso_grow_leaves_dev gpso_grow_ucb_argmax gpso_state_bytes "
-    "gpso_export_state_dev gpso_import_state_dev gpso_launch_count gpso_debug_fetch gpso_last_timing gpso_set_window"
+    "gpso_export_state_dev gpso_import_state_dev gpso_launch_count gpso_debug_fetch gpso_last_timing gpso_set_window "
+    "gpso_set_profile gpso_last_windows"
 ).split()
 
 
@@ -215,6 +218,12 @@ class CudaSession:
         out = np.zeros(4)
         _check(self._lib, self._lib.gpso_last_timing(self._h, _dptr(out)), "gpso_last_timing")
         return out
+
+    def set_profile(self, enabled=True):
+        _check(self._lib, self._lib.gpso_set_profile(self._h, int(bool(enabled))), "gpso_set_profile")
+
+    def last_windows(self):
+        return int(self._lib.gpso_last_windows(self._h))
 
     def set_window(self, candidates):
         _check(self._lib, self._lib.gpso_set_window(self._h, int(candidates)), "gpso_set_window")

@@ -107,6 +107,11 @@ struct gpso_handle {
     double factor_nlml = 0.0;
     long long launches = 0;
     double last_ms[4] = {0, 0, 0, 0};
+    // optional per-stage profiling: 4 events per window on the launch stream
+    bool profile = false;
+    std::vector<cudaEvent_t> prof_events;
+    size_t prof_used = 0;
+    long long last_windows = 0;
     int n_ls() const { return ard ? d : 1; }
     int n_params() const { return n_ls() + 2 + (mean_id == GPSO_MEAN_CONSTANT ? 1 : 0); }
 };
@@ -344,6 +349,7 @@ extern "C" int gpso_destroy(gpso_handle* h) {
     }
     cudaEventDestroy(h->ev_t0);
     cudaEventDestroy(h->ev_t1);
+    for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
     cudaStreamDestroy(h->stream);
     cudaStreamDestroy(h->copy_stream);
     delete h;
@@ -486,10 +492,39 @@ static int ensure_window(gpso_handle* h, long long W) {
     return 0;
 }
 
+static int prof_mark(gpso_handle* h, cudaStream_t st) {
+    if (!h->profile) return 0;
+    if (h->prof_used == h->prof_events.size()) {
+        cudaEvent_t e;
+        CU_TRY(cudaEventCreate(&e));
+        h->prof_events.push_back(e);
+    }
+    CU_TRY(cudaEventRecord(h->prof_events[h->prof_used++], st));
+    return 0;
+}
+
+// sums the per-window stage times recorded by prof_mark (call after the stream has been synchronised)
+static void prof_collect(gpso_handle* h) {
+    h->last_ms[1] = h->last_ms[2] = h->last_ms[3] = 0.0;
+    if (!h->profile) return;
+    for (size_t i = 0; i + 3 < h->prof_used; i += 4) {
+        float a = 0, b = 0, c = 0;
+        cudaEventElapsedTime(&a, h->prof_events[i], h->prof_events[i + 1]);
+        cudaEventElapsedTime(&b, h->prof_events[i + 1], h->prof_events[i + 2]);
+        cudaEventElapsedTime(&c, h->prof_events[i + 2], h->prof_events[i + 3]);
+        h->last_ms[1] += a;
+        h->last_ms[2] += b;
+        h->last_ms[3] += c;
+    }
+    h->prof_used = 0;
+}
+
 // one window, candidates already on the device.  mode 0: mean/var -> out_mean/out_var (device); mode 1: running best
 static int run_window(gpso_handle* h, cudaStream_t st, const double* Xc_dev, long long Mw, long long idx0, int mode,
                       double varsigma, double* out_mean, double* out_var, bool first) {
     long long Mw_pad = ((Mw + TB - 1) / TB) * TB;
+    h->last_windows++;
+    GP_TRY(prof_mark(h, st));
     DISPATCH_KID(h, launch_crosscov, h, st, Xc_dev, Mw, Mw_pad);
     GP_TRY(check_launch(h, "crosscov"));
     PredictParams P;
@@ -502,8 +537,10 @@ static int run_window(gpso_handle* h, cudaStream_t st, const double* Xc_dev, lon
     P.counter = h->counter.as<int>();
     CU_TRY(cudaMemsetAsync(h->counter.p, 0, sizeof(int), st));
     int grid = std::min(h->nsm, P.nct * P.nb);
+    GP_TRY(prof_mark(h, st));
     predict_trmm_kernel<<<grid, GTHREADS, GEMM_SMEM_BYTES, st>>>(P);
     GP_TRY(check_launch(h, "predict_trmm"));
+    GP_TRY(prof_mark(h, st));
     int fb = (int)((Mw + 255) / 256);
     predict_finalize_kernel<<<fb, 256, 0, st>>>(h->part.as<double>(), h->wmean.as<double>(), h->nb, (int)Mw_pad, Mw, idx0,
                                                 h->variance, h->noise, varsigma, mode, out_mean, out_var,
@@ -513,6 +550,7 @@ static int run_window(gpso_handle* h, cudaStream_t st, const double* Xc_dev, lon
         best_merge_kernel<<<1, 256, 0, st>>>(h->blockbest.as<BestRec>(), fb, h->running.as<BestRec>(), first ? 1 : 0);
         GP_TRY(check_launch(h, "best_merge"));
     }
+    GP_TRY(prof_mark(h, st));
     return 0;
 }
 
@@ -520,6 +558,8 @@ static int predict_common_checks(gpso_handle* h, const void* a, long long M, con
     if (!h || !a) return fail(GPSO_E_BADARG, std::string(who) + ": null argument");
     if (M <= 0) return fail(GPSO_E_BADARG, std::string(who) + ": M must be positive");
     if (!h->factorized) return fail(GPSO_E_STATE, std::string(who) + ": call gpso_factorize first");
+    h->prof_used = 0;
+    h->last_windows = 0;
     return set_device(h);
 }
 
@@ -527,6 +567,7 @@ static int fetch_best(gpso_handle* h, cudaStream_t st, double* result_host) {
     BestRec r;
     CU_TRY(cudaMemcpyAsync(&r, h->running.p, sizeof r, cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaStreamSynchronize(st));
+    prof_collect(h);
     result_host[0] = (double)r.idx;
     result_host[1] = r.mean;
     result_host[2] = r.var;
@@ -624,6 +665,7 @@ extern "C" int gpso_predict_y_host(gpso_handle* h, const double* Xc_host, int64_
     if (!mean_host || !var_host) return fail(GPSO_E_BADARG, "gpso_predict_y_host: null output");
     GP_TRY(run_host(h, Xc_host, M, 0, 0.0, mean_host, var_host));
     CU_TRY(cudaStreamSynchronize(h->stream));
+    prof_collect(h);
     float ms = 0;
     cudaEventElapsedTime(&ms, h->ev_t0, h->ev_t1);
     h->last_ms[0] = ms;
@@ -702,6 +744,8 @@ extern "C" int gpso_grow_ucb_argmax(gpso_handle* h, const double* bounds_host, i
                                     double* result_host) {
     if (!h || !bounds_host || !result_host) return fail(GPSO_E_BADARG, "gpso_grow_ucb_argmax: null argument");
     if (!h->factorized) return fail(GPSO_E_STATE, "gpso_grow_ucb_argmax: call gpso_factorize first");
+    h->prof_used = 0;
+    h->last_windows = 0;
     if (d != h->d) return fail(GPSO_E_BADARG, "gpso_grow_ucb_argmax: dimension differs from the training data");
     GP_TRY(set_device(h));
     long long rows = gpso_grow_count(depth);
@@ -814,7 +858,7 @@ extern "C" int gpso_debug_fetch(gpso_handle* h, int which, double* out_host, int
         CU_TRY(cudaMemcpy(out_host, h->alpha.p, sizeof(double) * N, cudaMemcpyDeviceToHost));
         return 0;
     }
-    const DevBuf* src = which == 0 || which == 1 ? &h->K : which == 2 ? &h->Linv : which == 4 ? &h->Kinv : nullptr;
+    const DevBuf* src = which == 1 ? &h->K : which == 2 ? &h->Linv : which == 4 ? &h->Kinv : nullptr;
     if (!src || !src->p) return fail(GPSO_E_BADARG, "gpso_debug_fetch: unknown or unavailable matrix");
     if (count < (int64_t)N * N) return fail(GPSO_E_BADARG, "gpso_debug_fetch: buffer too small");
     CU_TRY(cudaMemcpy2D(out_host, sizeof(double) * N, src->p, sizeof(double) * Np, sizeof(double) * N, N, cudaMemcpyDeviceToHost));
@@ -828,6 +872,14 @@ extern "C" int gpso_last_timing(gpso_handle* h, double* out_ms4) {
     for (int i = 0; i < 4; i++) out_ms4[i] = h->last_ms[i];
     return 0;
 }
+
+extern "C" int gpso_set_profile(gpso_handle* h, int enabled) {
+    if (!h) return fail(GPSO_E_BADARG, "gpso_set_profile: null handle");
+    h->profile = enabled != 0;
+    return 0;
+}
+
+extern "C" int64_t gpso_last_windows(gpso_handle* h) { return h ? h->last_windows : 0; }
 
 extern "C" int gpso_set_window(gpso_handle* h, int64_t candidates) {
     if (!h || candidates < 0) return fail(GPSO_E_BADARG, "gpso_set_window: bad argument");

@@ -1,0 +1,166 @@
+"""
+Multi-GPU sharding of the two axes of the path that shard naturally -- one process per GPU,
+``torch.distributed`` (NCCL over NVLink/NVSwitch on the B200 box, gloo in the CPU tests) for the plumbing:
+
+  1. candidates: rows of the candidate matrix are independent, so rank r scores ``shard_bounds(M, W, r)`` with the fused
+     predict_y + UCB + arg-max kernel locally.  One exchange per *fit*: the fitting rank broadcasts its state (scaled
+     inputs, alpha, L^-1, hyper-parameters) as ONE contiguous buffer (``gpso_export_state_dev`` -> NCCL broadcast ->
+     ``gpso_import_state_dev``).  One exchange per *scoring call*: an all-gather of a 32-byte record
+     (ucb, global index, mean, var) per rank; every rank then picks the winner with numpy's arg-max rule (first NaN,
+     else the largest UCB, lowest global index on ties), which is exactly what a single GPU / the reference returns.
+  2. multi-start restarts of the hyper-parameter fit: restart i runs on rank i mod W (independent L-BFGS-B runs),
+     followed by an all-gather of (-LML*, u*); the winner is the smallest -LML, lowest restart id on ties.
+
+Nothing here does arithmetic on candidates or Gram matrices; it only partitions, exchanges and selects.
+"""
+import numpy as np
+import scipy.optimize
+
+RECORD_LEN = 4  # ucb, global index, mean, var
+
+
+def shard_bounds(total, world_size, rank):
+    """Contiguous shard [start, stop) of ``total`` items for ``rank``; the first ``total % world_size`` ranks get one more."""
+    base, extra = divmod(int(total), int(world_size))
+    start = rank * base + min(rank, extra)
+    return start, start + base + (1 if rank < extra else 0)
+
+
+def pick_best(records):
+    """
+    Winner among per-shard records ``[[ucb, global_idx, mean, var], ...]`` with np.argmax semantics over the
+    concatenated candidate list: the first NaN if any, else the largest UCB, the lowest global index on ties.
+    Records of empty shards carry ``global_idx < 0`` and are skipped.  Returns (global_idx, mean, var, ucb).
+    """
+    best = None
+    for ucb, gidx, mean, var in np.asarray(records, dtype=np.float64).reshape(-1, RECORD_LEN):
+        if gidx < 0:
+            continue
+        cand = (float(ucb), int(gidx), float(mean), float(var))
+        if best is None:
+            best = cand
+            continue
+        cn, bn = np.isnan(cand[0]), np.isnan(best[0])
+        if cn or bn:
+            better = (cn and not bn) or (cn and bn and cand[1] < best[1])
+        else:
+            better = cand[0] > best[0] or (cand[0] == best[0] and cand[1] < best[1])
+        if better:
+            best = cand
+    if best is None:
+        raise ValueError("no candidates in any shard")
+    return best[1], best[2], best[3], best[0]
+
+
+def _dist():
+    import torch.distributed as dist
+
+    return dist
+
+
+def _comm_device(group=None):
+    """Device on which collective buffers must live: CUDA for NCCL, CPU for gloo."""
+    import torch
+
+    dist = _dist()
+    if dist.get_backend(group) == "nccl":
+        return torch.device("cuda", torch.cuda.current_device())
+    return torch.device("cpu")
+
+
+def gather_records(record, group=None):
+    """All-gather one RECORD_LEN-double record per rank; returns an array [world, RECORD_LEN] on every rank."""
+    import torch
+
+    dist = _dist()
+    world = dist.get_world_size(group)
+    dev = _comm_device(group)
+    mine = torch.tensor(np.asarray(record, dtype=np.float64), dtype=torch.float64, device=dev)
+    parts = [torch.empty(RECORD_LEN, dtype=torch.float64, device=dev) for _ in range(world)]
+    dist.all_gather(parts, mine, group=group)
+    return torch.stack(parts).cpu().numpy()
+
+
+class ShardedScorer:
+    """
+    Candidate-sharded ``gp_eval_best_ucb``.  ``session`` is this rank's device session (``model._session``); any object
+    with ``ucb_argmax(X, varsigma) -> (idx, mean, var, ucb)`` works, which is how the gloo test drives it on CPU.
+    """
+
+    def __init__(self, session, group=None):
+        self.session = session
+        self.group = group
+        dist = _dist()
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+
+    # -- one exchange per fit -----------------------------------------------------------------------------------------
+    def broadcast_fit(self, n, d, src=0):
+        """Broadcast the fitted state of rank ``src`` to every rank's session (NCCL, one contiguous buffer)."""
+        import torch
+
+        dist = _dist()
+        nbytes = self.session.state_bytes(n, d)
+        buf = torch.empty(nbytes, dtype=torch.uint8, device=_comm_device(self.group))
+        stream = torch.cuda.current_stream().cuda_stream
+        if self.rank == src:
+            self.session.export_state_dev(buf.data_ptr(), nbytes, stream)
+        dist.broadcast(buf, src=src, group=self.group)
+        if self.rank != src:
+            torch.cuda.current_stream().synchronize()
+            self.session.import_state_dev(buf.data_ptr(), nbytes, n, d, stream)
+        return nbytes
+
+    # -- one exchange per scoring call --------------------------------------------------------------------------------
+    def local_record(self, x_local, global_offset, varsigma):
+        if len(x_local) == 0:
+            return [-np.inf, -1.0, 0.0, 0.0]
+        idx, mean, var, ucb = self.session.ucb_argmax(x_local, varsigma)
+        return [ucb, float(global_offset + idx), mean, var]
+
+    def ucb_argmax(self, x_local, global_offset, varsigma):
+        """Score this rank's shard (rows ``global_offset ...`` of the full candidate list) and agree on the winner."""
+        records = gather_records(self.local_record(x_local, global_offset, varsigma), self.group)
+        return pick_best(records)
+
+    def ucb_argmax_full(self, x_all, varsigma):
+        """Convenience: every rank holds the full candidate matrix and scores only its own contiguous shard."""
+        start, stop = shard_bounds(len(x_all), self.world, self.rank)
+        return self.ucb_argmax(x_all[start:stop], start, varsigma)
+
+
+def restart_points(u0, n_restarts, seed=20240517):
+    """Restart 0 is the warm start ``u0``; restart i > 0 is ``u0 + N(0, 1)`` in unconstrained space."""
+    rng = np.random.default_rng(seed)
+    starts = [np.array(u0, dtype=np.float64)]
+    for _ in range(1, n_restarts):
+        starts.append(u0 + rng.normal(0.0, 1.0, size=len(u0)))
+    return starts
+
+
+def sharded_multistart_fit(objective, u0, n_restarts, group=None, seed=20240517, maxiter=50, on_error=np.inf):
+    """
+    Multi-start L-BFGS-B with the restarts dealt round-robin over the ranks.  ``objective(u) -> (f, grad)`` is this
+    rank's device closure (``model.neg_log_marginal_likelihood_and_grad``).  Returns (u_best, f_best, restart_id, table)
+    identically on every rank; ``table[i] = (f_i, restart i's optimum)``.
+    """
+    import torch
+
+    dist = _dist()
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    starts = restart_points(u0, n_restarts, seed)
+    p = len(u0)
+    mine = np.full((n_restarts, p + 1), np.nan)
+    for i in range(rank, n_restarts, world):
+        try:
+            res = scipy.optimize.minimize(objective, starts[i], jac=True, method="L-BFGS-B", options={"maxiter": maxiter})
+            mine[i, 0], mine[i, 1:] = res.fun, res.x
+        except np.linalg.LinAlgError:
+            mine[i, 0], mine[i, 1:] = on_error, starts[i]
+    dev = _comm_device(group)
+    local = torch.tensor(np.nan_to_num(mine, nan=0.0), dtype=torch.float64, device=dev)
+    dist.all_reduce(local, op=dist.ReduceOp.SUM, group=group)  # each row is non-zero on exactly one rank
+    table = local.cpu().numpy()
+    f = table[:, 0]
+    best = int(np.argmin(f))  # first minimum = lowest restart id on ties
+    return table[best, 1:].copy(), float(f[best]), best, table

@@ -1,0 +1,111 @@
+"""
+World-size-2 test of the sharding logic on CPU (gloo): candidate shards + record gather + winner selection, and the
+multi-start restart sharding.  The per-rank scorer is the oracle session (explicitly injected); the collectives and
+the selection rule are the product code in pygpso_b200/distributed.py.
+"""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch.multiprocessing as mp
+
+from pygpso_b200.distributed import pick_best, restart_points, shard_bounds
+
+
+def test_shard_bounds_cover_and_are_contiguous():
+    for total in (0, 1, 7, 8, 1000, 10_000_001):
+        for world in (1, 2, 3, 8):
+            pieces = [shard_bounds(total, world, r) for r in range(world)]
+            assert pieces[0][0] == 0 and pieces[-1][1] == total
+            assert all(pieces[i][1] == pieces[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in pieces]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_pick_best_numpy_argmax_semantics():
+    recs = [[1.0, 5, 0.1, 0.2], [3.0, 9, 0.3, 0.4], [3.0, 2, 0.5, 0.6], [-np.inf, -1, 0, 0]]
+    assert pick_best(recs) == (2, 0.5, 0.6, 3.0)  # tie -> lowest global index
+    recs.append([np.nan, 40, 0.0, 0.0])
+    recs.append([np.nan, 30, 1.0, 2.0])
+    got = pick_best(recs)
+    assert got[0] == 30 and np.isnan(got[3])  # first NaN wins
+    with pytest.raises(ValueError):
+        pick_best([[-np.inf, -1, 0, 0]])
+
+
+def test_restart_points_are_reproducible():
+    u0 = np.array([0.1, -0.2, 0.3])
+    a, b = restart_points(u0, 5), restart_points(u0, 5)
+    assert np.array_equal(a[0], u0) and all(np.array_equal(x, y) for x, y in zip(a, b))
+    assert not np.array_equal(a[1], a[2])
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out_dir):
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import torch.distributed as dist
+
+    from oracle import gpr_oracle as go
+    from pygpso_b200.distributed import ShardedScorer, sharded_multistart_fit
+    from tests.oracle_backend import OracleSession
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(0)
+        X = rng.random((30, 2))
+        y = np.sin(3 * X.sum(1))[:, None]
+        sess = OracleSession("Matern52", 1, True)
+        sess.set_data(X, y)
+        sess.factorize(np.array([0.3, 1.0, 1e-3, 0.0]))
+        Xc = rng.random((1001, 2))
+        Xc[700] = Xc[100]  # an exact duplicate in the other shard: the lower index must win a tie
+        scorer = ShardedScorer(sess)
+        got = scorer.ucb_argmax_full(Xc, go.VARSIGMA_DEFAULT)
+        mean, var = go.predict_y("Matern52", X, y, sess.h, Xc)
+        want = go.ucb_argmax(mean, var)
+        # force the duplicate pair to be the winner as well
+        Xd = np.vstack([Xc, Xc[want[0]][None, :]])
+        got_dup = scorer.ucb_argmax_full(Xd, go.VARSIGMA_DEFAULT)
+        # ragged: fewer candidates than ranks
+        got_one = scorer.ucb_argmax_full(Xc[:1], go.VARSIGMA_DEFAULT)
+
+        model = go.OracleGPR(X, y, "Matern52", 0.25, 1.0, 1e-3, 0.0)
+        u_best, f_best, rid, table = sharded_multistart_fit(model.training_loss, model.h.pack(), 5, maxiter=30)
+        np.save(os.path.join(out_dir, f"r{rank}.npy"),
+                np.array([*got, *want, *got_dup, *got_one, f_best, rid, *u_best, *table[:, 0]], dtype=np.float64))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world_size_2_gloo(tmp_path):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    r0 = np.load(tmp_path / "r0.npy")
+    r1 = np.load(tmp_path / "r1.npy")
+    assert np.array_equal(r0, r1)  # every rank agrees bit for bit
+    got, want, got_dup, got_one = r0[0:4], r0[4:8], r0[8:12], r0[12:16]
+    assert got[0] == want[0] and got[1] == want[1] and got[2] == want[2] and got[3] == want[3]
+    assert got_dup[0] == want[0]  # duplicate appended at the end loses the tie to the earlier row
+    assert got_one[0] == 0
+    f_best, rid, fs = r0[16], int(r0[17]), r0[22:27]
+    assert f_best == fs.min() and rid == int(np.argmin(fs)) and np.all(np.isfinite(fs))
+    # restart 0 (the warm start) must reproduce the single-process fit
+    import sys
+
+    from oracle import gpr_oracle as go
+
+    rng = np.random.default_rng(0)
+    X = rng.random((30, 2))
+    y = np.sin(3 * X.sum(1))[:, None]
+    single = go.OracleGPR(X, y, "Matern52", 0.25, 1.0, 1e-3, 0.0).fit(options={"maxiter": 30})
+    assert fs[0] == pytest.approx(single.fun, rel=1e-12)
