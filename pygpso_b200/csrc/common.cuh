@@ -14,6 +14,10 @@ constexpr int KERNEL_SE = 3;
 constexpr int TB = 128;           // tile / panel edge: every dense matrix is padded to a multiple of TB
 constexpr double R2_CLIP = 1e-36; // GPflow clips the scaled squared distance before the sqrt (Matern kernels)
 
+// tf.maximum(r2, 1e-36) propagates NaN (a NaN input must reach the Cholesky and be reported, not be clipped away);
+// fmax() would return the non-NaN operand
+__device__ __forceinline__ double clip_r2(double r2) { return (r2 < R2_CLIP) ? R2_CLIP : r2; }
+
 // ---- FP64 tensor op: D(8x8) = A(8x4) * B(4x8) + C.  SASS: DMMA.8x8x4 -------------------------------------------
 // fragment layout (g = lane>>2, t = lane&3):  a = A[g][t],  b = B[t][g],  c0 = C[g][2t], c1 = C[g][2t+1]
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
@@ -40,7 +44,7 @@ __device__ __forceinline__ double cov_from_r2(double r2, double var) {
     if (KID == KERNEL_SE) {
         return var * exp(-0.5 * r2);
     } else {
-        double r = sqrt(fmax(r2, R2_CLIP));
+        double r = sqrt(clip_r2(r2));
         if (KID == KERNEL_MATERN52) {
             const double s5 = 2.23606797749978969641;
             double sr = s5 * r;
@@ -65,7 +69,7 @@ __device__ __forceinline__ void cov_and_radial(double r2, double var, double& k,
         g = k;
     } else {
         bool live = r2 > R2_CLIP;
-        double r = sqrt(fmax(r2, R2_CLIP));
+        double r = sqrt(clip_r2(r2));
         if (KID == KERNEL_MATERN52) {
             const double s5 = 2.23606797749978969641;
             double sr = s5 * r;

@@ -48,9 +48,9 @@ def theta_of(h):
     return np.array(t)
 
 
-def assert_predict_close(mean, var, mean_ref, var_ref, y, variance):
-    mtol = 1e-8 * np.maximum(np.abs(mean_ref), np.abs(y).max())
-    vtol = 1e-8 * np.maximum(np.abs(var_ref), variance)
+def assert_predict_close(mean, var, mean_ref, var_ref, y, variance, rel=1e-8):
+    mtol = rel * np.maximum(np.abs(mean_ref), np.abs(y).max())
+    vtol = rel * np.maximum(np.abs(var_ref), variance)
     assert np.all(np.abs(mean - mean_ref) <= mtol), float(np.max(np.abs(mean - mean_ref) / mtol))
     assert np.all(np.abs(var - var_ref) <= vtol), float(np.max(np.abs(var - var_ref) / vtol))
 
@@ -164,7 +164,11 @@ def test_predict_other_kernels_ard(cuda, kernel):
     s = open_session(cuda, kernel, X, y, n_ls=3, has_mean=False)
     s.factorize(theta_of(h))
     mean, var = s.predict_y(Xc)
-    assert_predict_close(mean, var, mean_ref[:, 0], var_ref[:, 0], y, h.variance)
+    # Matern12 is not differentiable at r = 0: GPflow's |x|^2+|x'|^2-2x.x' distance (restated by the oracle) leaves
+    # ~1e-16 rounding noise on the Gram diagonal, i.e. r_ii ~ 1e-8 and k_ii = variance*(1 - 1e-8), while the CUDA kernels
+    # take coordinate differences first and get r_ii = 0 exactly.  Two evaluations of GPflow's own formula differ at
+    # this level for Matern12 (same note as in test_neg_lml_and_grad); the smooth kernels keep 1e-8.
+    assert_predict_close(mean, var, mean_ref[:, 0], var_ref[:, 0], y, h.variance, rel=1e-7 if kernel == "Matern12" else 1e-8)
     s.close()
 
 
