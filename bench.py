@@ -152,6 +152,9 @@ def main():
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--candidates", type=int, default=0, help="override the number of candidates (smoke runs only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--engine", default="auto", choices=["auto", "dmma", "int8"],
+                    help="variance-product engine: FP64 DMMA or the exact-integer int8 tcgen05 emulation (auto picks int8 at this size)")
+    ap.add_argument("--slices", type=int, default=0, help="8-bit digits per operand for the int8 engine (0 = automatic)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -188,6 +191,7 @@ def main():
     model = gpmodel.GPR(data=(X, y), kernel=kernel, mean_function=gpmodel.Constant(theta[3]), noise_variance=theta[2],
                         backend=backend.CudaBackend(device=local_rank))
     session = model._session
+    session.set_predict_mode({"auto": 0, "dmma": 1, "int8": 2}[args.engine], args.slices)
     t0 = time.perf_counter()
     if rank == 0:
         model._ensure_factor()  # Gram -> Cholesky -> L^-1 -> alpha on rank 0 only

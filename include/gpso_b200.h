@@ -112,6 +112,18 @@ int gpso_debug_fetch(gpso_handle* h, int which, double* out_host, int64_t count)
 int gpso_last_timing(gpso_handle* h, double* out_ms4);
 int gpso_set_profile(gpso_handle* h, int enabled);
 int64_t gpso_last_windows(gpso_handle* h);
+/* Engine of the variance product V = L^-1 k* inside predict_y / ucb_argmax (takes effect at the next gpso_factorize):
+ *   mode 0 automatic (int8 when the padded N >= 512), 1 = FP64 DMMA (mma.sync m8n8k4.f64), 2 = exact-integer emulation
+ *   of the fp64 product on the int8 tensor cores (tcgen05.mma kind::i8, accumulators in TMEM).
+ *   slices: 8-bit digits per operand for mode 2, 5..8, or 0 = chosen per fit from the row scales of L^-1 so that the
+ *   estimated error stays below 2% of the parity tolerance 1e-8 * kernel variance. */
+int gpso_set_predict_mode(gpso_handle* h, int mode, int slices);
+/* out[0] = engine in force after the last gpso_factorize (1 or 2), out[1] = digits per operand (0 for engine 1),
+ * out[2] = estimated error of the variance / parity tolerance for that choice */
+int gpso_predict_info(gpso_handle* h, double* out3);
+/* int8 engine only: overlap the cross-covariance of window w+1 (FP64 CUDA cores, side stream) with the tensor-core
+ * product of window w (default on; results are bit-identical either way) */
+int gpso_set_overlap(gpso_handle* h, int enabled);
 /* tuning knob: candidates per rolling window (0 = automatic) */
 int gpso_set_window(gpso_handle* h, int64_t candidates);
 

@@ -80,6 +80,9 @@ def load_library():
         "gpso_debug_fetch": (i32, [H, i32, _c_double_p, i64]),
         "gpso_last_timing": (i32, [H, _c_double_p]),
         "gpso_set_window": (i32, [H, i64]),
+        "gpso_set_predict_mode": (i32, [H, i32, i32]),
+        "gpso_predict_info": (i32, [H, _c_double_p]),
+        "gpso_set_overlap": (i32, [H, i32]),
         "gpso_set_profile": (i32, [H, i32]),
         "gpso_last_windows": (i64, [H]),
     }
@@ -101,7 +104,7 @@ EXPORTED_SYMBOLS = (
     "gpso_factorize gpso_factor_lml gpso_predict_y_host gpso_predict_y_dev gpso_ucb_argmax_host gpso_ucb_argmax_dev "
     "gpso_grow_count gpso_grow_leaves_host gpso_grow_leaves_dev gpso_grow_ucb_argmax gpso_state_bytes "
     "gpso_export_state_dev gpso_import_state_dev gpso_launch_count gpso_debug_fetch gpso_last_timing gpso_set_window "
-    "gpso_set_profile gpso_last_windows"
+    "gpso_set_profile gpso_last_windows gpso_set_predict_mode gpso_predict_info gpso_set_overlap"
 ).split()
 
 
@@ -224,6 +227,18 @@ class CudaSession:
 
     def last_windows(self):
         return int(self._lib.gpso_last_windows(self._h))
+
+    def set_predict_mode(self, mode=0, slices=0):
+        """0 automatic, 1 FP64 DMMA, 2 int8 tcgen05 (``slices`` 8-bit digits per operand, 0 = automatic)."""
+        _check(self._lib, self._lib.gpso_set_predict_mode(self._h, int(mode), int(slices)), "gpso_set_predict_mode")
+
+    def set_overlap(self, enabled=True):
+        _check(self._lib, self._lib.gpso_set_overlap(self._h, int(bool(enabled))), "gpso_set_overlap")
+
+    def predict_info(self):
+        out = np.zeros(3)
+        _check(self._lib, self._lib.gpso_predict_info(self._h, _dptr(out)), "gpso_predict_info")
+        return {"engine": "int8-tcgen05" if out[0] == 2 else "fp64-dmma", "slices": int(out[1]), "error_estimate_over_tol": float(out[2])}
 
     def set_window(self, candidates):
         _check(self._lib, self._lib.gpso_set_window(self._h, int(candidates)), "gpso_set_window")

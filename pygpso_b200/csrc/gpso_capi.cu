@@ -20,6 +20,7 @@
 #include "kern_cov.cuh"
 #include "kern_dense.cuh"
 #include "kern_leaves.cuh"
+#include "kern_ozaki.cuh"
 #include "kern_predict.cuh"
 
 using namespace gpso;
@@ -52,6 +53,10 @@ namespace {
 constexpr int MAX_LS = LEAF_MAXD;  // maximum input dimension supported
 constexpr double NOISE_FLOOR = 1.0e-6;
 constexpr long long WINDOW_BYTES = 2LL << 30;  // rolling cross-covariance window budget (2 GiB)
+constexpr int OZ_XCOV_SMEM_MAX = 112 * 1024;   // crosscov_slices_kernel dynamic shared memory at d = 64
+constexpr int OZ_MIN_NP = 512;                 // below this the int8 path is not worth its fixed costs (automatic mode)
+constexpr int OZ_MAX_NP = 16384;               // int32 accumulators stay exact: S * 2^14 * Np < 2^31
+constexpr double OZ_TARGET = 0.02;             // accepted (estimated error) / (parity tolerance 1e-8 * variance)
 
 struct DevBuf {
     void* p = nullptr;
@@ -99,7 +104,16 @@ struct gpso_handle {
     DevBuf K, Linv, LinvT, T, Kinv;
     DevBuf resid, a, logdet, scalars, gpart, gout, info, counter;
     // predict workspaces
-    DevBuf KsT, part, wmean, blockbest, running, cand[2], leaves, omean, ovar;
+    DevBuf KsT, part, blockbest, running, cand[2], leaves, omean, ovar;
+    // int8 tensor-core (tcgen05) variance product: digit tiles of L^-1 and of the cross-covariance window
+    DevBuf ozA, ozBb[2], wmeanb[2], rowscale, rowmax;
+    cudaStream_t aux_stream = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_xcov[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+    int overlap = 1;
+    int predict_mode = 0;   // 0 = automatic, 1 = FP64 DMMA product, 2 = int8 tcgen05 product
+    int oz_force_slices = 0;
+    int oz_S = 0;           // digits per operand chosen at the last factorisation (0: DMMA path in force)
+    double oz_est = 0.0;    // error estimate / tolerance for the chosen S
     long long window_override = 0;
     // host copies of the hyper-parameters in force
     double ls_host[MAX_LS] = {0}, variance = 1.0, noise = 1.0, c0 = 0.0;
@@ -111,6 +125,9 @@ struct gpso_handle {
     bool profile = false;
     std::vector<cudaEvent_t> prof_events;
     size_t prof_used = 0;
+    // always on: one event pair around every variance-product launch (its summed duration is last_ms[2])
+    std::vector<cudaEvent_t> prod_events;
+    size_t prod_used = 0;
     long long last_windows = 0;
     int n_ls() const { return ard ? d : 1; }
     int n_params() const { return n_ls() + 2 + (mean_id == GPSO_MEAN_CONSTANT ? 1 : 0); }
@@ -146,8 +163,70 @@ static void launch_crosscov(gpso_handle* h, cudaStream_t st, const double* Xc, l
     size_t sm = (size_t)(XG * h->d + 8 * XG) * sizeof(double);
     crosscov_kernel<KID><<<(unsigned)(Mw_pad / XG), 256, sm, st>>>(Xc, Mw, h->d, h->ls.as<double>(), h->n_ls(), h->Xs.as<double>(),
                                                                   h->alpha.as<double>(), h->N, h->Np, h->variance, h->c0,
-                                                                  h->KsT.as<double>(), h->wmean.as<double>());
+                                                                  h->KsT.as<double>(), h->wmeanb[0].as<double>());
 }
+
+template <int S>
+static int oz_configure() {
+    CU_TRY(cudaFuncSetAttribute(ozaki_trmm_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, OzCfg<S>::SMEM_BYTES));
+    CU_TRY(cudaFuncSetAttribute(crosscov_slices_kernel<KERNEL_MATERN12, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_XCOV_SMEM_MAX));
+    CU_TRY(cudaFuncSetAttribute(crosscov_slices_kernel<KERNEL_MATERN32, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_XCOV_SMEM_MAX));
+    CU_TRY(cudaFuncSetAttribute(crosscov_slices_kernel<KERNEL_MATERN52, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_XCOV_SMEM_MAX));
+    CU_TRY(cudaFuncSetAttribute(crosscov_slices_kernel<KERNEL_SE, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_XCOV_SMEM_MAX));
+    return 0;
+}
+
+static size_t oz_xcov_smem(int d) { return (size_t)(OZ_NT * (d | 1) + 2 * d * 64 + 2 * 64 + 4 * 64) * sizeof(double); }
+
+template <int KID, int S>
+static void launch_oz_crosscov(gpso_handle* h, cudaStream_t st, const double* Xc, long long Mw, long long nct, double bscale,
+                               uint8_t* B, double* wmean) {
+    crosscov_slices_kernel<KID, S><<<(unsigned)nct, 256, oz_xcov_smem(h->d), st>>>(
+        Xc, Mw, h->d, h->ls.as<double>(), h->n_ls(), h->Xs.as<double>(), h->alpha.as<double>(), h->N, h->Np, h->variance, h->c0, bscale,
+        h->Np / 32, B, wmean);
+}
+
+template <int S>
+static void launch_oz_crosscov_s(gpso_handle* h, cudaStream_t st, const double* Xc, long long Mw, long long nct, double bscale,
+                                 uint8_t* B, double* wmean) {
+    switch (h->kernel_id) {
+        case KERNEL_MATERN12: launch_oz_crosscov<KERNEL_MATERN12, S>(h, st, Xc, Mw, nct, bscale, B, wmean); break;
+        case KERNEL_MATERN32: launch_oz_crosscov<KERNEL_MATERN32, S>(h, st, Xc, Mw, nct, bscale, B, wmean); break;
+        case KERNEL_MATERN52: launch_oz_crosscov<KERNEL_MATERN52, S>(h, st, Xc, Mw, nct, bscale, B, wmean); break;
+        default: launch_oz_crosscov<KERNEL_SE, S>(h, st, Xc, Mw, nct, bscale, B, wmean); break;
+    }
+}
+
+template <int S>
+static void launch_oz_trmm(gpso_handle* h, cudaStream_t st, long long nct, long long ldp, double gscale, const uint8_t* B) {
+    OzParams P;
+    P.A = h->ozA.as<uint8_t>();
+    P.B = B;
+    P.rowscale = h->rowscale.as<double>();
+    P.part = h->part.as<double>();
+    P.gscale = gscale;
+    P.nb = h->nb;
+    P.nks = h->Np / 32;
+    P.nct = (int)nct;
+    P.ldp = ldp;
+    long long units = nct * ((h->nb + 1) / 2);
+    int grid = (int)std::min<long long>(h->nsm, units);
+    ozaki_trmm_kernel<S><<<grid, OZ_THREADS, OzCfg<S>::SMEM_BYTES, st>>>(P);
+}
+
+template <int S>
+static void launch_oz_slices(gpso_handle* h, cudaStream_t st) {
+    dim3 grid(h->Np / 32, h->nb);
+    linv_slices_kernel<S><<<grid, 256, 0, st>>>(h->Linv.as<double>(), h->rowscale.as<double>(), h->Np, h->Np / 32, h->ozA.as<uint8_t>());
+}
+
+#define DISPATCH_S(S_, fn, ...)                \
+    switch (S_) {                              \
+        case 5: fn<5>(__VA_ARGS__); break;     \
+        case 6: fn<6>(__VA_ARGS__); break;     \
+        case 7: fn<7>(__VA_ARGS__); break;     \
+        default: fn<8>(__VA_ARGS__); break;    \
+    }
 
 template <int KID>
 static void launch_grad(gpso_handle* h, cudaStream_t st, int nblk, int stride) {
@@ -182,6 +261,10 @@ static int configure_kernels() {
     CU_TRY(cudaFuncSetAttribute(dense_gemm_kernel<MODE_LAUUM>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     CU_TRY(cudaFuncSetAttribute(predict_trmm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     CU_TRY(cudaFuncSetAttribute(diag_factor_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM_BYTES));
+    GP_TRY(oz_configure<5>());
+    GP_TRY(oz_configure<6>());
+    GP_TRY(oz_configure<7>());
+    GP_TRY(oz_configure<8>());
     return 0;
 }
 
@@ -286,6 +369,60 @@ static double nlml_from_scalars(const gpso_handle* h, const double* sc) {
     return 0.5 * sc[0] + 0.5 * h->N * log(2.0 * M_PI) + sc[1];
 }
 
+// Digits per operand for the int8 product.  Error model (kern_ozaki.cuh): the fixed-point rounding of both operands
+// and the neglected digit-pair levels give  std(dV_i) ~ 3 * rho_i * beta * 2^(-8S) * sqrt(N)  (rho_i = row scale of
+// L^-1, beta = scale of k*), hence  |d(sum V^2)| <~ 6 * sigma_f * beta * 2^(-8S) * sqrt(N) * max_i rho_i.  The parity
+// tolerance of the posterior variance is 1e-8 * kernel variance; S is the smallest digit count whose estimate is below
+// OZ_TARGET of it.
+static int pick_slices(const gpso_handle* h, double rho_max, double beta, double* est_out) {
+    const double sigma_f = sqrt(h->variance);
+    const double tol = 1.0e-8 * h->variance;
+    for (int S = 5; S <= 8; S++) {
+        double est = 6.0 * sigma_f * beta * ldexp(1.0, -8 * S) * sqrt((double)h->N) * rho_max / tol;
+        if (est <= OZ_TARGET || S == 8) {
+            *est_out = est;
+            return S;
+        }
+    }
+    return 8;
+}
+
+static double oz_beta(const gpso_handle* h) {  // 2^f with kernel variance < 2^f: k* / 2^f in [0, 1)
+    return ldexp(1.0, ilogb(h->variance) + 1);
+}
+
+// After L^-1 is known: decide whether the int8 tensor-core product is used for this fit and build its A digit tiles.
+static int prepare_ozaki(gpso_handle* h, cudaStream_t st) {
+    h->oz_S = 0;
+    h->oz_est = 0.0;
+    bool want = h->predict_mode == 2 || (h->predict_mode == 0 && h->Np >= OZ_MIN_NP);
+    if (!want || h->Np > OZ_MAX_NP) return 0;
+    const int Np = h->Np;
+    GP_TRY(h->rowscale.ensure((size_t)Np * sizeof(double)));
+    GP_TRY(h->rowmax.ensure((size_t)Np * sizeof(double)));
+    linv_rowscale_kernel<<<(Np + 7) / 8, 256, 0, st>>>(h->Linv.as<double>(), Np, h->rowscale.as<double>(), h->rowmax.as<double>());
+    GP_TRY(check_launch(h, "linv_rowscale"));
+    std::vector<double> rs(Np);
+    CU_TRY(cudaMemcpyAsync(rs.data(), h->rowscale.p, sizeof(double) * Np, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    double rho_max = 0.0;
+    for (int i = 0; i < h->N; i++) rho_max = std::max(rho_max, rs[i]);
+    if (!(rho_max > 0.0) || !std::isfinite(rho_max)) return 0;  // degenerate factor: stay on the FP64 path
+    double est = 0.0;
+    int S = h->oz_force_slices ? h->oz_force_slices : pick_slices(h, rho_max, oz_beta(h), &est);
+    if (h->oz_force_slices) {
+        double e2 = 0.0;
+        pick_slices(h, rho_max, oz_beta(h), &e2);
+        est = 6.0 * sqrt(h->variance) * oz_beta(h) * ldexp(1.0, -8 * S) * sqrt((double)h->N) * rho_max / (1.0e-8 * h->variance);
+    }
+    GP_TRY(h->ozA.ensure((size_t)Np * Np * S));
+    DISPATCH_S(S, launch_oz_slices, h, st);
+    GP_TRY(check_launch(h, "linv_slices"));
+    h->oz_S = S;
+    h->oz_est = est;
+    return 0;
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // library
 // ---------------------------------------------------------------------------------------------------------------------
@@ -323,9 +460,13 @@ extern "C" int gpso_create(int device, int kernel_id, int ard, int mean_id, gpso
     h->nsm = prop.multiProcessorCount;
     CU_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CU_TRY(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    CU_TRY(cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
+    CU_TRY(cudaEventCreateWithFlags(&h->ev_start, cudaEventDisableTiming));
     for (int i = 0; i < 2; i++) {
         CU_TRY(cudaEventCreateWithFlags(&h->ev_copy[i], cudaEventDisableTiming));
         CU_TRY(cudaEventCreateWithFlags(&h->ev_used[i], cudaEventDisableTiming));
+        CU_TRY(cudaEventCreateWithFlags(&h->ev_xcov[i], cudaEventDisableTiming));
+        CU_TRY(cudaEventCreateWithFlags(&h->ev_free[i], cudaEventDisableTiming));
     }
     CU_TRY(cudaEventCreate(&h->ev_t0));
     CU_TRY(cudaEventCreate(&h->ev_t1));
@@ -340,16 +481,23 @@ extern "C" int gpso_destroy(gpso_handle* h) {
     cudaStreamSynchronize(h->stream);
     cudaStreamSynchronize(h->copy_stream);
     DevBuf* bufs[] = {&h->X, &h->y, &h->Xs, &h->ls, &h->alpha, &h->K, &h->Linv, &h->LinvT, &h->T, &h->Kinv, &h->resid, &h->a,
-                      &h->logdet, &h->scalars, &h->gpart, &h->gout, &h->info, &h->counter, &h->KsT, &h->part, &h->wmean,
-                      &h->blockbest, &h->running, &h->cand[0], &h->cand[1], &h->leaves, &h->omean, &h->ovar};
+                      &h->logdet, &h->scalars, &h->gpart, &h->gout, &h->info, &h->counter, &h->KsT, &h->part,
+                      &h->blockbest, &h->running, &h->cand[0], &h->cand[1], &h->leaves, &h->omean, &h->ovar,
+                      &h->ozA, &h->ozBb[0], &h->ozBb[1], &h->wmeanb[0], &h->wmeanb[1], &h->rowscale, &h->rowmax};
     for (DevBuf* b : bufs) b->release();
+    cudaStreamSynchronize(h->aux_stream);
     for (int i = 0; i < 2; i++) {
         cudaEventDestroy(h->ev_copy[i]);
         cudaEventDestroy(h->ev_used[i]);
+        cudaEventDestroy(h->ev_xcov[i]);
+        cudaEventDestroy(h->ev_free[i]);
     }
+    cudaEventDestroy(h->ev_start);
+    cudaStreamDestroy(h->aux_stream);
     cudaEventDestroy(h->ev_t0);
     cudaEventDestroy(h->ev_t1);
     for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->prod_events) cudaEventDestroy(e);
     cudaStreamDestroy(h->stream);
     cudaStreamDestroy(h->copy_stream);
     delete h;
@@ -462,6 +610,7 @@ extern "C" int gpso_factorize(gpso_handle* h, const double* theta_host, int p) {
         return info;
     }
     h->factor_nlml = nlml_from_scalars(h, sc);
+    GP_TRY(prepare_ozaki(h, st));
     h->factorized = true;
     return 0;
 }
@@ -478,18 +627,11 @@ extern "C" int gpso_factor_lml(gpso_handle* h, double* lml_host) {
 // ---------------------------------------------------------------------------------------------------------------------
 static long long window_size(const gpso_handle* h, long long M) {
     long long group = (long long)PRED_GROUP * TB;
-    long long maxw = h->window_override > 0 ? h->window_override : WINDOW_BYTES / ((long long)h->Np * 8);
+    long long per_cand = h->oz_S ? (long long)h->Np * h->oz_S : (long long)h->Np * 8;
+    long long maxw = h->window_override > 0 ? h->window_override : WINDOW_BYTES / per_cand;
     maxw = std::max(group, (maxw / group) * group);
     long long need = ((M + TB - 1) / TB) * TB;
     return std::min(maxw, need);
-}
-
-static int ensure_window(gpso_handle* h, long long W) {
-    GP_TRY(h->KsT.ensure((size_t)W * h->Np * sizeof(double)));
-    GP_TRY(h->part.ensure((size_t)W * h->nb * sizeof(double)));
-    GP_TRY(h->wmean.ensure((size_t)W * sizeof(double)));
-    GP_TRY(h->blockbest.ensure((size_t)((W + 255) / 256) * sizeof(BestRec)));
-    return 0;
 }
 
 static int prof_mark(gpso_handle* h, cudaStream_t st) {
@@ -503,10 +645,27 @@ static int prof_mark(gpso_handle* h, cudaStream_t st) {
     return 0;
 }
 
+static int prod_mark(gpso_handle* h, cudaStream_t st) {
+    if (h->prod_used == h->prod_events.size()) {
+        cudaEvent_t e;
+        CU_TRY(cudaEventCreate(&e));
+        h->prod_events.push_back(e);
+    }
+    CU_TRY(cudaEventRecord(h->prod_events[h->prod_used++], st));
+    return 0;
+}
+
 // sums the per-window stage times recorded by prof_mark (call after the stream has been synchronised)
 static void prof_collect(gpso_handle* h) {
     h->last_ms[1] = h->last_ms[2] = h->last_ms[3] = 0.0;
+    for (size_t i = 0; i + 1 < h->prod_used; i += 2) {
+        float t = 0;
+        cudaEventElapsedTime(&t, h->prod_events[i], h->prod_events[i + 1]);
+        h->last_ms[2] += t;
+    }
+    h->prod_used = 0;
     if (!h->profile) return;
+    h->last_ms[2] = 0.0;
     for (size_t i = 0; i + 3 < h->prof_used; i += 4) {
         float a = 0, b = 0, c = 0;
         cudaEventElapsedTime(&a, h->prof_events[i], h->prof_events[i + 1]);
@@ -519,38 +678,132 @@ static void prof_collect(gpso_handle* h) {
     h->prof_used = 0;
 }
 
-// one window, candidates already on the device.  mode 0: mean/var -> out_mean/out_var (device); mode 1: running best
-static int run_window(gpso_handle* h, cudaStream_t st, const double* Xc_dev, long long Mw, long long idx0, int mode,
-                      double varsigma, double* out_mean, double* out_var, bool first) {
-    long long Mw_pad = ((Mw + TB - 1) / TB) * TB;
-    h->last_windows++;
-    GP_TRY(prof_mark(h, st));
-    DISPATCH_KID(h, launch_crosscov, h, st, Xc_dev, Mw, Mw_pad);
-    GP_TRY(check_launch(h, "crosscov"));
-    PredictParams P;
-    P.Linv = h->Linv.as<double>();
-    P.KsT = h->KsT.as<double>();
-    P.part = h->part.as<double>();
-    P.Np = h->Np;
-    P.nb = h->nb;
-    P.nct = (int)(Mw_pad / TB);
-    P.counter = h->counter.as<int>();
-    CU_TRY(cudaMemsetAsync(h->counter.p, 0, sizeof(int), st));
-    int grid = std::min(h->nsm, P.nct * P.nb);
-    GP_TRY(prof_mark(h, st));
-    predict_trmm_kernel<<<grid, GTHREADS, GEMM_SMEM_BYTES, st>>>(P);
-    GP_TRY(check_launch(h, "predict_trmm"));
-    GP_TRY(prof_mark(h, st));
-    int fb = (int)((Mw + 255) / 256);
-    predict_finalize_kernel<<<fb, 256, 0, st>>>(h->part.as<double>(), h->wmean.as<double>(), h->nb, (int)Mw_pad, Mw, idx0,
-                                                h->variance, h->noise, varsigma, mode, out_mean, out_var,
-                                                h->blockbest.as<BestRec>());
-    GP_TRY(check_launch(h, "predict_finalize"));
-    if (mode == 1) {
-        best_merge_kernel<<<1, 256, 0, st>>>(h->blockbest.as<BestRec>(), fb, h->running.as<BestRec>(), first ? 1 : 0);
-        GP_TRY(check_launch(h, "best_merge"));
+// ---- the window pipeline ---------------------------------------------------------------------------------------------
+// Candidates are processed in windows.  Per window:  [H2D copy]  ->  cross-covariance (+ mean)  ->  variance product  ->
+// finalise (+ running arg-max).  With the int8 engine the cross-covariance of window w+1 (FP64 CUDA cores, stream
+// `aux`) overlaps the tensor-core product of window w (stream `st`): digit tiles and means are double-buffered, events
+// order the two streams.  Host-resident candidates are staged through two device buffers by a third (copy) stream.
+// mode 0: mean/var of every candidate are written out; mode 1: only the running arg-max record is kept.
+static int run_windows(gpso_handle* h, cudaStream_t st, const double* Xc_dev, const double* Xc_host, long long M, int mode,
+                       double varsigma, double* mean_out, double* var_out) {
+    const bool oz = h->oz_S != 0;
+    const bool host = Xc_host != nullptr;
+    const int d = h->d;
+    const long long W = window_size(h, M);
+    const long long nwin = (M + W - 1) / W;
+    // overlap needs the second set of buffers; a single window or the profiling mode (per-stage events) runs in order
+    const bool overlap = oz && h->overlap && !h->profile && nwin > 1;
+    const int nbuf = overlap ? 2 : 1;
+    GP_TRY(h->part.ensure((size_t)W * h->nb * sizeof(double)));
+    GP_TRY(h->blockbest.ensure((size_t)((W + 255) / 256) * sizeof(BestRec)));
+    for (int b = 0; b < nbuf; b++) {
+        GP_TRY(h->wmeanb[b].ensure((size_t)W * sizeof(double)));
+        if (oz) GP_TRY(h->ozBb[b].ensure((size_t)W * h->Np * h->oz_S));
     }
-    GP_TRY(prof_mark(h, st));
+    if (!oz) GP_TRY(h->KsT.ensure((size_t)W * h->Np * sizeof(double)));
+    if (host) {
+        size_t cbytes = (size_t)W * d * sizeof(double);
+        GP_TRY(h->cand[0].ensure(cbytes));
+        GP_TRY(h->cand[1].ensure(cbytes));
+        if (mode == 0) {
+            GP_TRY(h->omean.ensure((size_t)W * sizeof(double)));
+            GP_TRY(h->ovar.ensure((size_t)W * sizeof(double)));
+        }
+    }
+    cudaStream_t xs = overlap ? h->aux_stream : st;  // stream of the cross-covariance kernels
+    cudaStream_t cs = h->copy_stream;
+    // everything enqueued so far on `st` (factorisation, leaf generation) precedes the first work on the side streams
+    CU_TRY(cudaEventRecord(h->ev_start, st));
+    if (xs != st) CU_TRY(cudaStreamWaitEvent(xs, h->ev_start, 0));
+    if (host) CU_TRY(cudaStreamWaitEvent(cs, h->ev_start, 0));
+    bool cand_busy[2] = {false, false}, buf_busy[2] = {false, false};
+
+    for (long long w = 0; w < nwin; w++) {
+        const int cb = (int)(w & 1);            // candidate staging buffer
+        const int b = overlap ? cb : 0;         // digit-tile / mean buffer
+        const long long off = w * W;
+        const long long Mw = std::min(W, M - off);
+        const long long Mw_pad = ((Mw + TB - 1) / TB) * TB;
+        h->last_windows++;
+        // ---- 1. candidates of this window on the device
+        const double* src;
+        if (host) {
+            if (cand_busy[cb]) CU_TRY(cudaStreamWaitEvent(cs, h->ev_used[cb], 0));
+            CU_TRY(cudaMemcpyAsync(h->cand[cb].p, Xc_host + off * d, (size_t)Mw * d * sizeof(double), cudaMemcpyHostToDevice, cs));
+            CU_TRY(cudaEventRecord(h->ev_copy[cb], cs));
+            CU_TRY(cudaStreamWaitEvent(xs, h->ev_copy[cb], 0));
+            src = h->cand[cb].as<double>();
+        } else {
+            src = Xc_dev + off * d;
+        }
+        // ---- 2. cross-covariance (+ posterior mean)
+        if (overlap && buf_busy[b]) CU_TRY(cudaStreamWaitEvent(xs, h->ev_free[b], 0));  // finalise(w-2) has read buffer b
+        GP_TRY(prof_mark(h, xs));
+        double gscale = 0.0;
+        long long nct = 0;
+        if (oz) {
+            const int S = h->oz_S;
+            nct = Mw_pad / OZ_NT;
+            const double beta = oz_beta(h);
+            const double bscale = ldexp(1.0, 8 * S - 2) / beta;
+            gscale = beta * ldexp(1.0, -2 * (8 * S - 2) + 8 * (S - 1));
+            DISPATCH_S(S, launch_oz_crosscov_s, h, xs, src, Mw, nct, bscale, h->ozBb[b].as<uint8_t>(), h->wmeanb[b].as<double>());
+            GP_TRY(check_launch(h, "crosscov_slices"));
+        } else {
+            DISPATCH_KID(h, launch_crosscov, h, xs, src, Mw, Mw_pad);
+            GP_TRY(check_launch(h, "crosscov"));
+        }
+        if (host) {
+            CU_TRY(cudaEventRecord(h->ev_used[cb], xs));
+            cand_busy[cb] = true;
+        }
+        if (xs != st) {
+            CU_TRY(cudaEventRecord(h->ev_xcov[b], xs));
+            CU_TRY(cudaStreamWaitEvent(st, h->ev_xcov[b], 0));
+        }
+        // ---- 3. variance product: part[I][c] = sum over the rows of block I of (L^-1 k*)^2
+        GP_TRY(prof_mark(h, st));
+        GP_TRY(prod_mark(h, st));
+        if (oz) {
+            DISPATCH_S(h->oz_S, launch_oz_trmm, h, st, nct, Mw_pad, gscale, h->ozBb[b].as<uint8_t>());
+            GP_TRY(check_launch(h, "ozaki_trmm"));
+        } else {
+            PredictParams P;
+            P.Linv = h->Linv.as<double>();
+            P.KsT = h->KsT.as<double>();
+            P.part = h->part.as<double>();
+            P.Np = h->Np;
+            P.nb = h->nb;
+            P.nct = (int)(Mw_pad / TB);
+            P.counter = h->counter.as<int>();
+            CU_TRY(cudaMemsetAsync(h->counter.p, 0, sizeof(int), st));
+            int grid = std::min(h->nsm, P.nct * P.nb);
+            predict_trmm_kernel<<<grid, GTHREADS, GEMM_SMEM_BYTES, st>>>(P);
+            GP_TRY(check_launch(h, "predict_trmm"));
+        }
+        GP_TRY(prod_mark(h, st));
+        GP_TRY(prof_mark(h, st));
+        // ---- 4. finalise: var, ucb, window arg-max merged into the running record
+        double* om = mode == 0 ? (host ? h->omean.as<double>() : mean_out + off) : nullptr;
+        double* ov = mode == 0 ? (host ? h->ovar.as<double>() : var_out + off) : nullptr;
+        int fb = (int)((Mw + 255) / 256);
+        predict_finalize_kernel<<<fb, 256, 0, st>>>(h->part.as<double>(), h->wmeanb[b].as<double>(), h->nb, (int)Mw_pad, Mw, off,
+                                                    h->variance, h->noise, varsigma, mode, om, ov, h->blockbest.as<BestRec>());
+        GP_TRY(check_launch(h, "predict_finalize"));
+        if (mode == 1) {
+            best_merge_kernel<<<1, 256, 0, st>>>(h->blockbest.as<BestRec>(), fb, h->running.as<BestRec>(), w == 0 ? 1 : 0);
+            GP_TRY(check_launch(h, "best_merge"));
+        }
+        GP_TRY(prof_mark(h, st));
+        if (overlap) {
+            CU_TRY(cudaEventRecord(h->ev_free[b], st));
+            buf_busy[b] = true;
+        }
+        if (host && mode == 0) {
+            CU_TRY(cudaMemcpyAsync(mean_out + off, h->omean.p, (size_t)Mw * sizeof(double), cudaMemcpyDeviceToHost, st));
+            CU_TRY(cudaMemcpyAsync(var_out + off, h->ovar.p, (size_t)Mw * sizeof(double), cudaMemcpyDeviceToHost, st));
+        }
+    }
     return 0;
 }
 
@@ -559,6 +812,7 @@ static int predict_common_checks(gpso_handle* h, const void* a, long long M, con
     if (M <= 0) return fail(GPSO_E_BADARG, std::string(who) + ": M must be positive");
     if (!h->factorized) return fail(GPSO_E_STATE, std::string(who) + ": call gpso_factorize first");
     h->prof_used = 0;
+    h->prod_used = 0;
     h->last_windows = 0;
     return set_device(h);
 }
@@ -575,24 +829,11 @@ static int fetch_best(gpso_handle* h, cudaStream_t st, double* result_host) {
     return 0;
 }
 
-// device-resident candidates, all windows on `st`
-static int run_dev(gpso_handle* h, cudaStream_t st, const double* Xc_dev, long long M, int mode, double varsigma,
-                   double* mean_dev, double* var_dev) {
-    long long W = window_size(h, M);
-    GP_TRY(ensure_window(h, W));
-    for (long long off = 0; off < M; off += W) {
-        long long Mw = std::min(W, M - off);
-        GP_TRY(run_window(h, st, Xc_dev + off * h->d, Mw, off, mode, varsigma, mean_dev ? mean_dev + off : nullptr,
-                          var_dev ? var_dev + off : nullptr, off == 0));
-    }
-    return 0;
-}
-
 extern "C" int gpso_predict_y_dev(gpso_handle* h, const double* Xc_dev, int64_t M, double* mean_dev, double* var_dev,
                                   void* stream) {
     GP_TRY(predict_common_checks(h, Xc_dev, M, "gpso_predict_y_dev"));
     if (!mean_dev || !var_dev) return fail(GPSO_E_BADARG, "gpso_predict_y_dev: null output");
-    return run_dev(h, (cudaStream_t)stream, Xc_dev, M, 0, 0.0, mean_dev, var_dev);
+    return run_windows(h, (cudaStream_t)stream, Xc_dev, nullptr, M, 0, 0.0, mean_dev, var_dev);
 }
 
 extern "C" int gpso_ucb_argmax_dev(gpso_handle* h, const double* Xc_dev, int64_t M, double varsigma, double* result_host,
@@ -601,7 +842,7 @@ extern "C" int gpso_ucb_argmax_dev(gpso_handle* h, const double* Xc_dev, int64_t
     if (!result_host) return fail(GPSO_E_BADARG, "gpso_ucb_argmax_dev: null output");
     cudaStream_t st = (cudaStream_t)stream;
     CU_TRY(cudaEventRecord(h->ev_t0, st));
-    GP_TRY(run_dev(h, st, Xc_dev, M, 1, varsigma, nullptr, nullptr));
+    GP_TRY(run_windows(h, st, Xc_dev, nullptr, M, 1, varsigma, nullptr, nullptr));
     CU_TRY(cudaEventRecord(h->ev_t1, st));
     GP_TRY(fetch_best(h, st, result_host));
     float ms = 0;
@@ -610,60 +851,12 @@ extern "C" int gpso_ucb_argmax_dev(gpso_handle* h, const double* Xc_dev, int64_t
     return 0;
 }
 
-// host-resident candidates: windows are staged through two device buffers; the H2D copy of window i+1 (copy stream)
-// overlaps the kernels of window i (compute stream)
-static int run_host(gpso_handle* h, const double* Xc_host, long long M, int mode, double varsigma, double* mean_host,
-                    double* var_host) {
-    long long W = window_size(h, M);
-    GP_TRY(ensure_window(h, W));
-    const int d = h->d;
-    size_t cbytes = (size_t)W * d * sizeof(double);
-    GP_TRY(h->cand[0].ensure(cbytes));
-    GP_TRY(h->cand[1].ensure(cbytes));
-    if (mode == 0) {
-        GP_TRY(h->omean.ensure((size_t)W * sizeof(double)));
-        GP_TRY(h->ovar.ensure((size_t)W * sizeof(double)));
-    }
-    cudaStream_t st = h->stream, cs = h->copy_stream;
-    CU_TRY(cudaEventRecord(h->ev_t0, st));
-    h->used_pending[0] = h->used_pending[1] = false;
-    long long nwin = (M + W - 1) / W;
-    // prefetch window 0
-    {
-        long long Mw = std::min(W, M);
-        CU_TRY(cudaMemcpyAsync(h->cand[0].p, Xc_host, (size_t)Mw * d * sizeof(double), cudaMemcpyHostToDevice, cs));
-        CU_TRY(cudaEventRecord(h->ev_copy[0], cs));
-    }
-    for (long long w = 0; w < nwin; w++) {
-        int b = (int)(w & 1);
-        long long off = w * W;
-        long long Mw = std::min(W, M - off);
-        CU_TRY(cudaStreamWaitEvent(st, h->ev_copy[b], 0));
-        GP_TRY(run_window(h, st, h->cand[b].as<double>(), Mw, off, mode, varsigma, h->omean.as<double>(), h->ovar.as<double>(),
-                          w == 0));
-        CU_TRY(cudaEventRecord(h->ev_used[b], st));
-        h->used_pending[b] = true;
-        if (w + 1 < nwin) {  // stage the next window while this one computes
-            int nb2 = b ^ 1;
-            long long off2 = (w + 1) * W;
-            long long Mw2 = std::min(W, M - off2);
-            if (h->used_pending[nb2]) CU_TRY(cudaStreamWaitEvent(cs, h->ev_used[nb2], 0));
-            CU_TRY(cudaMemcpyAsync(h->cand[nb2].p, Xc_host + off2 * d, (size_t)Mw2 * d * sizeof(double), cudaMemcpyHostToDevice, cs));
-            CU_TRY(cudaEventRecord(h->ev_copy[nb2], cs));
-        }
-        if (mode == 0) {
-            CU_TRY(cudaMemcpyAsync(mean_host + off, h->omean.p, (size_t)Mw * sizeof(double), cudaMemcpyDeviceToHost, st));
-            CU_TRY(cudaMemcpyAsync(var_host + off, h->ovar.p, (size_t)Mw * sizeof(double), cudaMemcpyDeviceToHost, st));
-        }
-    }
-    CU_TRY(cudaEventRecord(h->ev_t1, st));
-    return 0;
-}
-
 extern "C" int gpso_predict_y_host(gpso_handle* h, const double* Xc_host, int64_t M, double* mean_host, double* var_host) {
     GP_TRY(predict_common_checks(h, Xc_host, M, "gpso_predict_y_host"));
     if (!mean_host || !var_host) return fail(GPSO_E_BADARG, "gpso_predict_y_host: null output");
-    GP_TRY(run_host(h, Xc_host, M, 0, 0.0, mean_host, var_host));
+    CU_TRY(cudaEventRecord(h->ev_t0, h->stream));
+    GP_TRY(run_windows(h, h->stream, nullptr, Xc_host, M, 0, 0.0, mean_host, var_host));
+    CU_TRY(cudaEventRecord(h->ev_t1, h->stream));
     CU_TRY(cudaStreamSynchronize(h->stream));
     prof_collect(h);
     float ms = 0;
@@ -675,7 +868,9 @@ extern "C" int gpso_predict_y_host(gpso_handle* h, const double* Xc_host, int64_
 extern "C" int gpso_ucb_argmax_host(gpso_handle* h, const double* Xc_host, int64_t M, double varsigma, double* result_host) {
     GP_TRY(predict_common_checks(h, Xc_host, M, "gpso_ucb_argmax_host"));
     if (!result_host) return fail(GPSO_E_BADARG, "gpso_ucb_argmax_host: null output");
-    GP_TRY(run_host(h, Xc_host, M, 1, varsigma, nullptr, nullptr));
+    CU_TRY(cudaEventRecord(h->ev_t0, h->stream));
+    GP_TRY(run_windows(h, h->stream, nullptr, Xc_host, M, 1, varsigma, nullptr, nullptr));
+    CU_TRY(cudaEventRecord(h->ev_t1, h->stream));
     GP_TRY(fetch_best(h, h->stream, result_host));
     float ms = 0;
     cudaEventElapsedTime(&ms, h->ev_t0, h->ev_t1);
@@ -745,6 +940,7 @@ extern "C" int gpso_grow_ucb_argmax(gpso_handle* h, const double* bounds_host, i
     if (!h || !bounds_host || !result_host) return fail(GPSO_E_BADARG, "gpso_grow_ucb_argmax: null argument");
     if (!h->factorized) return fail(GPSO_E_STATE, "gpso_grow_ucb_argmax: call gpso_factorize first");
     h->prof_used = 0;
+    h->prod_used = 0;
     h->last_windows = 0;
     if (d != h->d) return fail(GPSO_E_BADARG, "gpso_grow_ucb_argmax: dimension differs from the training data");
     GP_TRY(set_device(h));
@@ -761,7 +957,7 @@ extern "C" int gpso_grow_ucb_argmax(gpso_handle* h, const double* bounds_host, i
     CU_TRY(cudaMemcpyAsync(bdev, bounds_host, sizeof(double) * 2 * d, cudaMemcpyHostToDevice, st));
     grow_leaves_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, st>>>(bdev, d, depth, rows, h->leaves.as<double>());
     GP_TRY(check_launch(h, "grow_leaves"));
-    GP_TRY(run_dev(h, st, h->leaves.as<double>(), rows, 1, varsigma, nullptr, nullptr));
+    GP_TRY(run_windows(h, st, h->leaves.as<double>(), nullptr, rows, 1, varsigma, nullptr, nullptr));
     CU_TRY(cudaEventRecord(h->ev_t1, st));
     GP_TRY(fetch_best(h, st, result_host));
     float ms = 0;
@@ -838,6 +1034,8 @@ extern "C" int gpso_import_state_dev(gpso_handle* h, const void* src_dev, int64_
     CU_TRY(cudaMemcpyAsync(h->Linv.p, src + STATE_HEADER + d * Np + Np, sizeof(double) * Np * Np, cudaMemcpyDeviceToDevice, st));
     GP_TRY(upload_lengthscales(h, st));
     CU_TRY(cudaStreamSynchronize(st));
+    GP_TRY(prepare_ozaki(h, st));  // the digit tiles are rebuilt locally from the imported L^-1 (bit-identical on every rank)
+    CU_TRY(cudaStreamSynchronize(st));
     h->have_data = false;  // no raw training data on this rank: predict only
     h->factorized = true;
     return 0;
@@ -880,6 +1078,29 @@ extern "C" int gpso_set_profile(gpso_handle* h, int enabled) {
 }
 
 extern "C" int64_t gpso_last_windows(gpso_handle* h) { return h ? h->last_windows : 0; }
+
+extern "C" int gpso_set_predict_mode(gpso_handle* h, int mode, int slices) {
+    if (!h || mode < 0 || mode > 2) return fail(GPSO_E_BADARG, "gpso_set_predict_mode: mode must be 0 (auto), 1 (fp64 DMMA) or 2 (int8 tcgen05)");
+    if (slices != 0 && (slices < 5 || slices > 8)) return fail(GPSO_E_BADARG, "gpso_set_predict_mode: slices must be 0 (auto) or 5..8");
+    h->predict_mode = mode;
+    h->oz_force_slices = slices;
+    h->factorized = false;  // takes effect at the next gpso_factorize
+    return 0;
+}
+
+extern "C" int gpso_set_overlap(gpso_handle* h, int enabled) {
+    if (!h) return fail(GPSO_E_BADARG, "gpso_set_overlap: null handle");
+    h->overlap = enabled != 0;
+    return 0;
+}
+
+extern "C" int gpso_predict_info(gpso_handle* h, double* out3) {
+    if (!h || !out3) return fail(GPSO_E_BADARG, "gpso_predict_info: null argument");
+    out3[0] = h->oz_S ? 2.0 : 1.0;
+    out3[1] = (double)h->oz_S;
+    out3[2] = h->oz_est;
+    return 0;
+}
 
 extern "C" int gpso_set_window(gpso_handle* h, int64_t candidates) {
     if (!h || candidates < 0) return fail(GPSO_E_BADARG, "gpso_set_window: bad argument");

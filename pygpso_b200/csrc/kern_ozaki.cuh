@@ -1,0 +1,436 @@
+// Posterior-variance product V = L^-1 K* on the 5th-generation tensor cores (tcgen05.mma kind::i8, accumulators in TMEM),
+// exact-integer ("Ozaki scheme") emulation of the fp64 product.
+//
+// Why: B200's FP64 pipe peaks at 37 TFLOP/s (DMMA == DFMA rate, profiles/r01_fp64_probe.txt) while its int8 tensor
+// path sustains 4.5 POP/s (profiles/r01_i8_tcgen05_probe.txt).  Both operands are split into S signed 8-bit digits of a
+// fixed-point representation,
+//
+//      L^-1[i,k] = 2^(e_i - (8S-2)) * sum_p a_p[i,k] 256^(S-1-p)        (per-row exponent e_i)
+//      K*[k,c]   = 2^(f   - (8S-2)) * sum_q b_q[k,c] 256^(S-1-q)        (one exponent f: 0 <= k* <= kernel variance)
+//
+// (balanced digits in [-128,127], so slice products are zero-mean), and
+//
+//      V[i,c] = 2^(e_i + f - 2(8S-2) + 8(S-1)) * sum_{t<S} 256^(S-1-t) * C_t[i,c],    C_t = sum_{p+q=t} a_p b_q^T
+//
+// where every C_t is an EXACT int32 sum (|a b| <= 2^14, K <= 8192, <= 8 digit pairs per level).  The only rounding is
+// the fixed-point conversion of the operands (8S-2 bits: 46 at S=6) and the neglected levels t >= S; S is chosen per fit
+// from the row scales so that the error stays two orders below the parity tolerance (see gpso_capi.cu, pick_slices).
+// Integer accumulation makes the result independent of summation order, tile position and GPU: duplicated candidates
+// give bit-identical variances by construction.
+//
+// Data flow (nothing below is a general GEMM library; every layout is produced by our own kernels for this product):
+//   linv_slices_kernel      L^-1 (fp64, lower)  -> A digit tiles  [I][ks][p][128 rows x 32 k]  canonical UMMA K-major,
+//                                                   no-swizzle core matrices (8 rows x 16 B), once per factorisation
+//   crosscov_slices_kernel  candidates -> k*(fp64, registers) -> B digit tiles [ct][ks][q][64 cand x 32 k] + posterior mean
+//   ozaki_trmm_kernel<S>    warp-specialised persistent kernel, one CTA per SM:
+//        warp 0   producer : cp.async.bulk (UBLKCP) of one k-step (S*4 KB of A, S*2 KB of B) per stage, mbarrier tx
+//        warp 1   issuer   : tcgen05.mma.cta_group::1.kind::i8, M=128, N up to 256: digit p of A against digits
+//                            0..S-1-p of B stacked along N, accumulating level t=p+q into TMEM columns [64t, 64t+64)
+//        warps 2-5 epilogue: tcgen05.ld, exact int64 recombination, one fp64 rounding, square, column sums over the
+//                            128 rows -> part[I][c]   (same partial-sum interface as the DMMA kernel)
+//   Work unit = candidate tile x PAIR of row blocks (I, nb-1-I): every unit costs nb+1 k-blocks, so a static
+//   round-robin over the persistent CTAs is balanced and the 148 CTAs share ~10 candidate tiles of B and all of A in L2.
+#pragma once
+#include "common.cuh"
+
+namespace gpso {
+
+constexpr int OZ_NT = 64;                 // candidates per tile
+constexpr int OZ_A_SLICE = 128 * 32;      // bytes of one A digit tile (128 rows x 32 k)
+constexpr int OZ_B_SLICE = OZ_NT * 32;    // bytes of one B digit tile
+constexpr int OZ_THREADS = 192;
+constexpr int OZ_TMEM_COLS = 512;
+
+template <int S>
+struct OzCfg {
+    static constexpr int STAGE_BYTES = S * (OZ_A_SLICE + OZ_B_SLICE);
+    static constexpr int STAGES = (S <= 5) ? 6 : (S == 6) ? 5 : 4;
+    static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
+    static constexpr int SMEM_BYTES = RING_BYTES + 1024 /* barriers + tmem slot */ + 4 * OZ_NT * (int)sizeof(double);
+};
+
+struct OzParams {
+    const uint8_t* A;        // [nb][nks][S][4096]
+    const uint8_t* B;        // [nct][nks][S][2048]
+    const double* rowscale;  // [Np] 2^(e_i)
+    double* part;            // [nb][ldp]
+    double gscale;           // 2^(f - 2(8S-2) + 8(S-1))
+    int nb, nks, nct;
+    long long ldp;
+};
+
+// ---- PTX wrappers -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t oz_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void oz_mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(oz_smem(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void oz_mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\tOZ_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra OZ_DONE;\n\tbra OZ_WAIT;\n\tOZ_DONE:\n\t}\n" ::"r"(oz_smem(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void oz_mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(oz_smem(bar)) : "memory");
+}
+__device__ __forceinline__ void oz_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(oz_smem(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void oz_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(oz_smem(dst)),
+                 "l"(src), "r"(bytes), "r"(oz_smem(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void oz_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(oz_smem(bar)) : "memory");
+}
+__device__ __forceinline__ void oz_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void oz_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// shared-memory matrix descriptor, K-major, no swizzle: core matrix = 8 rows x 16 B contiguous; LBO = 128 B between the
+// two 16-byte K chunks of a K=32 instruction, SBO = 256 B between 8-row groups (validated by tools/microbench/i8_probe.cu)
+__device__ __forceinline__ uint64_t oz_desc(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3fff) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) | ((uint64_t)1 << 46);
+}
+// instruction descriptor: D = S32, A = B = signed int8, both K-major, M = 128, N = n
+__device__ __forceinline__ uint32_t oz_idesc(int n) {
+    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+__device__ __forceinline__ void oz_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void oz_tmem_ld16(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+}
+
+// ---- fixed-point digits -------------------------------------------------------------------------------------------
+// x * scale is rounded to an integer X with |X| < 2^(8S-2); its balanced base-256 digits d_p in [-128,127]
+// (X = sum_p d_p 256^p) are the bytes of (X + 0x80..80) ^ 0x80..80 with the constant covering bytes 0..S-2: adding 128 to
+// every lower byte turns the signed digit into an unsigned byte with the right carry, the xor maps it back to int8.
+template <int S>
+__device__ __forceinline__ unsigned long long oz_digits(double x, double scale) {
+    long long X = __double2ll_rn(x * scale);
+    constexpr unsigned long long C = (S >= 8 ? 0x0080808080808080ULL : (0x8080808080808080ULL >> (8 * (9 - S))));
+    unsigned long long Y = (unsigned long long)X + C;
+    return Y ^ C;
+}
+// byte `pos` (0..3) of word w <- byte `b` (0..7) of the digit word z
+__device__ __forceinline__ uint32_t oz_put(uint32_t w, unsigned long long z, int b, int pos) {
+    uint32_t src = (b < 4) ? (uint32_t)z : (uint32_t)(z >> 32);
+    uint32_t sel = 0x3210u;
+    sel = (sel & ~(0xFu << (4 * pos))) | ((uint32_t)(4 + (b & 3)) << (4 * pos));
+    return __byte_perm(w, src, sel);
+}
+
+// ---- A digit tiles from L^-1 ----------------------------------------------------------------------------------------
+// rowscale[i] = 2^(e_i) with max_k |Linv[i,k]| < 2^(e_i - 0) (one warp per row, k <= i only)
+__global__ void __launch_bounds__(256) linv_rowscale_kernel(const double* __restrict__ Linv, int Np, double* __restrict__ rowscale,
+                                                            double* __restrict__ rowmax) {
+    int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= Np) return;
+    const double* r = Linv + (size_t)row * Np;
+    double m = 0.0;
+    for (int k = lane; k <= row; k += 32) m = fmax(m, fabs(r[k]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) {
+        int e = (m > 0.0 && isfinite(m)) ? ilogb(m) + 1 : 0;
+        rowscale[row] = ldexp(1.0, e);
+        rowmax[row] = m;
+    }
+}
+
+template <int S>
+__global__ void __launch_bounds__(256) linv_slices_kernel(const double* __restrict__ Linv, const double* __restrict__ rowscale, int Np,
+                                                          int nks, uint8_t* __restrict__ A) {
+    const int ks = blockIdx.x, I = blockIdx.y;
+    if (ks >= 4 * (I + 1)) return;  // above the block diagonal: never read
+    const int r = threadIdx.x & 127, half = threadIdx.x >> 7;
+    const int row = I * 128 + r;
+    const double scale = ldexp(1.0, 8 * S - 2) / rowscale[row];
+    const double* src = Linv + (size_t)row * Np + ks * 32 + half * 16;
+    uint32_t out[S][4];
+#pragma unroll
+    for (int p = 0; p < S; p++) out[p][0] = out[p][1] = out[p][2] = out[p][3] = 0u;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        unsigned long long z = oz_digits<S>(src[i], scale);
+#pragma unroll
+        for (int p = 0; p < S; p++) out[p][i >> 2] = oz_put(out[p][i >> 2], z, S - 1 - p, i & 3);  // slice 0 = most significant
+    }
+    uint8_t* dst = A + ((size_t)I * nks + ks) * S * OZ_A_SLICE + (r >> 3) * 256 + half * 128 + (r & 7) * 16;
+#pragma unroll
+    for (int p = 0; p < S; p++) *reinterpret_cast<uint4*>(dst + (size_t)p * OZ_A_SLICE) = make_uint4(out[p][0], out[p][1], out[p][2], out[p][3]);
+}
+
+// ---- B digit tiles + posterior mean from the candidates -------------------------------------------------------------
+// One block = one candidate tile (64 candidates) x all training points, in super-steps of 64 training points.
+// thread: c = tid & 63 (candidate), kq = tid >> 6 (which 16 of the 64 training points).  Every candidate goes through the
+// same operation sequence (position-independent results).
+template <int KID, int S>
+__global__ void __launch_bounds__(256) crosscov_slices_kernel(const double* __restrict__ Xc, long long Mw, int d,
+                                                              const double* __restrict__ ls, int n_ls,
+                                                              const double* __restrict__ Xs, const double* __restrict__ alpha, int N,
+                                                              int Np, double var, double c0, double bscale, int nks,
+                                                              uint8_t* __restrict__ B, double* __restrict__ mean) {
+    extern __shared__ double sm[];
+    const int dp = d | 1;
+    double* sC = sm;                    // [64][dp]   scaled candidate coordinates
+    double* sX = sC + OZ_NT * dp;       // [2][d][64] scaled training coordinates of the current / next super-step
+    double* sAl = sX + 2 * d * 64;      // [2][64]
+    double* sR = sAl + 2 * 64;          // [4][64]
+    const int tid = threadIdx.x, c = tid & 63, kq = tid >> 6;
+    const long long ct = blockIdx.x;
+    const long long cand = ct * OZ_NT + c;
+    for (int e = tid; e < OZ_NT * d; e += 256) {
+        int cc = e / d, dim = e - cc * d;
+        long long cg = ct * OZ_NT + cc;
+        sC[cc * dp + dim] = (cg < Mw) ? Xc[cg * d + dim] / ls[n_ls > 1 ? dim : 0] : 0.0;
+    }
+    for (int e = tid; e < d * 64; e += 256) sX[e] = Xs[(size_t)(e >> 6) * Np + (e & 63)];
+    if (tid < 64) sAl[tid] = alpha[tid];
+    const bool cvalid = cand < Mw;
+    double macc = 0.0;
+    const int nss = Np / 64;
+    for (int ss = 0; ss < nss; ss++) {
+        __syncthreads();
+        const int b = ss & 1;
+        if (ss + 1 < nss) {
+            double* nx = sX + (b ^ 1) * d * 64;
+            for (int e = tid; e < d * 64; e += 256) nx[e] = Xs[(size_t)(e >> 6) * Np + (ss + 1) * 64 + (e & 63)];
+            if (tid < 64) sAl[(b ^ 1) * 64 + tid] = alpha[(ss + 1) * 64 + tid];
+        }
+        const double* x = sX + b * d * 64 + kq * 16;
+        double r2[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) r2[i] = 0.0;
+        for (int dim = 0; dim < d; dim++) {
+            const double xc = sC[c * dp + dim];
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                double df = x[dim * 64 + i] - xc;
+                r2[i] = fma(df, df, r2[i]);
+            }
+        }
+        uint32_t out[S][4];
+#pragma unroll
+        for (int p = 0; p < S; p++) out[p][0] = out[p][1] = out[p][2] = out[p][3] = 0u;
+        const int j0 = ss * 64 + kq * 16;
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            double k = (cvalid && j0 + i < N) ? cov_from_r2<KID>(r2[i], var) : 0.0;
+            macc = fma(k, sAl[b * 64 + kq * 16 + i], macc);
+            unsigned long long z = oz_digits<S>(k, bscale);
+#pragma unroll
+            for (int p = 0; p < S; p++) out[p][i >> 2] = oz_put(out[p][i >> 2], z, S - 1 - p, i & 3);
+        }
+        const int ks = ss * 2 + (kq >> 1), half = kq & 1;
+        uint8_t* dst = B + ((size_t)ct * nks + ks) * S * OZ_B_SLICE + (c >> 3) * 256 + half * 128 + (c & 7) * 16;
+#pragma unroll
+        for (int p = 0; p < S; p++) *reinterpret_cast<uint4*>(dst + (size_t)p * OZ_B_SLICE) = make_uint4(out[p][0], out[p][1], out[p][2], out[p][3]);
+    }
+    sR[kq * 64 + c] = macc;
+    __syncthreads();
+    if (tid < 64) mean[ct * OZ_NT + tid] = ((sR[tid] + sR[64 + tid]) + (sR[128 + tid] + sR[192 + tid])) + c0;
+}
+
+// ---- the product kernel ---------------------------------------------------------------------------------------------
+template <int S>
+__global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_trmm_kernel(OzParams P) {
+    using Cfg = OzCfg<S>;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ __align__(1024) uint8_t oz_smem_raw[];
+    uint8_t* ring = oz_smem_raw;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(oz_smem_raw + Cfg::RING_BYTES);
+    uint64_t* full = bars;                  // [STAGES] producer -> issuer (tx bytes)
+    uint64_t* empty = bars + STAGES;        // [STAGES] issuer (tcgen05.commit) -> producer
+    uint64_t* tmem_full = bars + 2 * STAGES;   // issuer -> epilogue
+    uint64_t* tmem_empty = tmem_full + 1;      // epilogue (4 warps) -> issuer
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 1);
+    double* red = reinterpret_cast<double*>(oz_smem_raw + Cfg::RING_BYTES + 1024);  // [4][64]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < STAGES; i++) {
+            oz_mbar_init(&full[i], 1);
+            oz_mbar_init(&empty[i], 1);
+        }
+        oz_mbar_init(tmem_full, 1);
+        oz_mbar_init(tmem_empty, 4);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(oz_smem(tmem_slot)), "r"(OZ_TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    oz_fence_before();
+    __syncthreads();
+    oz_fence_after();
+    const uint32_t tbase = *tmem_slot;
+
+    const int nb = P.nb, nks = P.nks;
+    const int npairs = (nb + 1) >> 1;
+    const long long units = (long long)P.nct * npairs;
+
+    if (warp == 0) {
+        // ================= producer =================
+        if (lane == 0) {
+            int st = 0;
+            uint32_t ph = 0;
+            for (long long u = blockIdx.x; u < units; u += gridDim.x) {
+                const long long ct = u / npairs;
+                const int j = (int)(u - ct * npairs);
+                const int items = (nb - 1 - j != j) ? 2 : 1;
+                for (int it = 0; it < items; it++) {
+                    const int I = it == 0 ? nb - 1 - j : j;
+                    const uint8_t* a = P.A + (size_t)I * nks * S * OZ_A_SLICE;
+                    const uint8_t* b = P.B + (size_t)ct * nks * S * OZ_B_SLICE;
+                    const int n = 4 * (I + 1);
+                    for (int ks = 0; ks < n; ks++) {
+                        oz_mbar_wait(&empty[st], ph ^ 1);
+                        uint8_t* dst = ring + (size_t)st * Cfg::STAGE_BYTES;
+                        oz_mbar_expect_tx(&full[st], Cfg::STAGE_BYTES);
+                        oz_bulk_g2s(dst, a + (size_t)ks * S * OZ_A_SLICE, S * OZ_A_SLICE, &full[st]);
+                        oz_bulk_g2s(dst + S * OZ_A_SLICE, b + (size_t)ks * S * OZ_B_SLICE, S * OZ_B_SLICE, &full[st]);
+                        if (++st == STAGES) {
+                            st = 0;
+                            ph ^= 1;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            int st = 0;
+            uint32_t ph = 0, acc_ph = 0;
+            const uint32_t ring_addr = oz_smem(ring);
+            for (long long u = blockIdx.x; u < units; u += gridDim.x) {
+                const long long ct = u / npairs;
+                const int j = (int)(u - ct * npairs);
+                const int items = (nb - 1 - j != j) ? 2 : 1;
+                for (int it = 0; it < items; it++) {
+                    const int I = it == 0 ? nb - 1 - j : j;
+                    const int n = 4 * (I + 1);
+                    oz_mbar_wait(tmem_empty, acc_ph ^ 1);  // epilogue has drained the accumulators of the previous item
+                    oz_fence_after();
+                    for (int ks = 0; ks < n; ks++) {
+                        oz_mbar_wait(&full[st], ph);
+                        oz_fence_after();
+                        const uint32_t sa = ring_addr + (uint32_t)st * Cfg::STAGE_BYTES;
+                        const uint32_t sb = sa + S * OZ_A_SLICE;
+#pragma unroll
+                        for (int p = 0; p < S; p++) {
+                            // digit p of A against digits 0..S-1-p of B (stacked along N), level t = p+q -> columns 64 t
+                            const uint64_t ad = oz_desc(sa + p * OZ_A_SLICE);
+                            constexpr int dummy = 0;
+                            (void)dummy;
+                            const int rem = S - p;
+                            const int nch = (rem + 3) / 4;
+                            const int take = (rem + nch - 1) / nch;
+#pragma unroll
+                            for (int q0 = 0; q0 < rem; q0 += take) {
+                                const int nq = (rem - q0 < take) ? rem - q0 : take;
+                                oz_mma(tbase + (uint32_t)((p + q0) * OZ_NT), ad, oz_desc(sb + q0 * OZ_B_SLICE), oz_idesc(nq * OZ_NT),
+                                       (ks > 0 || p > 0) ? 1u : 0u);
+                            }
+                        }
+                        oz_commit(&empty[st]);  // frees the stage once these MMAs have read it
+                        if (++st == STAGES) {
+                            st = 0;
+                            ph ^= 1;
+                        }
+                    }
+                    oz_commit(tmem_full);  // accumulators of this item are complete
+                    acc_ph ^= 1;
+                }
+            }
+        }
+    } else {
+        // ================= epilogue (warps 2..5 -> TMEM lane groups 2,3,0,1) =================
+        const int lg = warp & 3;
+        const int et = threadIdx.x - 64;  // 0..127
+        uint32_t acc_ph = 0;
+        constexpr int H = S / 2;  // levels folded into the low word
+        const double hi_mul = ldexp(1.0, 8 * H);
+        for (long long u = blockIdx.x; u < units; u += gridDim.x) {
+            const long long ct = u / npairs;
+            const int j = (int)(u - ct * npairs);
+            const int items = (nb - 1 - j != j) ? 2 : 1;
+            for (int it = 0; it < items; it++) {
+                const int I = it == 0 ? nb - 1 - j : j;
+                const double rs = P.rowscale[I * 128 + lg * 32 + lane] * P.gscale;
+                oz_mbar_wait(tmem_full, acc_ph);
+                oz_fence_after();
+                acc_ph ^= 1;
+                double tot[4];  // this lane's share of the column sums: candidate cc*16 + idx(lane)
+#pragma unroll
+                for (int cc = 0; cc < 4; cc++) {
+                    uint32_t r[S][16];
+#pragma unroll
+                    for (int t = 0; t < S; t++) oz_tmem_ld16(tbase + ((uint32_t)(lg * 32) << 16) + (uint32_t)(t * OZ_NT + cc * 16), r[t]);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (cc == 3) {
+                        // all TMEM reads of this item are done: hand the accumulators back to the issuer
+                        oz_fence_before();
+                        __syncwarp();
+                        if (lane == 0) oz_mbar_arrive(tmem_empty);
+                    }
+                    double v[16];
+#pragma unroll
+                    for (int i = 0; i < 16; i++) {
+                        long long whi = 0, wlo = 0;
+#pragma unroll
+                        for (int t = 0; t < S - H; t++) whi += (long long)(int32_t)r[t][i] << (8 * (S - H - 1 - t));
+#pragma unroll
+                        for (int t = S - H; t < S; t++) wlo += (long long)(int32_t)r[t][i] << (8 * (S - 1 - t));
+                        double w = fma((double)whi, hi_mul, (double)wlo);
+                        double x = w * rs;
+                        v[i] = x * x;
+                    }
+                    // transposed butterfly: 16 values x 32 lanes -> every lane pair holds one column sum; fixed tree
+#pragma unroll
+                    for (int o = 16, n = 8; o >= 2; o >>= 1, n >>= 1) {
+                        const bool up = (lane & o) != 0;
+#pragma unroll
+                        for (int i = 0; i < n; i++) {
+                            double send = up ? v[i] : v[i + n];
+                            double keep = up ? v[i + n] : v[i];
+                            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+                        }
+                    }
+                    tot[cc] = v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+                }
+                // candidate index held by this lane within a 16-chunk: bit4 -> 8, bit3 -> 4, bit2 -> 2, bit1 -> 1
+                const int idx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+                asm volatile("bar.sync 1, 128;" ::: "memory");  // previous item's cross-warp reduction has been consumed
+                if ((lane & 1) == 0) {
+#pragma unroll
+                    for (int cc = 0; cc < 4; cc++) red[lg * OZ_NT + cc * 16 + idx] = tot[cc];
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (et < OZ_NT) {
+                    double s = (red[et] + red[OZ_NT + et]) + (red[2 * OZ_NT + et] + red[3 * OZ_NT + et]);
+                    P.part[(size_t)I * P.ldp + (size_t)ct * OZ_NT + et] = s;
+                }
+            }
+        }
+    }
+    oz_fence_before();
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(OZ_TMEM_COLS));
+}
+
+}  // namespace gpso

@@ -35,8 +35,14 @@ def cuda():
     return backend.default_backend()
 
 
-def open_session(cuda, kernel, X, y, n_ls=1, has_mean=True):
+# engines of the variance product: FP64 DMMA, and the exact-integer int8 tcgen05 emulation (automatic / forced digits)
+ENGINES = {"dmma": (1, 0), "int8": (2, 0), "int8x5": (2, 5), "int8x6": (2, 6), "int8x7": (2, 7), "int8x8": (2, 8)}
+
+
+def open_session(cuda, kernel, X, y, n_ls=1, has_mean=True, engine=None):
     s = cuda.open_session(kernel, n_ls, has_mean)
+    if engine is not None:
+        s.set_predict_mode(*ENGINES[engine])
     s.set_data(X, y)
     return s
 
@@ -136,14 +142,17 @@ def test_not_positive_definite_reports_info(cuda):
 # ---------------------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("N,d,M", [(1, 1, 1), (6, 2, 2), (52, 2, 121), (128, 3, 127), (129, 3, 129), (512, 2, 5000), (1100, 10, 3001)])
 @pytest.mark.parametrize("kernel", ["Matern52", "SquaredExponential"])
-def test_predict_y_and_argmax(cuda, kernel, N, d, M):
+@pytest.mark.parametrize("engine", ["dmma", "int8"])
+def test_predict_y_and_argmax(cuda, engine, kernel, N, d, M):
     X, y = synthetic(N, d)
     h = go.Hyper(0.25 * np.sqrt(d), 1.0, 1e-3, 0.05)
     rng = np.random.default_rng(N + M)
     Xc = rng.random((M, d))
     mean_ref, var_ref = go.predict_y(kernel, X, y, h, Xc)
-    s = open_session(cuda, kernel, X, y)
+    s = open_session(cuda, kernel, X, y, engine=engine)
     s.factorize(theta_of(h))
+    info = s.predict_info()
+    assert info["engine"] == ("fp64-dmma" if engine == "dmma" else "int8-tcgen05")
     mean, var = s.predict_y(Xc)
     assert_predict_close(mean, var, mean_ref[:, 0], var_ref[:, 0], y, h.variance)
     idx_ref, m_ref, v_ref, u_ref = go.ucb_argmax(mean_ref, var_ref, VARSIGMA)
@@ -191,7 +200,60 @@ def test_predict_ill_conditioned_fit(cuda):
     assert_predict_close(mean.numpy()[:, 0], var.numpy()[:, 0], mean_ref[:, 0], var_ref[:, 0], yv, h.variance)
 
 
-def test_duplicates_are_bit_identical_and_first_wins(cuda):
+@pytest.mark.parametrize("engine", ["int8x5", "int8x6", "int8x7", "int8x8"])
+def test_int8_engine_digit_counts(cuda, engine):
+    """Every digit count of the int8 engine against the FP64 DMMA engine on the same factor: the error must shrink with
+    the digit count and stay within the estimate reported by the library."""
+    N, d, M = 700, 4, 2000
+    X, y = synthetic(N, d, seed=3)
+    h = go.Hyper(0.5, 1.5, 1e-4, 0.1)
+    Xc = np.random.default_rng(9).random((M, d))
+    Xc[:50] = X[:50]  # cancellation: variance collapses to ~noise at training points
+    ref = open_session(cuda, "Matern52", X, y, engine="dmma")
+    ref.factorize(theta_of(h))
+    mean_r, var_r = ref.predict_y(Xc)
+    s = open_session(cuda, "Matern52", X, y, engine=engine)
+    s.factorize(theta_of(h))
+    info = s.predict_info()
+    assert info["engine"] == "int8-tcgen05" and info["slices"] == ENGINES[engine][1]
+    mean, var = s.predict_y(Xc)
+    # the mean never goes through the integer product (fp64 FMA in both engines, different summation trees)
+    np.testing.assert_allclose(mean, mean_r, rtol=0, atol=1e-12 * max(1.0, np.abs(y).max()))
+    err = np.abs(var - var_r).max() / (1e-8 * h.variance)
+    assert err <= max(10 * info["error_estimate_over_tol"], 1e-3), (err, info)
+    mean_o, var_o = go.predict_y("Matern52", X, y, h, Xc)
+    if engine != "int8x5":
+        assert_predict_close(mean, var, mean_o[:, 0], var_o[:, 0], y, h.variance)
+    ref.close()
+    s.close()
+
+
+def test_int8_engine_automatic_digit_choice(cuda):
+    """Well-conditioned factor -> 6 digits; noise at the 1e-6 floor (rows of L^-1 up to ~1e3) -> more digits."""
+    N, d = 600, 3
+    X, y = synthetic(N, d, seed=4)
+    s = open_session(cuda, "Matern52", X, y, engine="int8")
+    s.factorize(np.array([0.5, 1.0, 1e-3, 0.0]))
+    a = s.predict_info()
+    s.factorize(np.array([1.5, 4.0, 1.0e-6 + 5e-8, 0.0]))
+    b = s.predict_info()
+    assert a["engine"] == b["engine"] == "int8-tcgen05"
+    assert 5 <= a["slices"] <= b["slices"] <= 8 and b["slices"] > a["slices"]
+    assert a["error_estimate_over_tol"] <= 0.02 and b["error_estimate_over_tol"] <= 0.02
+    # the ill-conditioned factor still meets the parity tolerance against the oracle and the long-double truth
+    h = go.Hyper(1.5, 4.0, 1.0e-6 + 5e-8, 0.0)
+    Xc = np.random.default_rng(5).random((500, d))
+    mean, var = s.predict_y(Xc)
+    mean_ld, var_ld = go.predict_y_longdouble("Matern52", X, y, h, Xc)
+    mean_ref, var_ref = go.predict_y("Matern52", X, y, h, Xc)
+    err_gpu = np.abs(var - var_ld[:, 0].astype(float)).max()
+    err_ref = np.abs(var_ref[:, 0] - var_ld[:, 0].astype(float)).max()
+    assert err_gpu <= max(10 * err_ref, 1e-9 * h.variance), (err_gpu, err_ref)
+    s.close()
+
+
+@pytest.mark.parametrize("engine", ["dmma", "int8"])
+def test_duplicates_are_bit_identical_and_first_wins(cuda, engine):
     """Appendix C: exact duplicate rows must give bit-identical UCBs wherever they sit (tiles, windows, shards)."""
     N, d = 300, 3
     X, y = synthetic(N, d)
@@ -199,7 +261,7 @@ def test_duplicates_are_bit_identical_and_first_wins(cuda):
     rng = np.random.default_rng(0)
     base = rng.random((40, d))
     Xc = base[rng.integers(0, 40, size=5000)]
-    s = open_session(cuda, "Matern52", X, y)
+    s = open_session(cuda, "Matern52", X, y, engine=engine)
     s.factorize(theta_of(h))
     mean, var = s.predict_y(Xc)
     for b in range(40):
@@ -332,11 +394,12 @@ def test_end_to_end_sample_method_runs_on_gpu():
 # ---------------------------------------------------------------------------------------------------------------------
 # full-size configuration (BASELINE config C3 shape): size-independent properties
 # ---------------------------------------------------------------------------------------------------------------------
-def test_c3_shape_properties(cuda):
+@pytest.mark.parametrize("engine", ["dmma", "int8"])
+def test_c3_shape_properties(cuda, engine):
     N, d, M = 4096, 10, 200_000
     X, y = synthetic(N, d)
     theta = np.array([0.25 * np.sqrt(d), 1.0, 1e-3, 0.0])
-    s = open_session(cuda, "Matern52", X, y)
+    s = open_session(cuda, "Matern52", X, y, engine=engine)
     s.factorize(theta)
     Xc = np.random.default_rng([20240517, 0]).random((M, d))
     idx, m, v, u = s.ucb_argmax(Xc, VARSIGMA)
