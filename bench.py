@@ -34,6 +34,7 @@ WORKLOADS = {
     "c2": (512, 2, 100_000, "C2: predict_y+UCB microbench, N=512 train, d=2, 1e5 candidates, Matern-5/2 fp64"),
 }
 FP64_PEAK_TFLOPS = 37.03  # measured DMMA.8x8x4 issue peak of this pool's B200 (profiles/r01_fp64_probe.txt)
+INT8_PEAK_TOPS = 4528.7   # measured tcgen05.mma kind::i8 issue peak, M=128 N=256, 148 SMs (profiles/r01_i8_tcgen05_probe.txt)
 CPU_SAMPLE = 8192         # candidates per CPU-baseline step (bounded sample of the same workload)
 
 
@@ -154,6 +155,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--engine", default="auto", choices=["auto", "dmma", "int8"],
                     help="variance-product engine: FP64 DMMA or the exact-integer int8 tcgen05 emulation (auto picks int8 at this size)")
+    ap.add_argument("--no-overlap", action="store_true", help="int8 engine: run cross-covariance and product back to back")
     ap.add_argument("--slices", type=int, default=0, help="8-bit digits per operand for the int8 engine (0 = automatic)")
     args = ap.parse_args()
 
@@ -192,6 +194,7 @@ def main():
                         backend=backend.CudaBackend(device=local_rank))
     session = model._session
     session.set_predict_mode({"auto": 0, "dmma": 1, "int8": 2}[args.engine], args.slices)
+    session.set_overlap(not args.no_overlap)
     t0 = time.perf_counter()
     if rank == 0:
         model._ensure_factor()  # Gram -> Cholesky -> L^-1 -> alpha on rank 0 only
@@ -246,7 +249,6 @@ def main():
     # ---- device-resident measurement -------------------------------------------------------------------------------
     for _ in range(args.warmup):
         result = step_device()
-    session.set_profile(True)
     sync_all()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -265,7 +267,13 @@ def main():
     dev_ms = max_over_ranks(ev0.elapsed_time(ev1))
     launches = session.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
+    product_ms = stage_ms[2]  # summed duration of the variance-product launches (event pairs on their stream)
+    # per-stage breakdown: one extra, untimed step with per-stage events (stages run back to back, no stream overlap)
+    session.set_profile(True)
+    step_device()
+    stage_profile = session.last_timing_ms()
     session.set_profile(False)
+    engine = session.predict_info()
 
     # ---- end-to-end measurement (host buffers through the public API) ------------------------------------------------
     for _ in range(min(args.warmup, 1)):
@@ -283,41 +291,63 @@ def main():
         assert result_e2e[0] == result[0], "end-to-end and device-resident passes selected different candidates"
         value = M * args.steps / (dev_ms * 1e-3)
         e2e_value = M * args.steps / e2e_s
-        trmm_ms = stage_ms[2]
-        flops = float(N) * N * m_local * args.steps  # algorithmic: N^2 per candidate
-        achieved = flops / (trmm_ms * 1e-3) / 1e12 if trmm_ms > 0 else None
-        traffic = None
-        prof_json = os.path.join(ROOT, "profiles", "predict_trmm_traffic.json")
+        flops64 = float(N) * N * m_local * args.steps  # algorithmic fp64 work: N^2 per candidate
+        windows = max(windows, 1)
+        if engine["engine"] == "int8-tcgen05":
+            S = engine["slices"]
+            pairs = S * (S + 1) // 2
+            # the same N^2/2 multiply-adds per candidate, once per retained digit pair, on the int8 tensor pipe
+            ops = pairs * flops64
+            achieved = ops / (product_ms * 1e-3) / 1e12
+            roofline = {
+                "bound": "tensor",
+                "kernel": f"ozaki_trmm_kernel<{S}> (tcgen05.mma kind::i8, {S} 8-bit digits per operand, {pairs} digit pairs, "
+                          "TMEM accumulators, exact int32 sums recombined to fp64 in the epilogue)",
+                "achieved": achieved, "peak": INT8_PEAK_TOPS, "unit": "TFLOP/s", "frac": achieved / INT8_PEAK_TOPS,
+                "op_kind": "int8 tensor op (2 per multiply-add); algorithmic = digit_pairs * N^2 per candidate",
+                "traffic": None,
+                "peak_source": "measured tcgen05 kind::i8 issue peak on this pool's B200 at 1965 MHz (profiles/"
+                               "r01_i8_tcgen05_probe.txt, nominal 4500); under the 1 kW cap the SM clock settles near "
+                               "1.6 GHz in this kernel (see clocks); MEASURED_PEAKS.json has no int8 entry",
+                "fp64_equivalent": {"achieved_tflops": flops64 / (product_ms * 1e-3) / 1e12, "fp64_pipe_peak_tflops": FP64_PEAK_TFLOPS,
+                                    "ratio_to_fp64_peak": flops64 / (product_ms * 1e-3) / 1e12 / FP64_PEAK_TFLOPS},
+                "digits": S, "error_estimate_over_tolerance": engine["error_estimate_over_tol"],
+            }
+        else:
+            achieved = flops64 / (product_ms * 1e-3) / 1e12
+            roofline = {
+                "bound": "tensor", "kernel": "predict_trmm_kernel (FP64 DMMA triangular product + column sum of squares)",
+                "achieved": achieved, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": achieved / FP64_PEAK_TFLOPS, "traffic": None,
+                "peak_source": "measured DMMA.8x8x4 issue peak on this pool's B200 (profiles/r01_fp64_probe.txt; cuBLAS dgemm "
+                               "8192^3 reaches 36.06); MEASURED_PEAKS.json has no FP64 entry",
+            }
+        prof_json = os.path.join(ROOT, "profiles", "product_kernel_traffic.json")
         if os.path.exists(prof_json):
             try:
-                traffic = json.load(open(prof_json)).get("dram_bytes_per_launch")
+                roofline["traffic"] = json.load(open(prof_json)).get(engine["engine"], {}).get("dram_bytes_per_launch")
             except Exception:
-                traffic = None
+                pass
+        roofline.update({
+            "launches": int(windows), "avg_launch_ms": product_ms / windows,
+            "algorithmic_ops_per_launch": (roofline["achieved"] * 1e12 * product_ms * 1e-3) / windows,
+            "product_share_of_step": product_ms / dev_ms,
+            "hbm_algorithmic_gbs": (80.0 * M * args.steps / (dev_ms * 1e-3)) / 1e9,
+            "stage_ms_one_step_serialised": {"crosscov": stage_profile[1], "product": stage_profile[2], "finalize": stage_profile[3]},
+        })
         line = {
             "metric": "predict_y+UCB candidates/sec", "value": value, "unit": "candidates/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": desc, "N": N, "d": d, "M": M, "kernel": "Matern52", "theta": theta.tolist(),
                        "varsigma": varsigma, "parallelism": f"candidates sharded over {world} GPU(s)",
-                       "l2": "inputs larger than L2: 80 B/candidate x M candidates in HBM plus a 2 GiB rolling "
-                             "cross-covariance window per GPU vs 126 MB L2"},
+                       "engine": engine,
+                       "l2": "inputs larger than L2: 80 B/candidate x M candidates in HBM plus two 2 GiB rolling windows of "
+                             "cross-covariance digit tiles per GPU vs 126 MB L2"},
             "e2e": {"value": e2e_value, "unit": "candidates/s", "h2d_bytes_per_step": int(M) * d * 8,
                     "d2h_bytes_per_step": 32 * world, "ms_per_step": e2e_s / args.steps * 1e3},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {
-                "bound": "tensor", "kernel": "predict_trmm_kernel (FP64 DMMA triangular product + column sum of squares)",
-                "achieved": achieved, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
-                "frac": (achieved / FP64_PEAK_TFLOPS) if achieved else None, "traffic": traffic,
-                "peak_source": "measured DMMA.8x8x4 issue peak on this pool's B200 (profiles/r01_fp64_probe.txt; cuBLAS dgemm "
-                               "8192^3 reaches 36.06); MEASURED_PEAKS.json has no FP64 entry",
-                "launches": int(windows), "avg_launch_ms": trmm_ms / windows if windows else None,
-                "algorithmic_flops_per_launch": flops / windows if windows else None,
-                "whole_step_tflops": float(N) * N * M * args.steps / (dev_ms * 1e-3) / 1e12 / world,
-                "hbm_algorithmic_gbs": (80.0 * M * args.steps / (dev_ms * 1e-3)) / 1e9,
-                "stage_ms_per_step": {"crosscov": stage_ms[1] / args.steps, "trmm": stage_ms[2] / args.steps,
-                                      "finalize": stage_ms[3] / args.steps},
-            },
+            "roofline": roofline,
             "setup": {"factorize_ms": factor_ms, "broadcast_ms": broadcast_ms, "state_bytes": session.state_bytes(N, d)},
             "result": {"index": int(result[0]), "mean": result[1], "var": result[2], "ucb": result[3]},
         }

@@ -169,6 +169,13 @@ static void launch_crosscov(gpso_handle* h, cudaStream_t st, const double* Xc, l
 template <int S>
 static int oz_configure() {
     CU_TRY(cudaFuncSetAttribute(ozaki_trmm_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, OzCfg<S>::SMEM_BYTES));
+    // full shared-memory carve-out for both kernels: the persistent product CTA (one per SM) must leave room for a
+    // cross-covariance block of the next window on the same SM (they use different pipes and overlap)
+    CU_TRY(cudaFuncSetAttribute(ozaki_trmm_kernel<S>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CU_TRY(cudaFuncSetAttribute(crosscov_slices_kernel<KERNEL_MATERN12, S>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CU_TRY(cudaFuncSetAttribute(crosscov_slices_kernel<KERNEL_MATERN32, S>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CU_TRY(cudaFuncSetAttribute(crosscov_slices_kernel<KERNEL_MATERN52, S>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CU_TRY(cudaFuncSetAttribute(crosscov_slices_kernel<KERNEL_SE, S>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CU_TRY(cudaFuncSetAttribute(crosscov_slices_kernel<KERNEL_MATERN12, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_XCOV_SMEM_MAX));
     CU_TRY(cudaFuncSetAttribute(crosscov_slices_kernel<KERNEL_MATERN32, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_XCOV_SMEM_MAX));
     CU_TRY(cudaFuncSetAttribute(crosscov_slices_kernel<KERNEL_MATERN52, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_XCOV_SMEM_MAX));
@@ -458,7 +465,11 @@ extern "C" int gpso_create(int device, int kernel_id, int ard, int mean_id, gpso
     h->ard = ard ? 1 : 0;
     h->mean_id = mean_id;
     h->nsm = prop.multiProcessorCount;
-    CU_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    // h->stream carries the tensor-core product kernels: highest priority, so that its persistent CTAs are placed before
+    // the (default-priority) cross-covariance blocks of the next window when both become eligible at the same time
+    int prio_least = 0, prio_greatest = 0;
+    CU_TRY(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+    CU_TRY(cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, prio_greatest));
     CU_TRY(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
     CU_TRY(cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
     CU_TRY(cudaEventCreateWithFlags(&h->ev_start, cudaEventDisableTiming));
@@ -710,10 +721,15 @@ static int run_windows(gpso_handle* h, cudaStream_t st, const double* Xc_dev, co
             GP_TRY(h->ovar.ensure((size_t)W * sizeof(double)));
         }
     }
+    cudaStream_t user_st = st;
     cudaStream_t xs = overlap ? h->aux_stream : st;  // stream of the cross-covariance kernels
     cudaStream_t cs = h->copy_stream;
     // everything enqueued so far on `st` (factorisation, leaf generation) precedes the first work on the side streams
     CU_TRY(cudaEventRecord(h->ev_start, st));
+    if (overlap && st != h->stream) {  // products run on the handle's high-priority stream, joined back at the end
+        st = h->stream;
+        CU_TRY(cudaStreamWaitEvent(st, h->ev_start, 0));
+    }
     if (xs != st) CU_TRY(cudaStreamWaitEvent(xs, h->ev_start, 0));
     if (host) CU_TRY(cudaStreamWaitEvent(cs, h->ev_start, 0));
     bool cand_busy[2] = {false, false}, buf_busy[2] = {false, false};
@@ -803,6 +819,10 @@ static int run_windows(gpso_handle* h, cudaStream_t st, const double* Xc_dev, co
             CU_TRY(cudaMemcpyAsync(mean_out + off, h->omean.p, (size_t)Mw * sizeof(double), cudaMemcpyDeviceToHost, st));
             CU_TRY(cudaMemcpyAsync(var_out + off, h->ovar.p, (size_t)Mw * sizeof(double), cudaMemcpyDeviceToHost, st));
         }
+    }
+    if (st != user_st) {  // the caller's stream continues after the last product / finalise
+        CU_TRY(cudaEventRecord(h->ev_start, st));
+        CU_TRY(cudaStreamWaitEvent(user_st, h->ev_start, 0));
     }
     return 0;
 }

@@ -26,7 +26,8 @@
 //        warp 0   producer : cp.async.bulk (UBLKCP) of one k-step (S*4 KB of A, S*2 KB of B) per stage, mbarrier tx
 //        warp 1   issuer   : tcgen05.mma.cta_group::1.kind::i8, M=128, N up to 256: digit p of A against digits
 //                            0..S-1-p of B stacked along N, accumulating level t=p+q into TMEM columns [64t, 64t+64)
-//        warps 2-5 epilogue: tcgen05.ld, exact int64 recombination, one fp64 rounding, square, column sums over the
+//        warps 2-9 epilogue (two per TMEM lane group, 32 candidates each): tcgen05.ld, exact int64 recombination, one
+//                            fp64 rounding, square, column sums over the
 //                            128 rows -> part[I][c]   (same partial-sum interface as the DMMA kernel)
 //   Work unit = candidate tile x PAIR of row blocks (I, nb-1-I): every unit costs nb+1 k-blocks, so a static
 //   round-robin over the persistent CTAs is balanced and the 148 CTAs share ~10 candidate tiles of B and all of A in L2.
@@ -38,7 +39,7 @@ namespace gpso {
 constexpr int OZ_NT = 64;                 // candidates per tile
 constexpr int OZ_A_SLICE = 128 * 32;      // bytes of one A digit tile (128 rows x 32 k)
 constexpr int OZ_B_SLICE = OZ_NT * 32;    // bytes of one B digit tile
-constexpr int OZ_THREADS = 192;
+constexpr int OZ_THREADS = 320;            // producer warp, issuer warp, 8 epilogue warps
 constexpr int OZ_TMEM_COLS = 512;
 
 template <int S>
@@ -105,6 +106,11 @@ __device__ __forceinline__ void oz_mma(uint32_t tmem_d, uint64_t adesc, uint64_t
         "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
+}
+__device__ __forceinline__ void oz_tmem_ld8(uint32_t taddr, uint32_t* v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr));
 }
 __device__ __forceinline__ void oz_tmem_ld16(uint32_t taddr, uint32_t* v) {
     asm volatile(
@@ -256,7 +262,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_trmm_kernel(OzParams P) {
     uint64_t* full = bars;                  // [STAGES] producer -> issuer (tx bytes)
     uint64_t* empty = bars + STAGES;        // [STAGES] issuer (tcgen05.commit) -> producer
     uint64_t* tmem_full = bars + 2 * STAGES;   // issuer -> epilogue
-    uint64_t* tmem_empty = tmem_full + 1;      // epilogue (4 warps) -> issuer
+    uint64_t* tmem_empty = tmem_full + 1;      // epilogue (8 warps) -> issuer
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 1);
     double* red = reinterpret_cast<double*>(oz_smem_raw + Cfg::RING_BYTES + 1024);  // [4][64]
 
@@ -267,7 +273,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_trmm_kernel(OzParams P) {
             oz_mbar_init(&empty[i], 1);
         }
         oz_mbar_init(tmem_full, 1);
-        oz_mbar_init(tmem_empty, 4);
+        oz_mbar_init(tmem_empty, 8);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -359,9 +365,10 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_trmm_kernel(OzParams P) {
             }
         }
     } else {
-        // ================= epilogue (warps 2..5 -> TMEM lane groups 2,3,0,1) =================
+        // ================= epilogue (warps 2..9: TMEM lane group warp & 3, candidate half (warp - 2) >> 2) =================
         const int lg = warp & 3;
-        const int et = threadIdx.x - 64;  // 0..127
+        const int hsel = (warp - 2) >> 2;
+        const int et = threadIdx.x - 64;  // 0..255
         uint32_t acc_ph = 0;
         constexpr int H = S / 2;  // levels folded into the low word
         const double hi_mul = ldexp(1.0, 8 * H);
@@ -375,12 +382,13 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_trmm_kernel(OzParams P) {
                 oz_mbar_wait(tmem_full, acc_ph);
                 oz_fence_after();
                 acc_ph ^= 1;
-                double tot[4];  // this lane's share of the column sums: candidate cc*16 + idx(lane)
+                double tot[4];  // this lane's share of the column sums: candidate hsel*32 + cc*8 + idx(lane)
 #pragma unroll
                 for (int cc = 0; cc < 4; cc++) {
-                    uint32_t r[S][16];
+                    uint32_t r[S][8];
 #pragma unroll
-                    for (int t = 0; t < S; t++) oz_tmem_ld16(tbase + ((uint32_t)(lg * 32) << 16) + (uint32_t)(t * OZ_NT + cc * 16), r[t]);
+                    for (int t = 0; t < S; t++)
+                        oz_tmem_ld8(tbase + ((uint32_t)(lg * 32) << 16) + (uint32_t)(t * OZ_NT + hsel * 32 + cc * 8), r[t]);
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                     if (cc == 3) {
                         // all TMEM reads of this item are done: hand the accumulators back to the issuer
@@ -388,9 +396,9 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_trmm_kernel(OzParams P) {
                         __syncwarp();
                         if (lane == 0) oz_mbar_arrive(tmem_empty);
                     }
-                    double v[16];
+                    double v[8];
 #pragma unroll
-                    for (int i = 0; i < 16; i++) {
+                    for (int i = 0; i < 8; i++) {
                         long long whi = 0, wlo = 0;
 #pragma unroll
                         for (int t = 0; t < S - H; t++) whi += (long long)(int32_t)r[t][i] << (8 * (S - H - 1 - t));
@@ -400,9 +408,10 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_trmm_kernel(OzParams P) {
                         double x = w * rs;
                         v[i] = x * x;
                     }
-                    // transposed butterfly: 16 values x 32 lanes -> every lane pair holds one column sum; fixed tree
+                    // transposed butterfly: 8 values x 32 lanes -> four lanes hold each column sum; the same fixed tree
+                    // over the 32 rows for every candidate (position-independent rounding)
 #pragma unroll
-                    for (int o = 16, n = 8; o >= 2; o >>= 1, n >>= 1) {
+                    for (int o = 16, n = 4; o >= 4; o >>= 1, n >>= 1) {
                         const bool up = (lane & o) != 0;
 #pragma unroll
                         for (int i = 0; i < n; i++) {
@@ -411,16 +420,17 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_trmm_kernel(OzParams P) {
                             v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
                         }
                     }
-                    tot[cc] = v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+                    double t2 = v[0] + __shfl_xor_sync(0xffffffffu, v[0], 2);
+                    tot[cc] = t2 + __shfl_xor_sync(0xffffffffu, t2, 1);
                 }
-                // candidate index held by this lane within a 16-chunk: bit4 -> 8, bit3 -> 4, bit2 -> 2, bit1 -> 1
-                const int idx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-                asm volatile("bar.sync 1, 128;" ::: "memory");  // previous item's cross-warp reduction has been consumed
-                if ((lane & 1) == 0) {
+                // candidate index held by this lane within an 8-chunk: bit4 -> 4, bit3 -> 2, bit2 -> 1
+                const int idx = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+                asm volatile("bar.sync 1, 256;" ::: "memory");  // previous item's cross-warp reduction has been consumed
+                if ((lane & 3) == 0) {
 #pragma unroll
-                    for (int cc = 0; cc < 4; cc++) red[lg * OZ_NT + cc * 16 + idx] = tot[cc];
+                    for (int cc = 0; cc < 4; cc++) red[lg * OZ_NT + hsel * 32 + cc * 8 + idx] = tot[cc];
                 }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                asm volatile("bar.sync 1, 256;" ::: "memory");
                 if (et < OZ_NT) {
                     double s = (red[et] + red[OZ_NT + et]) + (red[2 * OZ_NT + et] + red[3 * OZ_NT + et]);
                     P.part[(size_t)I * P.ldp + (size_t)ct * OZ_NT + et] = s;
