@@ -110,6 +110,36 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm)}
 
 
+def bench_lml_grad(cuda, go, cpu=True, shapes=((4096, 10), (8192, 20)), evals=5):
+    """LML + gradient evaluations per second through the C ABI (gpso_neg_lml_grad: Gram -> Cholesky -> L^-1 -> K_y^-1 ->
+    fused gradient reduction), host in / host out, at the shapes of configs C3 and C4.  Algorithmic work: N^3 flops."""
+    out = []
+    for N, d in shapes:
+        X, y = synthetic_training(N, d)
+        h = go.Hyper(0.25 * np.sqrt(d), 1.0, 1.0e-3, 0.0)
+        u = h.pack()
+        sess = cuda.open_session("Matern52", 1, True)
+        sess.set_data(X, y)
+        f, g = sess.neg_lml_and_grad(u)  # warm-up (allocations)
+        t0 = time.perf_counter()
+        dev_ms = 0.0
+        for i in range(evals):
+            f, g = sess.neg_lml_and_grad(u + 1e-3 * (i + 1))
+            dev_ms += sess.last_timing_ms()[0]
+        wall = time.perf_counter() - t0
+        rec = {"N": N, "d": d, "evals_per_s": evals / wall, "device_ms_per_eval": dev_ms / evals,
+               "fp64_tflops": (float(N) ** 3 / (dev_ms / evals * 1e-3)) / 1e12, "fp64_peak_tflops": FP64_PEAK_TFLOPS,
+               "frac_of_fp64_peak": (float(N) ** 3 / (dev_ms / evals * 1e-3)) / 1e12 / FP64_PEAK_TFLOPS, "neg_lml": f}
+        if cpu and N <= 4096:
+            t0 = time.perf_counter()
+            f_ref, g_ref = go.neg_lml_and_grad("Matern52", X, y, u + 1e-3 * evals, 1, True)
+            rec["cpu_evals_per_s"] = 1.0 / (time.perf_counter() - t0)
+            rec["lml_rel_err_vs_cpu"] = abs(f - f_ref) / max(abs(f_ref), N)
+        sess.close()
+        out.append(rec)
+    return out
+
+
 def run_reference(args, rank):
     """--impl reference: the CPU path on the host cores (rank 0 only)."""
     if rank != 0:
@@ -153,6 +183,7 @@ def main():
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--candidates", type=int, default=0, help="override the number of candidates (smoke runs only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-lml", action="store_true", help="skip the LML+grad evaluations/s side measurement")
     ap.add_argument("--engine", default="auto", choices=["auto", "dmma", "int8"],
                     help="variance-product engine: FP64 DMMA or the exact-integer int8 tcgen05 emulation (auto picks int8 at this size)")
     ap.add_argument("--no-overlap", action="store_true", help="int8 engine: run cross-covariance and product back to back")
@@ -351,6 +382,9 @@ def main():
             "setup": {"factorize_ms": factor_ms, "broadcast_ms": broadcast_ms, "state_bytes": session.state_bytes(N, d)},
             "result": {"index": int(result[0]), "mean": result[1], "var": result[2], "ucb": result[3]},
         }
+        # ---- second half of the BASELINE metric: LML + gradient evaluations per second (the L-BFGS-B closure) ---------
+        if world == 1 and not args.no_lml:
+            line["lml_grad"] = bench_lml_grad(backend.CudaBackend(device=local_rank), go, cpu=not args.no_cpu_baseline)
         # ---- CPU baseline beside it (bounded sample, rank 0, single GPU runs only) -----------------------------------
         if world == 1 and not args.no_cpu_baseline:
             sample = min(M, CPU_SAMPLE)

@@ -16,37 +16,147 @@ namespace gpso {
 // ---- diagonal block: Cholesky of the 128x128 block p, its inverse, and sum(log(diag)) ----------------------------
 // In:  K[p-block] (lower triangle used).  Out: L_pp -> K (lower), L_pp^-1 -> Linv (lower, zeros above),
 // (L_pp^-1)^T -> LinvT, logdet[p] = sum_j log(L_jj) over the real (un-padded) rows, info = first non-positive pivot.
+//
+// This kernel is the serial spine of the factorisation (one launch per 128-column panel), so it is organised to keep
+// the dependent chain short: the block is a 4x4 grid of 32x32 sub-blocks held in shared memory.
+//   * a 32x32 diagonal sub-block is factorised and inverted by ONE warp with its rows in registers (pivot broadcast by
+//     shuffle, no block barrier inside the 32 column steps);
+//   * everything else is 32x32x32 sub-block products done by four 64-thread groups in parallel (4x4 register tiles):
+//     panel  L_ip = A_ip D_pp^-T,  trailing  A_ik -= L_ip L_kp^T,  and the in-place block inverse, column by column
+//     from the right:  X_ij = -( sum_{k=j+1..i} X_ik L_kj ) X_jj.
 constexpr int DB_PITCH = TB + 1;
-constexpr int DIAG_SMEM_BYTES = (TB * DB_PITCH + TB + 8) * (int)sizeof(double);
+constexpr int SB = 32;                 // sub-block edge
+constexpr int SB_PITCH = SB + 1;
+constexpr int DIAG_SMEM_DOUBLES = TB * DB_PITCH + 4 * SB * SB_PITCH /* D^-1 */ + 3 * SB * SB_PITCH /* temporaries */ + 8;
+constexpr int DIAG_SMEM_BYTES = DIAG_SMEM_DOUBLES * (int)sizeof(double);
+
+// C(32x32) = alpha * A(32x32) * op(B) (+ C);  op(B)(k,n) = BT ? B[n][k] : B[k][n].  Executed by one 64-thread group; `bar`
+// is the group's named barrier, used when C aliases an operand (all reads of the group happen before any write).
+template <bool BT>
+__device__ __forceinline__ void sub_gemm(const double* A, int pa, const double* B, int pb, double* C, int pc, double alpha,
+                                         bool accumulate, bool in_place, int gt, int bar) {
+    const int r0 = (gt >> 3) * 4, c0 = (gt & 7) * 4;
+    double acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j] = 0.0;
+#pragma unroll 4
+    for (int k = 0; k < SB; k++) {
+        double a[4], b[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) a[i] = A[(r0 + i) * pa + k];
+#pragma unroll
+        for (int j = 0; j < 4; j++) b[j] = BT ? B[(c0 + j) * pb + k] : B[k * pb + c0 + j];
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+    }
+    if (in_place) asm volatile("bar.sync %0, 64;" ::"r"(bar) : "memory");
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            double* c = C + (r0 + i) * pc + c0 + j;
+            *c = accumulate ? fma(alpha, acc[i][j], *c) : alpha * acc[i][j];
+        }
+}
+
+// One warp: Cholesky of the 32x32 sub-block D (lower, in shared memory, pitch pd) in place, and its inverse -> Dinv
+// (pitch SB_PITCH, explicit zeros above the diagonal).  pivot_base = global 1-based index of the block's first pivot.
+// Rows / columns live in registers; the column loops are unrolled by template recursion so that every register index is
+// a compile-time constant (a plain `#pragma unroll` of the 32x32 nest is refused and spills the row to local memory).
+template <int J>
+struct CholCol {
+    static __device__ __forceinline__ void run(double (&a)[SB], int lane, int pivot_base, int* info) {
+        const double djj = __shfl_sync(0xffffffffu, a[J], J);
+        if (lane == 0 && !(djj > 0.0)) atomicCAS(info, 0, pivot_base + J);
+        const double l = sqrt(djj);
+        const double lrj = (lane > J) ? a[J] / l : (lane == J ? l : 0.0);
+        a[J] = lrj;
+#pragma unroll
+        for (int k = J + 1; k < SB; k++) {
+            const double lkj = __shfl_sync(0xffffffffu, lrj, k);
+            if (lane >= k) a[k] = fma(-lrj, lkj, a[k]);
+        }
+        CholCol<J + 1>::run(a, lane, pivot_base, info);
+    }
+};
+template <>
+struct CholCol<SB> {
+    static __device__ __forceinline__ void run(double (&)[SB], int, int, int*) {}
+};
+
+template <int R>
+struct InvRow {
+    static __device__ __forceinline__ void run(double (&x)[SB], const double* D, int pd, int lane) {
+        double s0 = (R == lane) ? 1.0 : 0.0, s1 = 0.0;
+#pragma unroll
+        for (int k = 0; k + 1 < R; k += 2) {
+            s0 = fma(-D[R * pd + k], x[k], s0);
+            s1 = fma(-D[R * pd + k + 1], x[k + 1], s1);
+        }
+        if (R & 1) s0 = fma(-D[R * pd + R - 1], x[R - 1], s0);
+        x[R] = (R >= lane) ? (s0 + s1) / D[R * pd + R] : 0.0;
+        InvRow<R + 1>::run(x, D, pd, lane);
+    }
+};
+template <>
+struct InvRow<SB> {
+    static __device__ __forceinline__ void run(double (&)[SB], const double*, int, int) {}
+};
+
+__device__ __forceinline__ void chol_inv_32(double* D, int pd, double* Dinv, int lane, int pivot_base, int* info) {
+    double a[SB];
+#pragma unroll
+    for (int k = 0; k < SB; k++) a[k] = (k <= lane) ? D[lane * pd + k] : 0.0;
+    CholCol<0>::run(a, lane, pivot_base, info);
+#pragma unroll
+    for (int k = 0; k < SB; k++)
+        if (k <= lane) D[lane * pd + k] = a[k];
+    __syncwarp();
+    // inverse: lane c owns column c of X = D^-1;  X[r][c] = (delta_rc - sum_{k<r} D[r][k] X[k][c]) / D[r][r]
+    double x[SB];
+    InvRow<0>::run(x, D, pd, lane);
+#pragma unroll
+    for (int r = 0; r < SB; r++) Dinv[r * SB_PITCH + lane] = x[r];
+}
 
 __global__ void __launch_bounds__(256) diag_factor_inverse_kernel(double* __restrict__ K, double* __restrict__ Linv,
                                                                   double* __restrict__ LinvT, int Np, int p, int N,
                                                                   double* __restrict__ logdet, int* __restrict__ info) {
     extern __shared__ double sm[];
-    double* S = sm;                       // [TB][DB_PITCH]
-    double* col = sm + TB * DB_PITCH;     // [TB] saved column
-    double* red = col + TB;               // [8]
+    double* S = sm;                                  // [TB][DB_PITCH]
+    double* Dinv = sm + TB * DB_PITCH;               // [4][SB][SB_PITCH] inverses of the diagonal sub-blocks
+    double* Tmp = Dinv + 4 * SB * SB_PITCH;          // [3][SB][SB_PITCH]
+    double* red = Tmp + 3 * SB * SB_PITCH;           // [8]
     const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int grp = tid >> 6, gt = tid & 63;         // 64-thread group and index inside it
+    const int bar = 1 + grp;
     const size_t base = (size_t)p * TB * Np + (size_t)p * TB;
     for (int e = tid; e < TB * TB; e += 256) {
         int r = e >> 7, c = e & 127;
         S[r * DB_PITCH + c] = K[base + (size_t)r * Np + c];
     }
     __syncthreads();
-    // ---- right-looking Cholesky, one column per step ----
-    const int ri = tid >> 1, rh = tid & 1;  // row handled in the rank-1 update, half of its columns
-    for (int j = 0; j < TB; j++) {
-        double djj = S[j * DB_PITCH + j];
-        if (tid == 0 && !(djj > 0.0)) atomicCAS(info, 0, p * TB + j + 1);
-        double l = sqrt(djj);
-        __syncthreads();  // everybody has read the pivot
-        if (tid == 0) S[j * DB_PITCH + j] = l;
-        if (tid > j && tid < TB) S[tid * DB_PITCH + j] = S[tid * DB_PITCH + j] / l;
+#define SBLK(i, k) (S + (i) * SB * DB_PITCH + (k) * SB)
+    // ---- blocked right-looking Cholesky over the 4 sub-block columns ----
+    for (int pb = 0; pb < 4; pb++) {
+        if (warp == 0) chol_inv_32(SBLK(pb, pb), DB_PITCH, Dinv + pb * SB * SB_PITCH, lane, p * TB + pb * SB + 1, info);
         __syncthreads();
-        if (ri > j) {
-            double lij = S[ri * DB_PITCH + j];
-            for (int k = j + 1 + rh; k <= ri; k += 2) S[ri * DB_PITCH + k] = fma(-lij, S[k * DB_PITCH + j], S[ri * DB_PITCH + k]);
-        }
+        // panel: L_ip = A_ip * D^-T, in place
+        if (pb + 1 + grp < 4)
+            sub_gemm<true>(SBLK(pb + 1 + grp, pb), DB_PITCH, Dinv + pb * SB * SB_PITCH, SB_PITCH, SBLK(pb + 1 + grp, pb), DB_PITCH, 1.0,
+                           false, true, gt, bar);
+        __syncthreads();
+        // trailing: A_ik -= L_ip L_kp^T for pb < k <= i
+        int q = 0;
+        for (int i = pb + 1; i < 4; i++)
+            for (int k = pb + 1; k <= i; k++, q++)
+                if ((q & 3) == grp)
+                    sub_gemm<true>(SBLK(i, pb), DB_PITCH, SBLK(k, pb), DB_PITCH, SBLK(i, k), DB_PITCH, -1.0, true, false, gt, bar);
         __syncthreads();
     }
     // log-determinant contribution (fixed order) and write L back
@@ -61,31 +171,36 @@ __global__ void __launch_bounds__(256) diag_factor_inverse_kernel(double* __rest
         if (c <= r) K[base + (size_t)r * Np + c] = S[r * DB_PITCH + c];
     }
     __syncthreads();
-    // ---- in-place inverse of the lower-triangular block, last column first ----
-    // X[i][j] = -x_jj * sum_{k=j+1..i} X[i][k] * L[k][j] ; columns > j already hold X, column j still holds L.
-    for (int j = TB - 1; j >= 0; j--) {
-        double xjj = 1.0 / S[j * DB_PITCH + j];
-        if (tid < TB) col[tid] = (tid > j) ? S[tid * DB_PITCH + j] : 0.0;
+    // ---- in-place block inverse, block columns from the right; diagonal blocks live in Dinv ----
+    for (int j = 2; j >= 0; j--) {
+        // T_i = sum_{k=j+1..i} X_ik L_kj   (X_ii = Dinv[i], X_ik = S block (i,k) already inverted)
+        const int i = j + 1 + grp;
+        if (i < 4) {
+            double* T = Tmp + grp * SB * SB_PITCH;
+            for (int k = j + 1; k <= i; k++) {
+                const double* X = (k == i) ? Dinv + i * SB * SB_PITCH : SBLK(i, k);
+                const int px = (k == i) ? SB_PITCH : DB_PITCH;
+                sub_gemm<false>(X, px, SBLK(k, j), DB_PITCH, T, SB_PITCH, 1.0, k > j + 1, false, gt, bar);
+            }
+        }
         __syncthreads();
-        double acc = 0.0;
-        if (ri > j) {
-            for (int k = j + 1 + rh; k <= ri; k += 2) acc = fma(S[ri * DB_PITCH + k], col[k], acc);
-        }
-        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-        if (rh == 0) {
-            if (ri > j) S[ri * DB_PITCH + j] = -xjj * acc;
-            else if (ri == j) S[j * DB_PITCH + j] = xjj;
-        }
+        // X_ij = -T_i X_jj
+        if (i < 4)
+            sub_gemm<false>(Tmp + grp * SB * SB_PITCH, SB_PITCH, Dinv + j * SB * SB_PITCH, SB_PITCH, SBLK(i, j), DB_PITCH, -1.0, false,
+                            false, gt, bar);
         __syncthreads();
     }
+#undef SBLK
     for (int e = tid; e < TB * TB; e += 256) {
         int r = e >> 7, c = e & 127;
-        double v = (c <= r) ? S[r * DB_PITCH + c] : 0.0;
+        double v = 0.0;
+        if (c <= r) v = ((r >> 5) == (c >> 5)) ? Dinv[(r >> 5) * SB * SB_PITCH + (r & 31) * SB_PITCH + (c & 31)] : S[r * DB_PITCH + c];
         Linv[base + (size_t)r * Np + c] = v;
     }
     for (int e = tid; e < TB * TB; e += 256) {
         int r = e >> 7, c = e & 127;  // LinvT[r][c] = Linv[c][r]
-        double v = (r <= c) ? S[c * DB_PITCH + r] : 0.0;
+        double v = 0.0;
+        if (r <= c) v = ((r >> 5) == (c >> 5)) ? Dinv[(r >> 5) * SB * SB_PITCH + (c & 31) * SB_PITCH + (r & 31)] : S[c * DB_PITCH + r];
         LinvT[base + (size_t)r * Np + c] = v;
     }
 }

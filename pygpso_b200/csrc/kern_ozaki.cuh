@@ -85,6 +85,19 @@ __device__ __forceinline__ void oz_bulk_g2s(void* dst, const void* src, uint32_t
                  "l"(src), "r"(bytes), "r"(oz_smem(bar))
                  : "memory");
 }
+// same copy with an L2 eviction-priority hint (createpolicy): the A digits of L^-1 are re-read by every candidate tile of
+// every window and must survive the 2 GB of B digits that stream through L2 per window
+__device__ __forceinline__ void oz_bulk_g2s_hint(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                     oz_smem(dst)),
+                 "l"(src), "r"(bytes), "r"(oz_smem(bar)), "l"(policy)
+                 : "memory");
+}
+__device__ __forceinline__ uint64_t oz_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
 __device__ __forceinline__ void oz_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(oz_smem(bar)) : "memory");
 }
@@ -294,6 +307,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_trmm_kernel(OzParams P) {
         if (lane == 0) {
             int st = 0;
             uint32_t ph = 0;
+            const uint64_t keep = oz_policy_evict_last();
             for (long long u = blockIdx.x; u < units; u += gridDim.x) {
                 const long long ct = u / npairs;
                 const int j = (int)(u - ct * npairs);
@@ -307,7 +321,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_trmm_kernel(OzParams P) {
                         oz_mbar_wait(&empty[st], ph ^ 1);
                         uint8_t* dst = ring + (size_t)st * Cfg::STAGE_BYTES;
                         oz_mbar_expect_tx(&full[st], Cfg::STAGE_BYTES);
-                        oz_bulk_g2s(dst, a + (size_t)ks * S * OZ_A_SLICE, S * OZ_A_SLICE, &full[st]);
+                        oz_bulk_g2s_hint(dst, a + (size_t)ks * S * OZ_A_SLICE, S * OZ_A_SLICE, &full[st], keep);
                         oz_bulk_g2s(dst + S * OZ_A_SLICE, b + (size_t)ks * S * OZ_B_SLICE, S * OZ_B_SLICE, &full[st]);
                         if (++st == STAGES) {
                             st = 0;
