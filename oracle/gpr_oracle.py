@@ -54,7 +54,9 @@ def softplus(u):
 
 def softplus_inv(v):
     v = np.asarray(v, dtype=np.float64)
-    return np.log(np.expm1(v))
+    # log(expm1(v)); beyond v = 30 the overflow-free form v + log1p(-exp(-v)) (tfp.math.softplus_inverse is stable too)
+    small = np.minimum(v, 30.0)
+    return np.where(v > 30.0, v + np.log1p(-np.exp(-np.maximum(v, 30.0))), np.log(np.expm1(small)))
 
 
 def sigmoid(u):

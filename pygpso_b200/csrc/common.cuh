@@ -37,25 +37,57 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
 
+// ---- exp(-s) for s >= 0 -----------------------------------------------------------------------------------------------
+// Every covariance function on the path evaluates exp of a non-positive argument.  Branch-free Cody-Waite reduction
+// (n = rint(-s log2 e) by the 1.5*2^52 trick, r = -s - n ln2 in two FMAs) and a degree-13 Horner polynomial; the result
+// is scaled by adding n to the exponent field.  19 FP64-pipe operations against ~26 DFMA-equivalents of exp()
+// (profiles/r01_fp64_probe.txt) and no per-call constant materialisation; max relative error 2.2e-16 on [0, 690]
+// (the same as libm's exp against long double), exactly 1 at s = 0, 0 beyond s = 700 (true value < 1e-304), NaN -> NaN.
+__device__ __forceinline__ double exp_neg(double s) {
+    const double MAGIC = 6755399441055744.0;
+    double t = fma(-s, 1.4426950408889634074, MAGIC);
+    double nf = t - MAGIC;
+    int n = __double2loint(t);
+    double r = fma(-nf, 6.93147180369123816490e-01, -s);
+    r = fma(-nf, 1.90821492927058770002e-10, r);
+    double p = 1.0 / 6227020800.0;
+    p = fma(p, r, 1.0 / 479001600.0);
+    p = fma(p, r, 1.0 / 39916800.0);
+    p = fma(p, r, 1.0 / 3628800.0);
+    p = fma(p, r, 1.0 / 362880.0);
+    p = fma(p, r, 1.0 / 40320.0);
+    p = fma(p, r, 1.0 / 5040.0);
+    p = fma(p, r, 1.0 / 720.0);
+    p = fma(p, r, 1.0 / 120.0);
+    p = fma(p, r, 1.0 / 24.0);
+    p = fma(p, r, 1.0 / 6.0);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    double v = __longlong_as_double(__double_as_longlong(p) + ((long long)n << 52));
+    v = (s > 700.0) ? 0.0 : v;
+    return (s != s) ? s : v;
+}
+
 // ---- covariance functions (gpflow.kernels.stationaries) ----------------------------------------------------------
 // r2 = scaled squared distance (inputs already divided by the lengthscale), var = kernel variance
 template <int KID>
 __device__ __forceinline__ double cov_from_r2(double r2, double var) {
     if (KID == KERNEL_SE) {
-        return var * exp(-0.5 * r2);
+        return var * exp_neg(0.5 * r2);
     } else {
         double r = sqrt(clip_r2(r2));
         if (KID == KERNEL_MATERN52) {
             const double s5 = 2.23606797749978969641;
             double sr = s5 * r;
             // variance * (1 + sqrt5 r + 5/3 r^2) * exp(-sqrt5 r), GPflow's evaluation order
-            return var * (1.0 + sr + (5.0 / 3.0) * (r * r)) * exp(-sr);
+            return var * (1.0 + sr + (5.0 / 3.0) * (r * r)) * exp_neg(sr);
         } else if (KID == KERNEL_MATERN32) {
             const double s3 = 1.73205080756887729353;
             double sr = s3 * r;
-            return var * (1.0 + sr) * exp(-sr);
+            return var * (1.0 + sr) * exp_neg(sr);
         } else {
-            return var * exp(-r);
+            return var * exp_neg(r);
         }
     }
 }
@@ -65,7 +97,7 @@ __device__ __forceinline__ double cov_from_r2(double r2, double var) {
 template <int KID>
 __device__ __forceinline__ void cov_and_radial(double r2, double var, double& k, double& g) {
     if (KID == KERNEL_SE) {
-        k = var * exp(-0.5 * r2);
+        k = var * exp_neg(0.5 * r2);
         g = k;
     } else {
         bool live = r2 > R2_CLIP;
@@ -73,17 +105,17 @@ __device__ __forceinline__ void cov_and_radial(double r2, double var, double& k,
         if (KID == KERNEL_MATERN52) {
             const double s5 = 2.23606797749978969641;
             double sr = s5 * r;
-            double e = exp(-sr);
+            double e = exp_neg(sr);
             k = var * (1.0 + sr + (5.0 / 3.0) * (r * r)) * e;
             g = live ? (5.0 / 3.0) * var * (1.0 + sr) * e : 0.0;
         } else if (KID == KERNEL_MATERN32) {
             const double s3 = 1.73205080756887729353;
             double sr = s3 * r;
-            double e = exp(-sr);
+            double e = exp_neg(sr);
             k = var * (1.0 + sr) * e;
             g = live ? 3.0 * var * e : 0.0;
         } else {
-            k = var * exp(-r);
+            k = var * exp_neg(r);
             g = live ? k / r : 0.0;
         }
     }

@@ -72,8 +72,9 @@ struct CholCol {
     static __device__ __forceinline__ void run(double (&a)[SB], int lane, int pivot_base, int* info) {
         const double djj = __shfl_sync(0xffffffffu, a[J], J);
         if (lane == 0 && !(djj > 0.0)) atomicCAS(info, 0, pivot_base + J);
-        const double l = sqrt(djj);
-        const double lrj = (lane > J) ? a[J] / l : (lane == J ? l : 0.0);
+        // reciprocal square root + one multiply instead of sqrt + divide on the dependent chain (<= 1 ulp apart)
+        const double il = rsqrt(djj);
+        const double lrj = (lane > J) ? a[J] * il : (lane == J ? djj * il : 0.0);
         a[J] = lrj;
 #pragma unroll
         for (int k = J + 1; k < SB; k++) {
@@ -90,7 +91,7 @@ struct CholCol<SB> {
 
 template <int R>
 struct InvRow {
-    static __device__ __forceinline__ void run(double (&x)[SB], const double* D, int pd, int lane) {
+    static __device__ __forceinline__ void run(double (&x)[SB], const double* D, int pd, int lane, double rdiag) {
         double s0 = (R == lane) ? 1.0 : 0.0, s1 = 0.0;
 #pragma unroll
         for (int k = 0; k + 1 < R; k += 2) {
@@ -98,13 +99,14 @@ struct InvRow {
             s1 = fma(-D[R * pd + k + 1], x[k + 1], s1);
         }
         if (R & 1) s0 = fma(-D[R * pd + R - 1], x[R - 1], s0);
-        x[R] = (R >= lane) ? (s0 + s1) / D[R * pd + R] : 0.0;
-        InvRow<R + 1>::run(x, D, pd, lane);
+        const double rd = __shfl_sync(0xffffffffu, rdiag, R);  // executed by all lanes (never inside the select below)
+        x[R] = (R >= lane) ? (s0 + s1) * rd : 0.0;
+        InvRow<R + 1>::run(x, D, pd, lane, rdiag);
     }
 };
 template <>
 struct InvRow<SB> {
-    static __device__ __forceinline__ void run(double (&)[SB], const double*, int, int) {}
+    static __device__ __forceinline__ void run(double (&)[SB], const double*, int, int, double) {}
 };
 
 __device__ __forceinline__ void chol_inv_32(double* D, int pd, double* Dinv, int lane, int pivot_base, int* info) {
@@ -118,7 +120,8 @@ __device__ __forceinline__ void chol_inv_32(double* D, int pd, double* Dinv, int
     __syncwarp();
     // inverse: lane c owns column c of X = D^-1;  X[r][c] = (delta_rc - sum_{k<r} D[r][k] X[k][c]) / D[r][r]
     double x[SB];
-    InvRow<0>::run(x, D, pd, lane);
+    const double rdiag = 1.0 / D[lane * pd + lane];  // all 32 reciprocals at once, broadcast by shuffle when needed
+    InvRow<0>::run(x, D, pd, lane, rdiag);
 #pragma unroll
     for (int r = 0; r < SB; r++) Dinv[r * SB_PITCH + lane] = x[r];
 }
@@ -136,6 +139,7 @@ __global__ void __launch_bounds__(256) diag_factor_inverse_kernel(double* __rest
     const int grp = tid >> 6, gt = tid & 63;         // 64-thread group and index inside it
     const int bar = 1 + grp;
     const size_t base = (size_t)p * TB * Np + (size_t)p * TB;
+#pragma unroll 16
     for (int e = tid; e < TB * TB; e += 256) {
         int r = e >> 7, c = e & 127;
         S[r * DB_PITCH + c] = K[base + (size_t)r * Np + c];

@@ -37,7 +37,10 @@ def _softplus(u):
 
 
 def _softplus_inv(v):
-    return np.log(np.expm1(v))
+    # log(expm1(v)); beyond v = 30 the overflow-free form v + log1p(-exp(-v)) (tfp.math.softplus_inverse is stable too)
+    v = np.asarray(v, dtype=np.float64)
+    small = np.minimum(v, 30.0)
+    return np.where(v > 30.0, v + np.log1p(-np.exp(-np.maximum(v, 30.0))), np.log(np.expm1(small)))
 
 
 class _Shape(tuple):

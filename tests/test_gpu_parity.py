@@ -391,6 +391,37 @@ def test_end_to_end_sample_method_runs_on_gpu():
     assert best.score_mu > 5.0
 
 
+def rastrigin_max(point):
+    """Config C5 objective: Rastrigin turned into a maximisation problem (domain shifted so that the optimum is not the
+    centre of the box, which is always the first point evaluated)."""
+    x = np.asarray(point, dtype=np.float64)
+    return -(10.0 * x.size + np.sum(x * x - 10.0 * np.cos(2.0 * np.pi * x)))
+
+
+def _rastrigin_run(backend_obj, d, depth, budget):
+    space = ParameterSpace(parameter_names=[f"p{i}" for i in range(d)], parameter_bounds=[[-4.1, 5.12]] * d)
+    opt = GPSOptimiser(parameter_space=space, gp_surrogate=GPRSurrogate.default(backend=backend_obj), exploration_method="tree",
+                       exploration_depth=depth, budget=budget, stopping_condition="evaluations", update_cycle=1, n_workers=1)
+    best = opt.run(rastrigin_max)
+    evaluated = [(tuple(np.round(pt.normed_coord, 12)), pt.score_mu) for pt in opt.gp_surr.points if pt.label.name == "evaluated"]
+    return opt, best, evaluated
+
+
+def test_c5_rastrigin_10d_same_decisions_as_oracle_run():
+    """Config C5 (10-D Rastrigin, ternary tree) at reduced depth/budget: the optimiser driven by the CUDA library must take
+    the same decisions (same evaluated points in the same order, same best point) as the same loop driven by the oracle."""
+    from tests.oracle_backend import OracleBackend
+
+    d, depth, budget = 10, 6, 60
+    opt_g, best_g, ev_g = _rastrigin_run(None, d, depth, budget)
+    opt_o, best_o, ev_o = _rastrigin_run(OracleBackend(), d, depth, budget)
+    assert opt_g.n_eval_counter == opt_o.n_eval_counter and opt_g.iterations == opt_o.iterations
+    assert [e[0] for e in ev_g] == [e[0] for e in ev_o]
+    assert [e[1] for e in ev_g] == [e[1] for e in ev_o]
+    np.testing.assert_array_equal(best_g.normed_coord, best_o.normed_coord)
+    assert best_g.score_mu == best_o.score_mu
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # full-size configuration (BASELINE config C3 shape): size-independent properties
 # ---------------------------------------------------------------------------------------------------------------------
