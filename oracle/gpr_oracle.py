@@ -191,7 +191,9 @@ def neg_lml_and_grad(kernel, X, y, u, n_ls, has_mean):
     else:
         # scalar lengthscale: sum_j Delta_j^2 / ls^3 = r2 * ls^2 / ls^3 = r2 / ls  (r2 un-clipped, >= 0 enforced)
         d_ls = np.array([0.5 * np.sum(WG * np.maximum(r2, 0.0)) / ls[0]])
-    d_var = 0.5 * np.sum(W * K) / h.variance
+    # TF autodiff gives 0.5*sum(W*k_unit) * sigmoid(u); when softplus(u) underflows to 0 the chain factor is 0 as well, so the
+    # reference's gradient entry is exactly 0 there (not 0/0) -- L-BFGS-B line searches do visit such points (config C5).
+    d_var = 0.5 * np.sum(W * K) / h.variance if h.variance > 0.0 else 0.0
     d_noise = 0.5 * np.trace(W)
     grad_theta = list(d_ls) + [d_var, d_noise]
     chain = list(sigmoid(u[:n_ls])) + [sigmoid(u[n_ls]), sigmoid(u[n_ls + 1])]

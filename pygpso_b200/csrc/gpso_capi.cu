@@ -294,6 +294,12 @@ static int ensure_shape(gpso_handle* h, int N, int d) {
     GP_TRY(h->info.ensure(sizeof(int)));
     GP_TRY(h->counter.ensure(sizeof(int)));
     GP_TRY(h->running.ensure(sizeof(BestRec)));
+    if (Np != h->Np) {
+        // the factor kernels never write the structural zeros of L^-1 / L^-T inside diagonal blocks: clear both buffers
+        // whenever the row pitch changes (a buffer that was large enough is reused with a different layout)
+        CU_TRY(cudaMemset(h->Linv.p, 0, mat));
+        CU_TRY(cudaMemset(h->LinvT.p, 0, mat));
+    }
     h->N = N;
     h->d = d;
     h->Np = Np;
@@ -328,8 +334,8 @@ static int factor_pipeline(gpso_handle* h, cudaStream_t st, bool need_kinv) {
     P.p = 0;
     P.s = 0;
     for (int p = 0; p < nb; p++) {
-        diag_factor_inverse_kernel<<<1, 256, DIAG_SMEM_BYTES, st>>>(P.K, P.Linv, P.LinvT, Np, p, h->N, h->logdet.as<double>(),
-                                                                    h->info.as<int>());
+        diag_factor_inverse_kernel<<<1, DIAG_THREADS, DIAG_SMEM_BYTES, st>>>(P.K, P.Linv, Np, p, h->N, h->logdet.as<double>(),
+                                                                             h->info.as<int>());
         GP_TRY(check_launch(h, "diag_factor_inverse"));
         int nt = nb - 1 - p;
         if (nt > 0) {
@@ -340,6 +346,8 @@ static int factor_pipeline(gpso_handle* h, cudaStream_t st, bool need_kinv) {
             GP_TRY(check_launch(h, "chol_trailing"));
         }
     }
+    diag_transpose_kernel<<<nb, 256, 0, st>>>(P.Linv, P.LinvT, Np);
+    GP_TRY(check_launch(h, "diag_transpose"));
     if (nb > 1) {
         GP_TRY(h->T.ensure((size_t)Np * Np * sizeof(double), true));
         P.T = h->T.as<double>();
@@ -531,7 +539,7 @@ extern "C" int gpso_set_data(gpso_handle* h, const double* X_host, const double*
     return 0;
 }
 
-static int load_theta(gpso_handle* h, const double* theta, int p, const char* who) {
+static int load_theta(gpso_handle* h, const double* theta, int p, const char* who, bool allow_zero = false) {
     if (p != h->n_params()) {
         char b[256];
         snprintf(b, sizeof b, "%s: expected %d hyper-parameters, got %d", who, h->n_params(), p);
@@ -539,12 +547,14 @@ static int load_theta(gpso_handle* h, const double* theta, int p, const char* wh
     }
     int nl = h->n_ls();
     for (int i = 0; i < nl; i++) {
-        if (!(theta[i] > 0.0)) return fail(GPSO_E_BADARG, std::string(who) + ": lengthscale must be positive");
+        if (!(theta[i] > 0.0) && !(allow_zero && theta[i] == 0.0))
+            return fail(GPSO_E_BADARG, std::string(who) + ": lengthscale must be positive");
         h->ls_host[i] = theta[i];
     }
     h->variance = theta[nl];
     h->noise = theta[nl + 1];
-    if (!(h->variance > 0.0) || !(h->noise > 0.0)) return fail(GPSO_E_BADARG, std::string(who) + ": variances must be positive");
+    if (!(h->variance > 0.0 || (allow_zero && h->variance == 0.0)) || !(h->noise > 0.0))
+        return fail(GPSO_E_BADARG, std::string(who) + ": variances must be positive");
     h->c0 = (h->mean_id == GPSO_MEAN_CONSTANT) ? theta[nl + 2] : 0.0;
     return 0;
 }
@@ -560,7 +570,9 @@ extern "C" int gpso_neg_lml_grad(gpso_handle* h, const double* u, int p, double*
     theta[nl] = softplus(u[nl]);
     theta[nl + 1] = NOISE_FLOOR + softplus(u[nl + 1]);
     if (h->mean_id == GPSO_MEAN_CONSTANT) theta[nl + 2] = u[nl + 2];
-    GP_TRY(load_theta(h, theta.data(), p, "gpso_neg_lml_grad"));
+    // softplus(u) underflows to exactly 0 for u < -745 and L-BFGS-B line searches do probe such points: like GPflow, evaluate
+    // them (kernel variance 0 -> K_y = noise * I; lengthscale 0 -> NaN objective) instead of rejecting the call
+    GP_TRY(load_theta(h, theta.data(), p, "gpso_neg_lml_grad", true));
     h->factorized = false;
     cudaStream_t st = h->stream;
     CU_TRY(cudaEventRecord(h->ev_t0, st));
@@ -595,7 +607,8 @@ extern "C" int gpso_neg_lml_grad(gpso_handle* h, const double* u, int p, double*
     *f_host = nlml_from_scalars(h, sc);
     // dLML/dtheta = 0.5 * sum W * dK/dtheta ; chain through softplus: dtheta/du = sigmoid(u)
     for (int i = 0; i < nl; i++) grad_host[i] = -(0.5 * g[2 + i] / h->ls_host[i]) * sigmoid(u[i]);
-    grad_host[nl] = -(0.5 * g[0] / h->variance) * sigmoid(u[nl]);
+    // variance == 0 only when softplus underflowed, where the chain factor sigmoid(u) is 0 too: the entry is 0, not 0/0
+    grad_host[nl] = h->variance > 0.0 ? -(0.5 * g[0] / h->variance) * sigmoid(u[nl]) : 0.0;
     grad_host[nl + 1] = -(0.5 * g[1]) * sigmoid(u[nl + 1]);
     if (h->mean_id == GPSO_MEAN_CONSTANT) grad_host[nl + 2] = -sc[2];
     return 0;

@@ -14,199 +14,345 @@
 namespace gpso {
 
 // ---- diagonal block: Cholesky of the 128x128 block p, its inverse, and sum(log(diag)) ----------------------------
-// In:  K[p-block] (lower triangle used).  Out: L_pp -> K (lower), L_pp^-1 -> Linv (lower, zeros above),
-// (L_pp^-1)^T -> LinvT, logdet[p] = sum_j log(L_jj) over the real (un-padded) rows, info = first non-positive pivot.
+// In:  K[p-block] (lower triangle used).  Out: L_pp -> K (lower; the entries above the diagonal of the four diagonal
+// sub-blocks receive unused values), L_pp^-1 -> Linv (lower; the zero sub-blocks above the diagonal are never written, the
+// buffer is cleared when it is (re)shaped), logdet[p] = sum_j log(L_jj) over the real (un-padded) rows, info = first
+// non-positive pivot.  (L_pp^-1)^T -> LinvT is produced for all panels at once by diag_transpose_kernel.
 //
-// This kernel is the serial spine of the factorisation (one launch per 128-column panel), so it is organised to keep
-// the dependent chain short: the block is a 4x4 grid of 32x32 sub-blocks held in shared memory.
-//   * a 32x32 diagonal sub-block is factorised and inverted by ONE warp with its rows in registers (pivot broadcast by
-//     shuffle, no block barrier inside the 32 column steps);
-//   * everything else is 32x32x32 sub-block products done by four 64-thread groups in parallel (4x4 register tiles):
-//     panel  L_ip = A_ip D_pp^-T,  trailing  A_ik -= L_ip L_kp^T,  and the in-place block inverse, column by column
-//     from the right:  X_ij = -( sum_{k=j+1..i} X_ik L_kj ) X_jj.
-constexpr int DB_PITCH = TB + 1;
+// This kernel is the serial spine of the factorisation (one launch per 128-column panel), so it is organised around its
+// dependent chain.  The block is a 4x4 grid of 32x32 sub-blocks in shared memory (row pitch 132: every DMMA fragment load
+// is bank-conflict free).  Per sub-block column pb:
+//   P1  warp 0 factorises the 32x32 diagonal sub-block AND inverts it in the same 32 column steps (rows of A and the
+//       running sums of the inverse live in registers; each column is broadcast through shared memory -- no shuffles, one
+//       __syncwarp per column; the inverse chain fills the latency bubbles of the Cholesky chain).  Meanwhile warps 1-7
+//       accumulate T_pb,j = sum_k L_pb,k X_kj, the row pb of the block inverse, from finished blocks (DMMA).
+//   P2  panel  L_i,pb = A_i,pb X_pb,pb^T (i > pb)  and  X_pb,j = -X_pb,pb T_pb,j (j < pb), 8x32 DMMA strips over all warps
+//   P3  trailing update  A_ik -= L_i,pb L_k,pb^T  (pb < k <= i), DMMA strips over all warps
+// Measured on B200 (tools/microbench/diag_probe.cu): the previous shuffle-based version spent 28-38k cycles in each of the
+// four warp-level factorisations (every __shfl_sync compiled to WARPSYNC + SHFL + ENDCOLLECTIVE) and 113 us in total.
+#ifndef DIAG_STAMP
+#define DIAG_STAMP(i)
+#define DIAG_STAMP_W(w, i)
+#endif
+constexpr int DIAG_THREADS = 256;
+constexpr int DP = TB + 4;             // row pitch of the 128x128 block (== 4 mod 16)
 constexpr int SB = 32;                 // sub-block edge
-constexpr int SB_PITCH = SB + 1;
-constexpr int DIAG_SMEM_DOUBLES = TB * DB_PITCH + 4 * SB * SB_PITCH /* D^-1 */ + 3 * SB * SB_PITCH /* temporaries */ + 8;
+constexpr int SP = SB + 4;             // row pitch of stand-alone 32x32 tiles (== 4 mod 16)
+// the inverse is kept as a "staircase": sub-block row k holds k+1 sub-blocks with row pitch XP(k) (== 4 mod 16)
+__host__ __device__ constexpr int XP(int k) { return SB * (k + 1) + 4; }
+__host__ __device__ constexpr int XO(int k) { return SB * (16 * k * (k + 1) + 4 * k); }
+constexpr int DIAG_SMEM_DOUBLES = TB * DP + XO(4) /* inverse */ + 4 * SB /* column + diagonal broadcast, x2 */;
 constexpr int DIAG_SMEM_BYTES = DIAG_SMEM_DOUBLES * (int)sizeof(double);
 
-// C(32x32) = alpha * A(32x32) * op(B) (+ C);  op(B)(k,n) = BT ? B[n][k] : B[k][n].  Executed by one 64-thread group; `bar`
-// is the group's named barrier, used when C aliases an operand (all reads of the group happen before any write).
-template <bool BT>
-__device__ __forceinline__ void sub_gemm(const double* A, int pa, const double* B, int pb, double* C, int pc, double alpha,
-                                         bool accumulate, bool in_place, int gt, int bar) {
-    const int r0 = (gt >> 3) * 4, c0 = (gt & 7) * 4;
-    double acc[4][4];
-#pragma unroll
-    for (int i = 0; i < 4; i++)
-#pragma unroll
-        for (int j = 0; j < 4; j++) acc[i][j] = 0.0;
-#pragma unroll 4
-    for (int k = 0; k < SB; k++) {
-        double a[4], b[4];
-#pragma unroll
-        for (int i = 0; i < 4; i++) a[i] = A[(r0 + i) * pa + k];
-#pragma unroll
-        for (int j = 0; j < 4; j++) b[j] = BT ? B[(c0 + j) * pb + k] : B[k * pb + c0 + j];
-#pragma unroll
-        for (int i = 0; i < 4; i++)
-#pragma unroll
-            for (int j = 0; j < 4; j++) acc[i][j] = fma(a[i], b[j], acc[i][j]);
-    }
-    if (in_place) asm volatile("bar.sync %0, 64;" ::"r"(bar) : "memory");
-#pragma unroll
-    for (int i = 0; i < 4; i++)
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            double* c = C + (r0 + i) * pc + c0 + j;
-            *c = accumulate ? fma(alpha, acc[i][j], *c) : alpha * acc[i][j];
-        }
+// 1/sqrt(d) and 1/d together: hardware seed y (MUFU.RSQ64H, ~2^-22) and e = 1 - d y^2, then
+//   1/sqrt(d) = y (1 + e/2 + 3e^2/8),   1/d = y^2 (1 + e + e^2)        (neglected terms ~ e^3 < 2^-64)
+// Four dependent FP64 operations after the seed for either result.  d <= 0 / NaN -> inf / NaN.
+__device__ __forceinline__ double rsqrt_seed(double d) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    return y;
+}
+__device__ __forceinline__ void rsqrt_rcp_finish(double d, double y, double& il, double& ild) {
+    const double t = d * y;
+    const double y2 = y * y;
+    const double e = fma(-t, y, 1.0);
+    const double q = y * e;
+    const double pl = fma(0.375, e, 0.5);
+    const double ee = fma(e, e, e);
+    il = fma(q, pl, y);
+    ild = fma(y2, ee, y2);
+}
+__device__ __forceinline__ void rsqrt_rcp_fast(double d, double& il, double& ild) { rsqrt_rcp_finish(d, rsqrt_seed(d), il, ild); }
+__device__ __forceinline__ double rsqrt_fast(double d) {
+    double il, ild;
+    rsqrt_rcp_fast(d, il, ild);
+    return il;
 }
 
-// One warp: Cholesky of the 32x32 sub-block D (lower, in shared memory, pitch pd) in place, and its inverse -> Dinv
-// (pitch SB_PITCH, explicit zeros above the diagonal).  pivot_base = global 1-based index of the block's first pivot.
-// Rows / columns live in registers; the column loops are unrolled by template recursion so that every register index is
-// a compile-time constant (a plain `#pragma unroll` of the 32x32 nest is refused and spills the row to local memory).
+// shared-memory accesses of the column broadcast: volatile asm keeps them ordered around the warp barrier while the
+// compiler stays free to schedule the register arithmetic of one column into the latency gaps of the next
+__device__ __forceinline__ double lds_f64(unsigned addr) {
+    double v;
+    asm volatile("ld.volatile.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void lds_v2f64(unsigned addr, double& x, double& y) {
+    asm volatile("ld.volatile.shared.v2.f64 {%0,%1}, [%2];" : "=d"(x), "=d"(y) : "r"(addr));
+}
+__device__ __forceinline__ void sts_f64(unsigned addr, double v) { asm volatile("st.volatile.shared.f64 [%0], %1;" ::"r"(addr), "d"(v)); }
+__device__ __forceinline__ void warp_bar() { asm volatile("bar.warp.sync 0xffffffff;"); }
+
+// One warp, 32 column steps (compile-time unrolled by template recursion so that every register index is a constant and
+// the whole factorisation is one basic block).
+//   a[k] = row `lane` of the sub-block (lower part), becomes row `lane` of L;  dg = the lane's own diagonal entry
+//   s[k] = sum_{j<k} L[k][j] X[j][lane]  (lane owns column `lane` of X = L^-1)
+// Column J of the partially reduced block (cb) and the partially reduced diagonal (dgb) are published in shared memory
+// (double buffered).  Dependent chain per column:  d_J -> (1/sqrt(d_J), 1/d_J) -> d_J+1 = dgb[J+1] - cb[J+1]^2 / d_J,
+// i.e. one seed + five FP64 operations; the shared-memory hop (a[J+1] update -> publish -> read back) runs beside it.
 template <int J>
-struct CholCol {
-    static __device__ __forceinline__ void run(double (&a)[SB], int lane, int pivot_base, int* info) {
-        const double djj = __shfl_sync(0xffffffffu, a[J], J);
-        if (lane == 0 && !(djj > 0.0)) atomicCAS(info, 0, pivot_base + J);
-        // reciprocal square root + one multiply instead of sqrt + divide on the dependent chain (<= 1 ulp apart)
-        const double il = rsqrt(djj);
-        const double lrj = (lane > J) ? a[J] * il : (lane == J ? djj * il : 0.0);
-        a[J] = lrj;
-#pragma unroll
-        for (int k = J + 1; k < SB; k++) {
-            const double lkj = __shfl_sync(0xffffffffu, lrj, k);
-            if (lane >= k) a[k] = fma(-lrj, lkj, a[k]);
+struct CholInvCol {
+    static __device__ __forceinline__ void run(double (&a)[SB], double (&s)[SB], double& dg, double d, double y, unsigned cb_addr,
+                                               double* D, double* X, int xp, int lane, int& bad, double& my_il) {
+        const unsigned cb = cb_addr + (J & 1) * 2 * SB * 8;          // this column:   cb[0..31], dgb[32..63]
+        const unsigned cbn = cb_addr + ((J + 1) & 1) * 2 * SB * 8;   // next column
+        bad = (bad == 0 && !(d > 0.0)) ? J + 1 : bad;
+        double il, ild;
+        rsqrt_rcp_finish(d, y, il, ild);
+        const double w = a[J] * ild;  // a_rJ / d
+        double d_next = 0.0, cn = 0.0, y_next = 0.0;
+        if (J + 1 < SB) {
+            cn = lds_f64(cb + (J + 1) * 8);
+            const double dn = lds_f64(cb + (SB + J + 1) * 8);
+            d_next = fma(-(cn * cn), ild, dn);
+            y_next = rsqrt_seed(d_next);
+            a[J + 1] = fma(-w, cn, a[J + 1]);
+            dg = fma(-w, a[J], dg);
+            sts_f64(cbn + lane * 8, a[J + 1]);
+            sts_f64(cbn + (SB + lane) * 8, dg);
+            warp_bar();
         }
-        CholCol<J + 1>::run(a, lane, pivot_base, info);
+        const double xj = ((lane == J ? 1.0 : 0.0) - s[J]) * il;
+        const double xs = xj * il;
+        if (lane == J) my_il = il;
+        X[J * xp + lane] = (lane <= J) ? xj : 0.0;
+        if (J + 1 < SB) s[J + 1] = fma(cn, xs, s[J + 1]);
+        constexpr int K0 = J + 2;
+        if (K0 < SB && (K0 & 1)) {
+            const double c = lds_f64(cb + K0 * 8);
+            a[K0] = fma(-w, c, a[K0]);
+            s[K0] = fma(c, xs, s[K0]);
+        }
+#pragma unroll
+        for (int k = K0 + (K0 & 1); k + 1 < SB; k += 2) {
+            double c0, c1;
+            lds_v2f64(cb + k * 8, c0, c1);
+            a[k] = fma(-w, c0, a[k]);
+            s[k] = fma(c0, xs, s[k]);
+            a[k + 1] = fma(-w, c1, a[k + 1]);
+            s[k + 1] = fma(c1, xs, s[k + 1]);
+        }
+        D[lane * DP + J] = a[J] * il;  // L[lane][J] (rows above the diagonal receive unused values)
+        CholInvCol<J + 1>::run(a, s, dg, d_next, y_next, cb_addr, D, X, xp, lane, bad, my_il);
     }
 };
 template <>
-struct CholCol<SB> {
-    static __device__ __forceinline__ void run(double (&)[SB], int, int, int*) {}
+struct CholInvCol<SB> {
+    static __device__ __forceinline__ void run(double (&)[SB], double (&)[SB], double&, double, double, unsigned, double*, double*, int, int,
+                                               int&, double&) {}
 };
 
-template <int R>
-struct InvRow {
-    static __device__ __forceinline__ void run(double (&x)[SB], const double* D, int pd, int lane, double rdiag) {
-        double s0 = (R == lane) ? 1.0 : 0.0, s1 = 0.0;
+// D: 32x32 sub-block in the big array (pitch DP), overwritten by L (lower); X: its inverse (pitch xp, zeros above);
+// colbuf: 4*SB doubles, 16-byte aligned.  Returns 1/L_jj of row `lane`.
+__device__ __noinline__ double chol_inv_32(double* D, double* X, int xp, double* colbuf, int lane, int pivot_base, int* info) {
+    double a[SB], s[SB];
+    DIAG_STAMP(20);
 #pragma unroll
-        for (int k = 0; k + 1 < R; k += 2) {
-            s0 = fma(-D[R * pd + k], x[k], s0);
-            s1 = fma(-D[R * pd + k + 1], x[k + 1], s1);
-        }
-        if (R & 1) s0 = fma(-D[R * pd + R - 1], x[R - 1], s0);
-        const double rd = __shfl_sync(0xffffffffu, rdiag, R);  // executed by all lanes (never inside the select below)
-        x[R] = (R >= lane) ? (s0 + s1) * rd : 0.0;
-        InvRow<R + 1>::run(x, D, pd, lane, rdiag);
+    for (int k = 0; k < SB; k += 2) {
+        const double2 v = *reinterpret_cast<const double2*>(D + lane * DP + k);
+        a[k] = (k <= lane) ? v.x : 0.0;
+        a[k + 1] = (k + 1 <= lane) ? v.y : 0.0;
+        s[k] = s[k + 1] = 0.0;
     }
-};
-template <>
-struct InvRow<SB> {
-    static __device__ __forceinline__ void run(double (&)[SB], const double*, int, int, double) {}
-};
-
-__device__ __forceinline__ void chol_inv_32(double* D, int pd, double* Dinv, int lane, int pivot_base, int* info) {
-    double a[SB];
-#pragma unroll
-    for (int k = 0; k < SB; k++) a[k] = (k <= lane) ? D[lane * pd + k] : 0.0;
-    CholCol<0>::run(a, lane, pivot_base, info);
-#pragma unroll
-    for (int k = 0; k < SB; k++)
-        if (k <= lane) D[lane * pd + k] = a[k];
+    double dg = D[lane * DP + lane];
+    const unsigned cb_addr = (unsigned)__cvta_generic_to_shared(colbuf);
+    sts_f64(cb_addr + lane * 8, a[0]);
+    sts_f64(cb_addr + (SB + lane) * 8, dg);
+    warp_bar();
+    const double d0 = lds_f64(cb_addr);
+    double my_il = 1.0;
+    int bad = 0;
+    DIAG_STAMP(21);
+    CholInvCol<0>::run(a, s, dg, d0, rsqrt_seed(d0), cb_addr, D, X, xp, lane, bad, my_il);
+    DIAG_STAMP(22);
+    if (bad != 0 && lane == 0) atomicCAS(info, 0, pivot_base + bad - 1);
     __syncwarp();
-    // inverse: lane c owns column c of X = D^-1;  X[r][c] = (delta_rc - sum_{k<r} D[r][k] X[k][c]) / D[r][r]
-    double x[SB];
-    const double rdiag = 1.0 / D[lane * pd + lane];  // all 32 reciprocals at once, broadcast by shuffle when needed
-    InvRow<0>::run(x, D, pd, lane, rdiag);
-#pragma unroll
-    for (int r = 0; r < SB; r++) Dinv[r * SB_PITCH + lane] = x[r];
+    DIAG_STAMP(23);
+    return my_il;
 }
 
-__global__ void __launch_bounds__(256) diag_factor_inverse_kernel(double* __restrict__ K, double* __restrict__ Linv,
-                                                                  double* __restrict__ LinvT, int Np, int p, int N,
-                                                                  double* __restrict__ logdet, int* __restrict__ info) {
-    extern __shared__ double sm[];
-    double* S = sm;                                  // [TB][DB_PITCH]
-    double* Dinv = sm + TB * DB_PITCH;               // [4][SB][SB_PITCH] inverses of the diagonal sub-blocks
-    double* Tmp = Dinv + 4 * SB * SB_PITCH;          // [3][SB][SB_PITCH]
-    double* red = Tmp + 3 * SB * SB_PITCH;           // [8]
+// 8x16 half-strip of a 32x32x32 sub-block product on DMMA:  acc[j][e] += sum_k A[g][k] * op(B)[k][col0 + 8j + 2t + e]
+//   A: first row of the strip (row pitch pa, K-contiguous);  BT: op(B)[k][n] = B[n][k]  else B[k][n]
+// 16 DMMA per call: at the 16 cycles an SMSP needs per DMMA (tools/microbench/lat_probe.cu) a job is 256 cycles of pipe time.
+template <bool BT>
+__device__ __forceinline__ void half_mma(const double* A, int pa, const double* B, int pb, int col0, double (&acc)[2][2], int lane) {
+    const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int kk = 0; kk < SB / 4; kk++) {
+        const double af = A[g * pa + kk * 4 + t];
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            const double bf = BT ? B[(col0 + j * 8 + g) * pb + kk * 4 + t] : B[(kk * 4 + t) * pb + col0 + j * 8 + g];
+            dmma884(acc[j][0], acc[j][1], af, bf);
+        }
+    }
+}
+
+// C[g][col0 + 8j + 2t + e] = sign * acc (+ C), C = first row of the strip
+__device__ __forceinline__ void half_store(double* C, int pc, int col0, const double (&acc)[2][2], double sign, bool accumulate, int lane) {
+    const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+        double2* dst = reinterpret_cast<double2*>(C + g * pc + col0 + j * 8 + 2 * t);
+        double2 v = make_double2(sign * acc[j][0], sign * acc[j][1]);
+        if (accumulate) {
+            const double2 old = *dst;
+            v.x += old.x;
+            v.y += old.y;
+        }
+        *dst = v;
+    }
+}
+
+// lower-triangle enumeration q -> (ii >= kk)
+__device__ __forceinline__ void tri_small(int q, int& ii, int& kk) {
+    ii = 0;
+    while ((ii + 1) * (ii + 2) / 2 <= q) ii++;
+    kk = q - ii * (ii + 1) / 2;
+}
+
+// ---- outputs by bulk async copies (shared -> global through the copy engine; a single SM sustains only ~12-16 B/clk
+// with ordinary STG, measured in tools/microbench/diag_probe.cu, which made the stores the longest phase of this kernel).
+__device__ __forceinline__ void bulk_store(double* gdst, const double* ssrc, unsigned bytes) {
+    const unsigned src = (unsigned)__cvta_generic_to_shared(ssrc);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// (L_pp^-1)^T for every diagonal block, after the factorisation loop (grid = nb): LinvT_pp[r][c] = Linv_pp[c][r]
+__global__ void __launch_bounds__(256) diag_transpose_kernel(const double* __restrict__ Linv, double* __restrict__ LinvT, int Np) {
+    __shared__ double tile[32][33];
+    const size_t base = (size_t)blockIdx.x * TB * Np + (size_t)blockIdx.x * TB;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int bi = 0; bi < 4; bi++)
+        for (int bj = 0; bj <= bi; bj++) {
+            __syncthreads();
+            for (int r = ty; r < 32; r += 8) tile[r][tx] = Linv[base + (size_t)(bi * 32 + r) * Np + bj * 32 + tx];
+            __syncthreads();
+            for (int r = ty; r < 32; r += 8) LinvT[base + (size_t)(bj * 32 + r) * Np + bi * 32 + tx] = tile[tx][r];
+        }
+}
+
+__global__ void __launch_bounds__(DIAG_THREADS) diag_factor_inverse_kernel(double* __restrict__ K, double* __restrict__ Linv,
+                                                                           int Np, int p, int N, double* __restrict__ logdet,
+                                                                           int* __restrict__ info) {
+    extern __shared__ __align__(16) double sm[];
+    double* S = sm;                  // [TB][DP]: lower sub-blocks A -> L in place; upper sub-blocks (0,1..3) = T_pb,j scratch
+    double* Xs = sm + TB * DP;       // staircase inverse: sub-block (k,j), j <= k, at Xs + XO(k) + j*SB, row pitch XP(k)
+    double* colbuf = Xs + XO(4);     // [2][2][SB]
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
-    const int grp = tid >> 6, gt = tid & 63;         // 64-thread group and index inside it
-    const int bar = 1 + grp;
     const size_t base = (size_t)p * TB * Np + (size_t)p * TB;
-#pragma unroll 16
-    for (int e = tid; e < TB * TB; e += 256) {
-        int r = e >> 7, c = e & 127;
-        S[r * DB_PITCH + c] = K[base + (size_t)r * Np + c];
-    }
-    __syncthreads();
-#define SBLK(i, k) (S + (i) * SB * DB_PITCH + (k) * SB)
-    // ---- blocked right-looking Cholesky over the 4 sub-block columns ----
-    for (int pb = 0; pb < 4; pb++) {
-        if (warp == 0) chol_inv_32(SBLK(pb, pb), DB_PITCH, Dinv + pb * SB * SB_PITCH, lane, p * TB + pb * SB + 1, info);
-        __syncthreads();
-        // panel: L_ip = A_ip * D^-T, in place
-        if (pb + 1 + grp < 4)
-            sub_gemm<true>(SBLK(pb + 1 + grp, pb), DB_PITCH, Dinv + pb * SB * SB_PITCH, SB_PITCH, SBLK(pb + 1 + grp, pb), DB_PITCH, 1.0,
-                           false, true, gt, bar);
-        __syncthreads();
-        // trailing: A_ik -= L_ip L_kp^T for pb < k <= i
-        int q = 0;
-        for (int i = pb + 1; i < 4; i++)
-            for (int k = pb + 1; k <= i; k++, q++)
-                if ((q & 3) == grp)
-                    sub_gemm<true>(SBLK(i, pb), DB_PITCH, SBLK(k, pb), DB_PITCH, SBLK(i, k), DB_PITCH, -1.0, true, false, gt, bar);
-        __syncthreads();
-    }
-    // log-determinant contribution (fixed order) and write L back
+    DIAG_STAMP(0);
     {
-        double v = 0.0;
-        if (tid < TB && p * TB + tid < N) v = log(S[tid * DB_PITCH + tid]);
-        double s = block_sum<256>(v, red);
-        if (tid == 0) logdet[p] = s;
-    }
-    for (int e = tid; e < TB * TB; e += 256) {
-        int r = e >> 7, c = e & 127;
-        if (c <= r) K[base + (size_t)r * Np + c] = S[r * DB_PITCH + c];
+        const int c2 = (tid & 63) * 2;
+#pragma unroll
+        for (int r = tid >> 6; r < TB; r += DIAG_THREADS / 64)
+            if (c2 < ((r >> 5) + 1) * SB) cp_async16(S + r * DP + c2, K + base + (size_t)r * Np + c2);
+        cp_async_commit();
+        cp_async_wait<0>();
     }
     __syncthreads();
-    // ---- in-place block inverse, block columns from the right; diagonal blocks live in Dinv ----
-    for (int j = 2; j >= 0; j--) {
-        // T_i = sum_{k=j+1..i} X_ik L_kj   (X_ii = Dinv[i], X_ik = S block (i,k) already inverted)
-        const int i = j + 1 + grp;
-        if (i < 4) {
-            double* T = Tmp + grp * SB * SB_PITCH;
-            for (int k = j + 1; k <= i; k++) {
-                const double* X = (k == i) ? Dinv + i * SB * SB_PITCH : SBLK(i, k);
-                const int px = (k == i) ? SB_PITCH : DB_PITCH;
-                sub_gemm<false>(X, px, SBLK(k, j), DB_PITCH, T, SB_PITCH, 1.0, k > j + 1, false, gt, bar);
+    DIAG_STAMP(1);
+#define SBLK(i, k) (S + (i) * SB * DP + (k) * SB)
+#define TBLK(j) SBLK(0, 1 + (j))
+#define XBLK(k, j) (Xs + XO(k) + (j) * SB)
+    double logacc = 0.0;
+    for (int pb = 0; pb < 4; pb++) {
+        // ---- P1: warp 0 factors + inverts the diagonal sub-block; the other warps work in its shadow
+        if (warp == 0) {
+            const double il = chol_inv_32(SBLK(pb, pb), XBLK(pb, pb), XP(pb), colbuf, lane, p * TB + pb * SB + 1, info);
+            if (p * TB + pb * SB + lane < N) logacc -= log(il);
+        } else if (pb > 0) {
+            if (warp == 4) {
+                // shares its SM sub-partition with warp 0: no FP64 work here, only the copies of the finished row pb-1
+                // (one bulk copy per matrix row: rows of Linv from the staircase, rows of L from S)
+                const int rb = pb - 1;
+                fence_async_smem();
+                const size_t grow = base + (size_t)(rb * SB + lane) * Np;
+                bulk_store(Linv + grow, Xs + XO(rb) + lane * XP(rb), (rb + 1) * SB * 8);
+                bulk_store(K + grow, S + (rb * SB + lane) * DP, (rb + 1) * SB * 8);
+                bulk_commit();
+            } else {
+                const int sw = warp < 4 ? warp - 1 : warp - 2;  // 0..5
+                // (a) deferred trailing update of step pb-1: A_ik -= L_i,pb-1 L_k,pb-1^T for pb+1 <= k <= i
+                const int m = 3 - pb;
+                const int n_def = m * (m + 1) / 2 * 8;
+                // (b) T_pb,j = sum_{k=j}^{pb-1} L_pb,k X_kj  (j < pb)
+                const int n_t = pb * 8;
+                for (int job = sw; job < n_def + n_t; job += 6) {
+                    double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+                    if (job < n_def) {
+                        int ii, kk;
+                        tri_small(job >> 3, ii, kk);
+                        const int i = pb + 1 + ii, k = pb + 1 + kk, strip = (job >> 1) & 3, col0 = (job & 1) * 16;
+                        half_mma<true>(SBLK(i, pb - 1) + strip * 8 * DP, DP, SBLK(k, pb - 1), DP, col0, acc, lane);
+                        half_store(SBLK(i, k) + strip * 8 * DP, DP, col0, acc, -1.0, true, lane);
+                    } else {
+                        const int q = job - n_def;
+                        const int j = q >> 3, strip = (q >> 1) & 3, col0 = (q & 1) * 16;
+                        for (int k = j; k < pb; k++)
+                            half_mma<false>(SBLK(pb, k) + strip * 8 * DP, DP, XBLK(k, j), XP(k), col0, acc, lane);
+                        half_store(TBLK(j) + strip * 8 * DP, DP, col0, acc, 1.0, false, lane);
+                    }
+                }
             }
         }
         __syncthreads();
-        // X_ij = -T_i X_jj
-        if (i < 4)
-            sub_gemm<false>(Tmp + grp * SB * SB_PITCH, SB_PITCH, Dinv + j * SB * SB_PITCH, SB_PITCH, SBLK(i, j), DB_PITCH, -1.0, false,
-                            false, gt, bar);
+        DIAG_STAMP(2 + 3 * pb);
+        // ---- P2: panel L_i,pb = A_i,pb X_pb,pb^T (i > pb, in place) and X_pb,j = -X_pb,pb T_pb,j (j < pb).
+        // Round = sub-block; warps (2s, 2s+1) share strip s and take one half each.  A panel half reads the whole strip it
+        // partly overwrites, so the two warps of a pair meet at a named barrier between their loads and their stores.
+        for (int blk = 0; blk < 3; blk++) {
+            double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+            const int strip = warp >> 1, col0 = (warp & 1) * 16;
+            if (blk < 3 - pb) {
+                const int i = pb + 1 + blk;
+                half_mma<true>(SBLK(i, pb) + strip * 8 * DP, DP, XBLK(pb, pb), XP(pb), col0, acc, lane);
+                asm volatile("bar.sync %0, 64;" ::"r"(1 + strip) : "memory");
+                half_store(SBLK(i, pb) + strip * 8 * DP, DP, col0, acc, 1.0, false, lane);
+            } else {
+                const int j = blk - (3 - pb);
+                half_mma<false>(XBLK(pb, pb) + strip * 8 * XP(pb), XP(pb), TBLK(j), DP, col0, acc, lane);
+                half_store(XBLK(pb, j) + strip * 8 * XP(pb), XP(pb), col0, acc, -1.0, false, lane);
+            }
+        }
         __syncthreads();
+        DIAG_STAMP(3 + 3 * pb);
+        // ---- P3: the part of the trailing update the next step waits for: A_i,pb+1 -= L_i,pb L_pb+1,pb^T (i > pb)
+        for (int job = warp; job < (3 - pb) * 8; job += 8) {
+            double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+            const int i = pb + 1 + (job >> 3), strip = (job >> 1) & 3, col0 = (job & 1) * 16;
+            half_mma<true>(SBLK(i, pb) + strip * 8 * DP, DP, SBLK(pb + 1, pb), DP, col0, acc, lane);
+            half_store(SBLK(i, pb + 1) + strip * 8 * DP, DP, col0, acc, -1.0, true, lane);
+        }
+        if (pb < 3) __syncthreads();
+        DIAG_STAMP(4 + 3 * pb);
     }
+    // log-determinant contribution (fixed order: the 32 rows of each sub-block in lane order, sub-blocks in sequence)
+    if (warp == 0) {
+        const double v = warp_sum(logacc);
+        if (lane == 0) logdet[p] = v;
+    }
+    DIAG_STAMP(14);
+    // ---- remaining outputs: row 3 of the inverse and of L, four matrix rows per warp; every bulk copy must have landed
+    // before the kernel ends
+    if (lane < 8) {
+        fence_async_smem();
+        const int rr = warp * 4 + (lane & 3);
+        const size_t grow = base + (size_t)(3 * SB + rr) * Np;
+        if (lane < 4) bulk_store(Linv + grow, Xs + XO(3) + rr * XP(3), 4 * SB * 8);
+        else bulk_store(K + grow, S + (3 * SB + rr) * DP, 4 * SB * 8);
+        bulk_commit();
+    }
+    DIAG_STAMP_W(4, 30);
+    if (lane < 8 || warp == 4) bulk_wait_all();
+    DIAG_STAMP_W(4, 31);
 #undef SBLK
-    for (int e = tid; e < TB * TB; e += 256) {
-        int r = e >> 7, c = e & 127;
-        double v = 0.0;
-        if (c <= r) v = ((r >> 5) == (c >> 5)) ? Dinv[(r >> 5) * SB * SB_PITCH + (r & 31) * SB_PITCH + (c & 31)] : S[r * DB_PITCH + c];
-        Linv[base + (size_t)r * Np + c] = v;
-    }
-    for (int e = tid; e < TB * TB; e += 256) {
-        int r = e >> 7, c = e & 127;  // LinvT[r][c] = Linv[c][r]
-        double v = 0.0;
-        if (r <= c) v = ((r >> 5) == (c >> 5)) ? Dinv[(r >> 5) * SB * SB_PITCH + (c & 31) * SB_PITCH + (r & 31)] : S[c * DB_PITCH + r];
-        LinvT[base + (size_t)r * Np + c] = v;
-    }
+#undef TBLK
+#undef XBLK
+    DIAG_STAMP(18);
 }
 
 // ---- tile GEMM with store epilogues -------------------------------------------------------------------------------
