@@ -124,6 +124,10 @@ int gpso_predict_info(gpso_handle* h, double* out3);
 /* int8 engine only: overlap the cross-covariance of window w+1 (FP64 CUDA cores, side stream) with the tensor-core
  * product of window w (default on; results are bit-identical either way) */
 int gpso_set_overlap(gpso_handle* h, int enabled);
+/* schedule of the blocked Cholesky inside gpso_neg_lml_grad / gpso_factorize: 1 (default) = one persistent kernel, one CTA
+ * per SM pulling DIAG / PANEL / UPDATE tile tasks from a dependency-ordered queue (look-ahead, no launch gaps); 0 = one
+ * launch per step (diagonal block, panel, trailing update).  Same tile arithmetic, bit-identical factors. */
+int gpso_set_factor_mode(gpso_handle* h, int mode);
 /* tuning knob: candidates per rolling window (0 = automatic) */
 int gpso_set_window(gpso_handle* h, int64_t candidates);
 

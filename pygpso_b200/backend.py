@@ -83,6 +83,7 @@ def load_library():
         "gpso_set_predict_mode": (i32, [H, i32, i32]),
         "gpso_predict_info": (i32, [H, _c_double_p]),
         "gpso_set_overlap": (i32, [H, i32]),
+        "gpso_set_factor_mode": (i32, [H, i32]),
         "gpso_set_profile": (i32, [H, i32]),
         "gpso_last_windows": (i64, [H]),
     }
@@ -104,7 +105,8 @@ EXPORTED_SYMBOLS = (
     "gpso_factorize gpso_factor_lml gpso_predict_y_host gpso_predict_y_dev gpso_ucb_argmax_host gpso_ucb_argmax_dev "
     "gpso_grow_count gpso_grow_leaves_host gpso_grow_leaves_dev gpso_grow_ucb_argmax gpso_state_bytes "
     "gpso_export_state_dev gpso_import_state_dev gpso_launch_count gpso_debug_fetch gpso_last_timing gpso_set_window "
-    "gpso_set_profile gpso_last_windows gpso_set_predict_mode gpso_predict_info gpso_set_overlap"
+    "gpso_set_profile gpso_last_windows gpso_set_predict_mode gpso_predict_info gpso_set_overlap "
+    "gpso_set_factor_mode"
 ).split()
 
 
@@ -231,6 +233,10 @@ class CudaSession:
     def set_predict_mode(self, mode=0, slices=0):
         """0 automatic, 1 FP64 DMMA, 2 int8 tcgen05 (``slices`` 8-bit digits per operand, 0 = automatic)."""
         _check(self._lib, self._lib.gpso_set_predict_mode(self._h, int(mode), int(slices)), "gpso_set_predict_mode")
+
+    def set_factor_mode(self, persistent=True):
+        """Cholesky schedule: persistent dataflow kernel (default) or one launch per step; bit-identical results."""
+        _check(self._lib, self._lib.gpso_set_factor_mode(self._h, int(bool(persistent))), "gpso_set_factor_mode")
 
     def set_overlap(self, enabled=True):
         _check(self._lib, self._lib.gpso_set_overlap(self._h, int(bool(enabled))), "gpso_set_overlap")

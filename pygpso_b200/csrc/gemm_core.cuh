@@ -16,9 +16,13 @@ namespace gpso {
 
 constexpr int GM = 128;                    // tile rows    (m)
 constexpr int GN = 128;                    // tile columns (n)
-constexpr int GK = 16;                     // k-slab per pipeline stage
-constexpr int GLD = GK + 4;                // shared row pitch in doubles (160 B: 16 B aligned, conflict-free)
-constexpr int GSTAGES = 4;
+#ifndef GPSO_GK
+#define GPSO_GK 16
+#define GPSO_GSTAGES 4
+#endif
+constexpr int GK = GPSO_GK;                // k-slab per pipeline stage
+constexpr int GLD = GK + 4;                // shared row pitch in doubles (== 4 mod 16: 16 B aligned, conflict-free)
+constexpr int GSTAGES = GPSO_GSTAGES;
 constexpr int GTHREADS = 256;
 constexpr int GSLAB = GM * GLD;            // doubles per operand per stage
 constexpr int GEMM_SMEM_BYTES = GSTAGES * 2 * GSLAB * (int)sizeof(double);  // 163840
@@ -42,9 +46,9 @@ struct TileAcc {
 
 __device__ __forceinline__ void gemm_load_slab(double* sA, double* sB, const TileOperands& w, int k, int tid) {
 #pragma unroll
-    for (int i = 0; i < (GM * GK / 2) / GTHREADS; i++) {  // 4 x 16-byte chunks per thread per operand
+    for (int i = 0; i < (GM * GK / 2) / GTHREADS; i++) {  // GK/4 x 16-byte chunks per thread per operand
         int id = tid + i * GTHREADS;
-        int r = id >> 3, c = (id & 7) * 2;
+        int r = id / (GK / 2), c = (id % (GK / 2)) * 2;
         cp_async16(sA + r * GLD + c, w.A + (size_t)r * w.lda + k + c);
         cp_async16(sB + r * GLD + c, w.B + (size_t)r * w.ldb + k + c);
     }

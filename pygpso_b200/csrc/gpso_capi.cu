@@ -73,7 +73,11 @@ struct DevBuf {
             return fail(GPSO_E_NOMEM, b);
         }
         cap = bytes;
-        if (zero) cudaMemset(p, 0, bytes);
+        if (zero) {
+            // the handle's streams are non-blocking: a legacy-stream memset is not ordered with them, so finish it here
+            cudaMemset(p, 0, bytes);
+            cudaDeviceSynchronize();
+        }
         return 0;
     }
     void release() {
@@ -103,6 +107,10 @@ struct gpso_handle {
     DevBuf X, y, Xs, ls, alpha;
     DevBuf K, Linv, LinvT, T, Kinv;
     DevBuf resid, a, logdet, scalars, gpart, gout, info, counter;
+    // persistent Cholesky scheduler: task queue (rebuilt when nb changes) and its state [next, err, cnt[nb*nb]]
+    DevBuf chol_tasks, chol_state;
+    int chol_tasks_nb = 0, chol_ntasks = 0, chol_W = 4;
+    int chol_mode = 1;      // 1 = persistent dataflow kernel, 0 = one launch per step (reference schedule)
     // predict workspaces
     DevBuf KsT, part, blockbest, running, cand[2], leaves, omean, ovar;
     // int8 tensor-core (tcgen05) variance product: digit tiles of L^-1 and of the cross-covariance window
@@ -268,6 +276,7 @@ static int configure_kernels() {
     CU_TRY(cudaFuncSetAttribute(dense_gemm_kernel<MODE_LAUUM>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     CU_TRY(cudaFuncSetAttribute(predict_trmm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     CU_TRY(cudaFuncSetAttribute(diag_factor_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM_BYTES));
+    CU_TRY(cudaFuncSetAttribute(chol_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM_BYTES));
     GP_TRY(oz_configure<5>());
     GP_TRY(oz_configure<6>());
     GP_TRY(oz_configure<7>());
@@ -297,8 +306,10 @@ static int ensure_shape(gpso_handle* h, int N, int d) {
     if (Np != h->Np) {
         // the factor kernels never write the structural zeros of L^-1 / L^-T inside diagonal blocks: clear both buffers
         // whenever the row pitch changes (a buffer that was large enough is reused with a different layout)
-        CU_TRY(cudaMemset(h->Linv.p, 0, mat));
-        CU_TRY(cudaMemset(h->LinvT.p, 0, mat));
+        CU_TRY(cudaStreamSynchronize(h->stream));
+        CU_TRY(cudaMemsetAsync(h->Linv.p, 0, mat, h->stream));
+        CU_TRY(cudaMemsetAsync(h->LinvT.p, 0, mat, h->stream));
+        CU_TRY(cudaStreamSynchronize(h->stream));  // rare (shape change); callers may continue on another stream
     }
     h->N = N;
     h->d = d;
@@ -309,6 +320,63 @@ static int ensure_shape(gpso_handle* h, int N, int d) {
 
 static int upload_lengthscales(gpso_handle* h, cudaStream_t st) {
     CU_TRY(cudaMemcpyAsync(h->ls.p, h->ls_host, sizeof(double) * h->n_ls(), cudaMemcpyHostToDevice, st));
+    return 0;
+}
+
+// Queue of the persistent Cholesky kernel (kern_dense.cuh): topological, with look-ahead.  Blocks of W panels.  Per panel p
+// of a block [p0, p1): DIAG(p) (the last narrow update of its tile is fused in when p > p0), the narrow updates of panel p-1
+// (they run beside DIAG(p)), wide updates of the previous block as cover for the time the diagonal block takes, PANEL(.,p),
+// cover for the panels.  Then the wide updates of block b: the columns of block b+1 first, the rest becomes the cover of the
+// next block's chain (the queue is popped at about nsm / T_wide tasks per microsecond).
+static int build_chol_tasks(gpso_handle* h) {
+    const int nb = h->nb, W = nb >= 48 ? 4 : 2;
+    if (h->chol_tasks_nb == nb) return 0;
+    h->chol_W = W;
+    if (nb > 255) return fail(GPSO_E_BADARG, "matrix too large for the tile scheduler (more than 255 panels)");
+    auto word = [](int type, int p, int i, int j) { return (unsigned)type << 24 | (unsigned)p << 16 | (unsigned)i << 8 | (unsigned)j; };
+    const int nsm = h->nsm > 0 ? h->nsm : 148;
+    const double t_wide_us = 17.0 * W + 12.0;  // tile time of a wide update (DMMA at peak + tile write-back)
+    const double pops_per_us = nsm / t_wide_us;
+    std::vector<unsigned> q, wide;
+    size_t wpos = 0;
+    auto cover = [&](double us) {
+        if (us <= 0) return;
+        const double want = pops_per_us * us;
+        const size_t e = want >= (double)(wide.size() - wpos) ? wide.size() : wpos + (size_t)want;
+        q.insert(q.end(), wide.begin() + wpos, wide.begin() + e);
+        wpos = e;
+    };
+    const int nblk = (nb + W - 1) / W;
+    for (int b = 0; b < nblk; b++) {
+        const int p0 = b * W, p1 = std::min(nb, p0 + W);
+        for (int p = p0; p < p1; p++) {
+            q.push_back(word(CT_DIAG, p, p, p));
+            size_t narrow = 0;
+            if (p > p0)
+                for (int j = p; j < p1; j++)
+                    for (int i = j; i < nb; i++)
+                        if (!(i == p && j == p)) {
+                            q.push_back(word(CT_UPD, p - 1, i, j));
+                            narrow++;
+                        }
+            cover((p > p0 ? 42.0 : 30.0) - narrow * 30.0 / nsm);
+            for (int i = p + 1; i < nb; i++) q.push_back(word(CT_PANEL, p, i, p));
+            cover(22.0);
+        }
+        cover(1e30);  // flush
+        wide.clear();
+        wpos = 0;
+        const int next_end = std::min(nb, p1 + W);
+        for (int j = p1; j < next_end; j++)
+            for (int i = j; i < nb; i++) q.push_back(word(CT_WIDE, b, i, j));
+        for (int j = next_end; j < nb; j++)
+            for (int i = j; i < nb; i++) wide.push_back(word(CT_WIDE, b, i, j));
+    }
+    GP_TRY(h->chol_tasks.ensure(q.size() * sizeof(unsigned)));
+    GP_TRY(h->chol_state.ensure((size_t)(2 + nb * nb) * sizeof(int)));
+    CU_TRY(cudaMemcpy(h->chol_tasks.p, q.data(), q.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
+    h->chol_tasks_nb = nb;
+    h->chol_ntasks = (int)q.size();
     return 0;
 }
 
@@ -333,6 +401,15 @@ static int factor_pipeline(gpso_handle* h, cudaStream_t st, bool need_kinv) {
     P.nb = nb;
     P.p = 0;
     P.s = 0;
+    if (h->chol_mode == 1 && nb > 1) {
+        GP_TRY(build_chol_tasks(h));
+        int* state = h->chol_state.as<int>();
+        CU_TRY(cudaMemsetAsync(state, 0, (size_t)(2 + nb * nb) * sizeof(int), st));
+        const int grid = std::min(h->chol_ntasks, h->nsm > 0 ? h->nsm : 148);
+        chol_persistent_kernel<<<grid, GTHREADS, DIAG_SMEM_BYTES, st>>>(P, h->N, h->chol_W, h->chol_tasks.as<unsigned>(), h->chol_ntasks, state,
+                                                                         h->logdet.as<double>(), h->info.as<int>());
+        GP_TRY(check_launch(h, "chol_persistent"));
+    } else
     for (int p = 0; p < nb; p++) {
         diag_factor_inverse_kernel<<<1, DIAG_THREADS, DIAG_SMEM_BYTES, st>>>(P.K, P.Linv, Np, p, h->N, h->logdet.as<double>(),
                                                                              h->info.as<int>());
@@ -598,6 +675,7 @@ extern "C" int gpso_neg_lml_grad(gpso_handle* h, const double* u, int p, double*
     cudaEventElapsedTime(&ms, h->ev_t0, h->ev_t1);
     h->last_ms[0] = ms;
     h->last_ms[1] = h->last_ms[2] = h->last_ms[3] = 0;
+    if (info < 0) return fail(GPSO_E_CUDA, "Cholesky tile scheduler timed out waiting for a dependency");
     if (info > 0) {
         char b[128];
         snprintf(b, sizeof b, "Gram matrix is not positive definite (pivot %d)", info);
@@ -627,6 +705,7 @@ extern "C" int gpso_factorize(gpso_handle* h, const double* theta_host, int p) {
     CU_TRY(cudaMemcpyAsync(sc, h->scalars.p, sizeof sc, cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaMemcpyAsync(&info, h->info.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaStreamSynchronize(st));
+    if (info < 0) return fail(GPSO_E_CUDA, "Cholesky tile scheduler timed out waiting for a dependency");
     if (info > 0) {
         char b[128];
         snprintf(b, sizeof b, "Gram matrix is not positive definite (pivot %d)", info);
@@ -1124,6 +1203,12 @@ extern "C" int gpso_set_predict_mode(gpso_handle* h, int mode, int slices) {
 extern "C" int gpso_set_overlap(gpso_handle* h, int enabled) {
     if (!h) return fail(GPSO_E_BADARG, "gpso_set_overlap: null handle");
     h->overlap = enabled != 0;
+    return 0;
+}
+
+extern "C" int gpso_set_factor_mode(gpso_handle* h, int mode) {
+    if (!h || mode < 0 || mode > 1) return fail(GPSO_E_BADARG, "gpso_set_factor_mode: bad argument");
+    h->chol_mode = mode;
     return 0;
 }
 

@@ -234,10 +234,13 @@ __global__ void __launch_bounds__(256) diag_transpose_kernel(const double* __res
         }
 }
 
-__global__ void __launch_bounds__(DIAG_THREADS) diag_factor_inverse_kernel(double* __restrict__ K, double* __restrict__ Linv,
-                                                                           int Np, int p, int N, double* __restrict__ logdet,
-                                                                           int* __restrict__ info) {
-    extern __shared__ __align__(16) double sm[];
+// Lprev != nullptr: the tile still lacks its last narrow update; it is applied here, in shared memory, before the
+// factorisation:  A_pp -= L_p,p-1 L_p,p-1^T  with L_p,p-1 = the 128x128 tile at Lprev (row pitch Np), streamed through the
+// not yet used inverse area in two halves of 64 columns.  Saves a separate 30 us task on the critical chain of the scheduler.
+constexpr int LHP = 64 + 4;  // row pitch of a 128x64 half of the left neighbour tile
+__device__ __forceinline__ void diag_block_device(double* __restrict__ K, double* __restrict__ Linv, int Np, int p, int N,
+                                                  double* __restrict__ logdet, int* __restrict__ info, double* sm,
+                                                  const double* __restrict__ Lprev = nullptr) {
     double* S = sm;                  // [TB][DP]: lower sub-blocks A -> L in place; upper sub-blocks (0,1..3) = T_pb,j scratch
     double* Xs = sm + TB * DP;       // staircase inverse: sub-block (k,j), j <= k, at Xs + XO(k) + j*SB, row pitch XP(k)
     double* colbuf = Xs + XO(4);     // [2][2][SB]
@@ -254,8 +257,29 @@ __global__ void __launch_bounds__(DIAG_THREADS) diag_factor_inverse_kernel(doubl
         cp_async_wait<0>();
     }
     __syncthreads();
-    DIAG_STAMP(1);
 #define SBLK(i, k) (S + (i) * SB * DP + (k) * SB)
+    if (Lprev != nullptr) {
+        double* Lh = Xs;  // [TB][LHP]
+        for (int half = 0; half < 2; half++) {
+            const int c2 = (tid & 31) * 2;
+#pragma unroll
+            for (int r = tid >> 5; r < TB; r += DIAG_THREADS / 32) cp_async16(Lh + r * LHP + c2, Lprev + (size_t)r * Np + half * 64 + c2);
+            cp_async_commit();
+            cp_async_wait<0>();
+            __syncthreads();
+            for (int job = warp; job < 80; job += 8) {
+                int ii, kk;
+                tri_small(job >> 3, ii, kk);
+                const int strip = (job >> 1) & 3, col0 = (job & 1) * 16;
+                double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+                half_mma<true>(Lh + (ii * SB + strip * 8) * LHP, LHP, Lh + kk * SB * LHP, LHP, col0, acc, lane);
+                half_mma<true>(Lh + (ii * SB + strip * 8) * LHP + SB, LHP, Lh + kk * SB * LHP + SB, LHP, col0, acc, lane);
+                half_store(SBLK(ii, kk) + strip * 8 * DP, DP, col0, acc, -1.0, true, lane);
+            }
+            __syncthreads();
+        }
+    }
+    DIAG_STAMP(1);
 #define TBLK(j) SBLK(0, 1 + (j))
 #define XBLK(k, j) (Xs + XO(k) + (j) * SB)
     double logacc = 0.0;
@@ -299,6 +323,7 @@ __global__ void __launch_bounds__(DIAG_THREADS) diag_factor_inverse_kernel(doubl
                 }
             }
         }
+        fence_async_smem();  // by the writers: the rows written here are read by bulk copies issued after the barrier
         __syncthreads();
         DIAG_STAMP(2 + 3 * pb);
         // ---- P2: panel L_i,pb = A_i,pb X_pb,pb^T (i > pb, in place) and X_pb,j = -X_pb,pb T_pb,j (j < pb).
@@ -318,6 +343,7 @@ __global__ void __launch_bounds__(DIAG_THREADS) diag_factor_inverse_kernel(doubl
                 half_store(XBLK(pb, j) + strip * 8 * XP(pb), XP(pb), col0, acc, -1.0, false, lane);
             }
         }
+        fence_async_smem();
         __syncthreads();
         DIAG_STAMP(3 + 3 * pb);
         // ---- P3: the part of the trailing update the next step waits for: A_i,pb+1 -= L_i,pb L_pb+1,pb^T (i > pb)
@@ -327,7 +353,7 @@ __global__ void __launch_bounds__(DIAG_THREADS) diag_factor_inverse_kernel(doubl
             half_mma<true>(SBLK(i, pb) + strip * 8 * DP, DP, SBLK(pb + 1, pb), DP, col0, acc, lane);
             half_store(SBLK(i, pb + 1) + strip * 8 * DP, DP, col0, acc, -1.0, true, lane);
         }
-        if (pb < 3) __syncthreads();
+        __syncthreads();
         DIAG_STAMP(4 + 3 * pb);
     }
     // log-determinant contribution (fixed order: the 32 rows of each sub-block in lane order, sub-blocks in sequence)
@@ -355,13 +381,21 @@ __global__ void __launch_bounds__(DIAG_THREADS) diag_factor_inverse_kernel(doubl
     DIAG_STAMP(18);
 }
 
+__global__ void __launch_bounds__(DIAG_THREADS) diag_factor_inverse_kernel(double* __restrict__ K, double* __restrict__ Linv,
+                                                                           int Np, int p, int N, double* __restrict__ logdet,
+                                                                           int* __restrict__ info) {
+    extern __shared__ __align__(16) double sm[];
+    diag_block_device(K, Linv, Np, p, N, logdet, info, sm);
+}
+
 // ---- tile GEMM with store epilogues -------------------------------------------------------------------------------
 enum GemmMode {
     MODE_CHOL_PANEL = 0,  // L[i,p] = A[i,p] * Linv_pp^T                       tiles: i = p+1 .. nb-1
     MODE_CHOL_TRAIL = 1,  // A[i,j] -= L[i,p] * L[j,p]^T                        tiles: p < j <= i
     MODE_TRTRI_XT = 2,    // T[u-blk, v-blk] = LinvT11 * L21^T  (= X^T)        per pair of half-blocks of size s
     MODE_TRTRI_Y = 3,     // Linv21 = -(Linv22 * X), LinvT12 = Linv21^T
-    MODE_LAUUM = 4        // Kinv[i,j] = sum_{k >= i} LinvT[i][k] LinvT[j][k]   tiles: j <= i
+    MODE_LAUUM = 4,       // Kinv[i,j] = sum_{k >= i} LinvT[i][k] LinvT[j][k]   tiles: j <= i
+    MODE_CHOL_UPD = 5     // A[ui,uj] -= L[ui, uk0..uk0+ukn) * L[uj, same panels]^T   one tile, K = ukn * 128
 };
 
 struct DenseParams {
@@ -373,6 +407,7 @@ struct DenseParams {
     int Np, nb;
     int p;  // Cholesky panel
     int s;  // half-block size (in tiles) of the inverse recursion level
+    int ui, uj, uk0, ukn;  // MODE_CHOL_UPD: output tile and range of panels contracted over
 };
 
 __device__ __forceinline__ void tri_index(int t, int& i, int& j) {  // t -> (i >= j), row-major lower enumeration
@@ -390,15 +425,14 @@ __host__ __device__ inline int trtri_pair_vtiles(int nb, int s, int q) {
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(GTHREADS, 1) dense_gemm_kernel(DenseParams P) {
-    extern __shared__ double smem[];
+__device__ __forceinline__ void gemm_tile_device(const DenseParams& P, const int tile, double* smem) {
     const int Np = P.Np;
     TileOperands w;
     w.lda = w.ldb = Np;
     w.tri_off = TRI_DENSE;
     int orow = 0, ocol = 0;  // output tile origin (rows, cols)
     if (MODE == MODE_CHOL_PANEL) {
-        int i = P.p + 1 + blockIdx.x;
+        int i = P.p + 1 + tile;
         w.A = P.K + (size_t)i * TB * Np + (size_t)P.p * TB;
         w.B = P.Linv + (size_t)P.p * TB * Np + (size_t)P.p * TB;
         w.kbeg = 0;
@@ -407,7 +441,7 @@ __global__ void __launch_bounds__(GTHREADS, 1) dense_gemm_kernel(DenseParams P) 
         ocol = P.p * TB;
     } else if (MODE == MODE_CHOL_TRAIL) {
         int ti, tj;
-        tri_index(blockIdx.x, ti, tj);
+        tri_index(tile, ti, tj);
         int i = P.p + 1 + ti, j = P.p + 1 + tj;
         w.A = P.K + (size_t)i * TB * Np + (size_t)P.p * TB;
         w.B = P.K + (size_t)j * TB * Np + (size_t)P.p * TB;
@@ -415,9 +449,16 @@ __global__ void __launch_bounds__(GTHREADS, 1) dense_gemm_kernel(DenseParams P) 
         w.kend = TB;
         orow = i * TB;
         ocol = j * TB;
+    } else if (MODE == MODE_CHOL_UPD) {
+        w.A = P.K + (size_t)P.ui * TB * Np + (size_t)P.uk0 * TB;
+        w.B = P.K + (size_t)P.uj * TB * Np + (size_t)P.uk0 * TB;
+        w.kbeg = 0;
+        w.kend = P.ukn * TB;
+        orow = P.ui * TB;
+        ocol = P.uj * TB;
     } else if (MODE == MODE_TRTRI_XT || MODE == MODE_TRTRI_Y) {
         // decode (pair q, u tile, v tile): tiles are enumerated pair by pair, u-major
-        int s = P.s, t = blockIdx.x, q = 0;
+        int s = P.s, t = tile, q = 0;
         for (;; q++) {
             int cnt = s * trtri_pair_vtiles(P.nb, s, q);
             if (t < cnt) break;
@@ -446,7 +487,7 @@ __global__ void __launch_bounds__(GTHREADS, 1) dense_gemm_kernel(DenseParams P) 
         }
     } else {  // MODE_LAUUM
         int i, j;
-        tri_index(blockIdx.x, i, j);
+        tri_index(tile, i, j);
         w.A = P.LinvT + (size_t)i * TB * Np;
         w.B = P.LinvT + (size_t)j * TB * Np;
         w.kbeg = i * TB;
@@ -470,9 +511,9 @@ __global__ void __launch_bounds__(GTHREADS, 1) dense_gemm_kernel(DenseParams P) 
             if (MODE == MODE_CHOL_PANEL) {
                 double2* dst = reinterpret_cast<double2*>(P.K + (size_t)r * Np + c);
                 *dst = make_double2(v0, v1);
-            } else if (MODE == MODE_CHOL_TRAIL) {
+            } else if (MODE == MODE_CHOL_TRAIL || MODE == MODE_CHOL_UPD) {
                 double2* dst = reinterpret_cast<double2*>(P.K + (size_t)r * Np + c);
-                double2 old = *dst;
+                double2 old = __ldcg(dst);  // L2: another SM may have updated this tile (persistent scheduler)
                 *dst = make_double2(old.x - v0, old.y - v1);
             } else if (MODE == MODE_TRTRI_XT) {
                 double2* dst = reinterpret_cast<double2*>(P.T + (size_t)r * Np + c);
@@ -488,6 +529,121 @@ __global__ void __launch_bounds__(GTHREADS, 1) dense_gemm_kernel(DenseParams P) 
             }
         }
     }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(GTHREADS, 1) dense_gemm_kernel(DenseParams P) {
+    extern __shared__ double smem[];
+    gemm_tile_device<MODE>(P, blockIdx.x, smem);
+}
+
+// ---- persistent blocked Cholesky: one CTA per SM, tile tasks pulled from two dependency-ordered queues ----------------
+// Two-level blocking: panels are grouped in blocks of W (4 for large matrices, 2 below 48 panels).  A tile (i, j) in block
+// column bj = j / W receives, in this order, bj "wide" updates (one per earlier block, K = W * 128: the read-modify-write of
+// the tile -- 8 us at the ~14 B/clk an SM can store -- is paid once per W panels), then j - bj*W "narrow" updates from the
+// earlier panels of its own block (K = 128), then its final operation (factor+invert if i == j, panel solve otherwise).
+// cnt[i*nb + j] counts the operations completed on the tile; ops(j) = bj + (j - bj*W) updates, final when cnt == ops(j) + 1.
+// The last narrow update of a diagonal tile is applied inside its DIAG task (fused), not as a task of its own.
+// Task word: type << 24 | p << 16 | i << 8 | j   (p = panel, or block for WIDE).
+//   DIAG(p)       p first in its block: waits cnt[p,p] >= ops(p);  else waits cnt[p,p] >= ops(p)-1 and tile (p,p-1) final
+//                                                                                 sets cnt[p,p] = ops(p)+1
+//   PANEL(i,p)    waits cnt[p,p] >= ops(p)+1, cnt[i,p] >= ops(p)                  sets cnt[i,p] = ops(p)+1
+//   UPD(i,j,p)    (p, j in one block) waits cnt[i,p], cnt[j,p] >= ops(p)+1, cnt[i,j] >= bj + p - bj*W   sets it +1
+//   WIDE(i,j,b)   (j beyond block b, q = last panel of b) waits cnt[i,q], cnt[j,q] >= ops(q)+1, cnt[i,j] >= b   sets b+1
+// Scheduling: one queue in a topological order chosen by the host (gpso_capi.cu: build_chol_tasks), tickets by atomicAdd
+// (no contention; claiming the queue head with compare-and-swap after a readiness check was tried and serialises at one
+// claim per ~3 us).  A CTA that draws a task whose inputs are not complete polls their counters.  Every dependency of a
+// task sits earlier in the queue and a CTA holds one task at a time, so the CTA that owns the oldest unfinished task can
+// always run: no deadlock as long as tasks are only taken by resident CTAs (grid <= #SMs).  The order threads the
+// factorisation chain of block b+1 through the wide updates of block b (look-ahead).
+// Tiles cross SMs through L2 only (cp.async.cg / ld.cg), flags with release / acquire at gpu scope.
+constexpr int CT_DIAG = 0, CT_PANEL = 1, CT_UPD = 2, CT_WIDE = 3;
+__host__ __device__ inline int chol_ops(int j, int W) { return j / W + j % W; }
+constexpr long long CHOL_SPIN_LIMIT = 1LL << 24;  // polls (each >= 100 ns) before a waiter gives up and reports an error
+
+__device__ __forceinline__ int ld_acquire(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+
+__device__ __forceinline__ bool chol_wait(const int* c, int need, int* err) {
+    long long spins = 0;
+    while (ld_acquire(c) < need) {
+        __nanosleep(100);
+        if (++spins > CHOL_SPIN_LIMIT || ld_acquire(err) != 0) {
+            atomicExch(err, 1);
+            return false;
+        }
+    }
+    return true;
+}
+
+// state: [0] next ticket, [1] error flag, [2...] cnt[nb*nb]
+__global__ void __launch_bounds__(GTHREADS, 1) chol_persistent_kernel(DenseParams P, int N, int W, const unsigned* __restrict__ tasks,
+                                                                      int ntasks, int* __restrict__ state, double* __restrict__ logdet,
+                                                                      int* __restrict__ info) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ int s_task, s_ok;
+    const int nb = P.nb;
+    int* err = state + 1;
+    int* cnt = state + 2;
+    if (threadIdx.x == 0) s_ok = 1;
+    for (;;) {
+        if (threadIdx.x == 0) s_task = atomicAdd(state, 1);
+        __syncthreads();
+        const int t = s_task;
+        if (t >= ntasks) break;
+        const unsigned w = tasks[t];
+        const int type = w >> 24, p = (w >> 16) & 255, i = (w >> 8) & 255, j = w & 255;
+        if (threadIdx.x == 0) {
+            bool ok;
+            if (type == CT_DIAG) {
+                if (p % W == 0) ok = chol_wait(cnt + p * nb + p, chol_ops(p, W), err);
+                else ok = chol_wait(cnt + p * nb + p, chol_ops(p, W) - 1, err) && chol_wait(cnt + p * nb + p - 1, chol_ops(p - 1, W) + 1, err);
+            } else if (type == CT_PANEL) {
+                ok = chol_wait(cnt + p * nb + p, chol_ops(p, W) + 1, err) && chol_wait(cnt + i * nb + p, chol_ops(p, W), err);
+            } else if (type == CT_UPD) {
+                ok = chol_wait(cnt + i * nb + p, chol_ops(p, W) + 1, err) && chol_wait(cnt + j * nb + p, chol_ops(p, W) + 1, err) &&
+                     chol_wait(cnt + i * nb + j, j / W + p % W, err);
+            } else {
+                const int q = min(nb, (p + 1) * W) - 1;  // last panel of block p
+                ok = chol_wait(cnt + i * nb + q, chol_ops(q, W) + 1, err) && chol_wait(cnt + j * nb + q, chol_ops(q, W) + 1, err) &&
+                     chol_wait(cnt + i * nb + j, p, err);
+            }
+            s_ok = ok;
+        }
+        __syncthreads();
+        if (!s_ok) break;
+        int* done;
+        int done_val;
+        if (type == CT_DIAG) {
+            const double* Lprev = (p % W != 0) ? P.K + (size_t)p * TB * P.Np + (size_t)(p - 1) * TB : nullptr;
+            diag_block_device(P.K, P.Linv, P.Np, p, N, logdet, info, smem, Lprev);
+            done = cnt + p * nb + p;
+            done_val = chol_ops(p, W) + 1;
+        } else if (type == CT_PANEL) {
+            DenseParams Q = P;
+            Q.p = p;
+            gemm_tile_device<MODE_CHOL_PANEL>(Q, i - p - 1, smem);
+            done = cnt + i * nb + p;
+            done_val = chol_ops(p, W) + 1;
+        } else {
+            DenseParams Q = P;
+            Q.ui = i;
+            Q.uj = j;
+            Q.uk0 = (type == CT_UPD) ? p : p * W;
+            Q.ukn = (type == CT_UPD) ? 1 : min(nb, (p + 1) * W) - p * W;
+            gemm_tile_device<MODE_CHOL_UPD>(Q, 0, smem);
+            done = cnt + i * nb + j;
+            done_val = (type == CT_UPD) ? j / W + p % W + 1 : p + 1;
+        }
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) st_release(done, done_val);
+    }
+    if (threadIdx.x == 0 && !s_ok) atomicExch(info, -1);  // a dependency never arrived: reported as a scheduler failure
 }
 
 // ---- triangular matrix-vector products: one warp per row, fixed summation order ----------------------------------

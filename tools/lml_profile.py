@@ -29,6 +29,8 @@ def main():
     cuda = backend.default_backend()
     s = cuda.open_session("Matern52", 1, True)
     s.set_data(X, y)
+    if "--stepwise" in sys.argv:
+        s.set_factor_mode(False)
     theta = np.array([0.25 * np.sqrt(d), 1.0, 1e-3, 0.0])
     u = np.array([softplus_inv(theta[0]), softplus_inv(theta[1]), softplus_inv(theta[2] - 1e-6), 0.0])
     if "--factorize" in sys.argv:
