@@ -127,7 +127,20 @@ def bench_lml_grad(cuda, go, cpu=True, shapes=((4096, 10), (8192, 20)), evals=5)
             f, g = sess.neg_lml_and_grad(u + 1e-3 * (i + 1))
             dev_ms += sess.last_timing_ms()[0]
         wall = time.perf_counter() - t0
+        # the same closure with the step-by-step launches (gpso_set_factor_mode 0) beside the persistent tile scheduler
+        sess.set_factor_mode(False)
+        sess.neg_lml_and_grad(u)
+        step_ms = 0.0
+        for i in range(evals):
+            sess.neg_lml_and_grad(u + 1e-3 * (i + 1))
+            step_ms += sess.last_timing_ms()[0]
+        sess.set_factor_mode(True)
         rec = {"N": N, "d": d, "evals_per_s": evals / wall, "device_ms_per_eval": dev_ms / evals,
+               "device_ms_per_eval_stepwise_launches": step_ms / evals,
+               "schedule": "persistent tile scheduler: blocked Cholesky as DIAG/PANEL/UPDATE tasks, one CTA per SM, "
+                           "two-level blocking + look-ahead; then L^-1 by recursive doubling and K^-1 = L^-T L^-1 (DMMA tiles)",
+               "library_bar_ms": {4096: {"cusolver_dpotrf": 1.675, "cusolver_dpotri": 14.005},
+                                  8192: {"cusolver_dpotrf": 7.753, "cusolver_dpotri": 61.528}}.get(N),
                "fp64_tflops": (float(N) ** 3 / (dev_ms / evals * 1e-3)) / 1e12, "fp64_peak_tflops": FP64_PEAK_TFLOPS,
                "frac_of_fp64_peak": (float(N) ** 3 / (dev_ms / evals * 1e-3)) / 1e12 / FP64_PEAK_TFLOPS, "neg_lml": f}
         if cpu and N <= 4096:

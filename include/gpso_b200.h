@@ -126,7 +126,8 @@ int gpso_predict_info(gpso_handle* h, double* out3);
 int gpso_set_overlap(gpso_handle* h, int enabled);
 /* schedule of the blocked Cholesky inside gpso_neg_lml_grad / gpso_factorize: 1 (default) = one persistent kernel, one CTA
  * per SM pulling DIAG / PANEL / UPDATE tile tasks from a dependency-ordered queue (look-ahead, no launch gaps); 0 = one
- * launch per step (diagonal block, panel, trailing update).  Same tile arithmetic, bit-identical factors. */
+ * launch per step (diagonal block, panel, trailing update).  Same tile arithmetic; the schedules differ in summation order
+ * only (wide K = 512 updates, one update fused into the diagonal block), i.e. at rounding level. */
 int gpso_set_factor_mode(gpso_handle* h, int mode);
 /* tuning knob: candidates per rolling window (0 = automatic) */
 int gpso_set_window(gpso_handle* h, int64_t candidates);

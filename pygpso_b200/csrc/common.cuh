@@ -69,6 +69,21 @@ __device__ __forceinline__ double exp_neg(double s) {
     return (s != s) ? s : v;
 }
 
+// ---- sqrt of a positive finite number ---------------------------------------------------------------------------------
+// sqrt(x) = x / sqrt(x):  hardware seed y ~ 1/sqrt(x) (MUFU.RSQ64H, ~2^-22) and one third-order correction
+// y(1 + e/2 + 3e^2/8), e = 1 - x y^2 (remaining error < 2^-64 before the final rounding; result within 1.5 ulp, measured
+// 1.4e-16 in tools/microbench/diag_probe.cu).  7 FP64-pipe operations instead of the ~17 DFMA-equivalents of the IEEE
+// sqrt() (profiles/r01_fp64_probe.txt).  The argument is always >= 1e-36 here (GPflow's clip).  NaN -> NaN.
+__device__ __forceinline__ double sqrt_pos(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double t = x * y;          // ~ sqrt(x)
+    const double e = fma(-t, y, 1.0);
+    const double pl = fma(0.375, e, 0.5);
+    const double q = t * e;
+    return fma(q, pl, t);
+}
+
 // ---- covariance functions (gpflow.kernels.stationaries) ----------------------------------------------------------
 // r2 = scaled squared distance (inputs already divided by the lengthscale), var = kernel variance
 template <int KID>
@@ -76,7 +91,7 @@ __device__ __forceinline__ double cov_from_r2(double r2, double var) {
     if (KID == KERNEL_SE) {
         return var * exp_neg(0.5 * r2);
     } else {
-        double r = sqrt(clip_r2(r2));
+        double r = sqrt_pos(clip_r2(r2));
         if (KID == KERNEL_MATERN52) {
             const double s5 = 2.23606797749978969641;
             double sr = s5 * r;
@@ -101,7 +116,7 @@ __device__ __forceinline__ void cov_and_radial(double r2, double var, double& k,
         g = k;
     } else {
         bool live = r2 > R2_CLIP;
-        double r = sqrt(clip_r2(r2));
+        double r = sqrt_pos(clip_r2(r2));
         if (KID == KERNEL_MATERN52) {
             const double s5 = 2.23606797749978969641;
             double sr = s5 * r;

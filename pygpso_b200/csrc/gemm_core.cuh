@@ -17,8 +17,8 @@ namespace gpso {
 constexpr int GM = 128;                    // tile rows    (m)
 constexpr int GN = 128;                    // tile columns (n)
 #ifndef GPSO_GK
-#define GPSO_GK 16
-#define GPSO_GSTAGES 4
+#define GPSO_GK 32
+#define GPSO_GSTAGES 3
 #endif
 constexpr int GK = GPSO_GK;                // k-slab per pipeline stage
 constexpr int GLD = GK + 4;                // shared row pitch in doubles (== 4 mod 16: 16 B aligned, conflict-free)

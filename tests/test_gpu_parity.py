@@ -127,6 +127,73 @@ def test_neg_lml_and_grad_sizes(cuda, N, d):
     s.close()
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# the two Cholesky schedules: persistent tile scheduler (default) and one launch per step
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("N,d", [(129, 2), (300, 3), (1100, 5), (2100, 6)])
+def test_factor_schedules_agree(cuda, N, d):
+    """Persistent dataflow kernel (blocks of 2 panels below 48 panels, fused diagonal update) against the step-by-step
+    launches: same factor up to summation order, same LML / gradient well inside the parity tolerances, both against the
+    oracle."""
+    X, y = synthetic(N, d, seed=3)
+    h = go.Hyper(0.25 * np.sqrt(d), 1.1, 1e-3, 0.05)
+    u = h.pack()
+    out = {}
+    for mode in (True, False):
+        s = open_session(cuda, "Matern52", X, y)
+        s.set_factor_mode(mode)
+        f, g = s.neg_lml_and_grad(u)
+        s.factorize(theta_of(h))
+        out[mode] = (f, g, s.debug_fetch(1), s.debug_fetch(2), s.debug_fetch(3))
+        s.close()
+    (f1, g1, L1, Li1, a1), (f0, g0, L0, Li0, a0) = out[True], out[False]
+    assert abs(f1 - f0) <= 1e-12 * max(abs(f0), N), (f1, f0)
+    assert np.all(np.abs(g1 - g0) <= 1e-8 * np.maximum(np.abs(g0), 1.0)), (g1, g0)
+    np.testing.assert_allclose(L1, L0, rtol=0, atol=1e-12)
+    np.testing.assert_allclose(Li1, Li0, rtol=0, atol=1e-9 * np.abs(Li0).max())
+    np.testing.assert_allclose(a1, a0, rtol=0, atol=1e-9 * np.abs(a0).max())
+    f_ref, g_ref = go.neg_lml_and_grad("Matern52", X, y, u, 1, True)
+    assert abs(f1 - f_ref) <= 1e-9 * max(abs(f_ref), N), (f1, f_ref)
+    assert np.all(np.abs(g1 - g_ref) <= 1e-6 * np.maximum(np.abs(g_ref), 1.0)), (g1, g_ref)
+    K = go.kern("Matern52", X, None, h) + h.noise_variance * np.eye(N)
+    np.testing.assert_allclose(L1, np.linalg.cholesky(K), rtol=0, atol=1e-11)
+
+
+def test_factor_wide_blocks_large_matrix(cuda):
+    """49 panels: the scheduler groups panels in blocks of 4 (K = 512 wide updates, look-ahead across blocks).  LML against
+    the oracle (1e-9 relative) and against the step-by-step schedule; L^-1 L = I on a sample of rows."""
+    N, d = 6200, 8
+    X, y = synthetic(N, d, seed=5)
+    h = go.Hyper(0.25 * np.sqrt(d), 1.0, 1e-3, 0.0)
+    vals = {}
+    for mode in (True, False):
+        s = open_session(cuda, "Matern52", X, y)
+        s.set_factor_mode(mode)
+        s.factorize(theta_of(h))
+        vals[mode] = s.log_marginal_likelihood()
+        if mode:
+            L, Linv = s.debug_fetch(1), s.debug_fetch(2)
+        s.close()
+    lml_ref = go.lml("Matern52", X, y, h)
+    assert abs(vals[True] - lml_ref) <= 1e-9 * max(abs(lml_ref), N), (vals[True], lml_ref)
+    assert abs(vals[True] - vals[False]) <= 1e-11 * max(abs(lml_ref), N), vals
+    rows = np.random.default_rng(0).integers(0, N, 64)
+    np.testing.assert_allclose(Linv[rows] @ L, np.eye(N)[rows], rtol=0, atol=1e-8)
+
+
+def test_not_positive_definite_under_the_scheduler(cuda):
+    """A matrix that loses positive definiteness in a late panel: the persistent kernel must finish (NaNs flow through
+    the remaining tasks, nothing waits forever) and report the LAPACK-style pivot."""
+    N, d = 600, 2
+    X, y = synthetic(N, d, seed=9)
+    X[450:] = X[:150]  # 150 exact duplicates and a noise variance far below rounding: K is numerically singular
+    s = open_session(cuda, "SquaredExponential", X, y)
+    with pytest.raises(np.linalg.LinAlgError) as err:
+        s.factorize(np.array([0.5, 1.0, 1.0e-18, 0.0]))
+    assert "pivot" in str(err.value)
+    s.close()
+
+
 def test_not_positive_definite_reports_info(cuda):
     y = np.array([[0.0], [1.0], [0.3], [0.5]])
     s = open_session(cuda, "Matern52", np.full((4, 2), np.nan), y)
