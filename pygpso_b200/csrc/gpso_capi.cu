@@ -324,7 +324,7 @@ static int upload_lengthscales(gpso_handle* h, cudaStream_t st) {
 }
 
 // Queue of the persistent Cholesky kernel (kern_dense.cuh): topological, with look-ahead.  Blocks of W panels.  Per panel p
-// of a block [p0, p1): DIAG(p) (the last narrow update of its tile is fused in when p > p0), the narrow updates of panel p-1
+// of a block [p0, p1): DIAG(p) (the last update of its tile, narrow or wide, is fused in), the narrow updates of panel p-1
 // (they run beside DIAG(p)), wide updates of the previous block as cover for the time the diagonal block takes, PANEL(.,p),
 // cover for the panels.  Then the wide updates of block b: the columns of block b+1 first, the rest becomes the cover of the
 // next block's chain (the queue is popped at about nsm / T_wide tasks per microsecond).
@@ -368,7 +368,8 @@ static int build_chol_tasks(gpso_handle* h) {
         wpos = 0;
         const int next_end = std::min(nb, p1 + W);
         for (int j = p1; j < next_end; j++)
-            for (int i = j; i < nb; i++) q.push_back(word(CT_WIDE, b, i, j));
+            for (int i = j; i < nb; i++)
+                if (!(i == p1 && j == p1)) q.push_back(word(CT_WIDE, b, i, j));  // tile (p1,p1): fused into DIAG(p1)
         for (int j = next_end; j < nb; j++)
             for (int i = j; i < nb; i++) wide.push_back(word(CT_WIDE, b, i, j));
     }

@@ -234,13 +234,14 @@ __global__ void __launch_bounds__(256) diag_transpose_kernel(const double* __res
         }
 }
 
-// Lprev != nullptr: the tile still lacks its last narrow update; it is applied here, in shared memory, before the
-// factorisation:  A_pp -= L_p,p-1 L_p,p-1^T  with L_p,p-1 = the 128x128 tile at Lprev (row pitch Np), streamed through the
-// not yet used inverse area in two halves of 64 columns.  Saves a separate 30 us task on the critical chain of the scheduler.
+// Lprev != nullptr: the tile still lacks its last update; it is applied here, in shared memory, before the factorisation:
+// A_pp -= L_p,q L_p,q^T over the nprev panels q whose tiles start at Lprev (row pitch Np; nprev = 1: last narrow update,
+// nprev = W: the wide update of the previous block), streamed through the not yet used inverse area in halves of 64
+// columns.  ~10 us per panel here instead of a separate 30-85 us task plus a hand-over on the critical chain.
 constexpr int LHP = 64 + 4;  // row pitch of a 128x64 half of the left neighbour tile
 __device__ __forceinline__ void diag_block_device(double* __restrict__ K, double* __restrict__ Linv, int Np, int p, int N,
                                                   double* __restrict__ logdet, int* __restrict__ info, double* sm,
-                                                  const double* __restrict__ Lprev = nullptr) {
+                                                  const double* __restrict__ Lprev = nullptr, int nprev = 0) {
     double* S = sm;                  // [TB][DP]: lower sub-blocks A -> L in place; upper sub-blocks (0,1..3) = T_pb,j scratch
     double* Xs = sm + TB * DP;       // staircase inverse: sub-block (k,j), j <= k, at Xs + XO(k) + j*SB, row pitch XP(k)
     double* colbuf = Xs + XO(4);     // [2][2][SB]
@@ -260,7 +261,7 @@ __device__ __forceinline__ void diag_block_device(double* __restrict__ K, double
 #define SBLK(i, k) (S + (i) * SB * DP + (k) * SB)
     if (Lprev != nullptr) {
         double* Lh = Xs;  // [TB][LHP]
-        for (int half = 0; half < 2; half++) {
+        for (int half = 0; half < 2 * nprev; half++) {
             const int c2 = (tid & 31) * 2;
 #pragma unroll
             for (int r = tid >> 5; r < TB; r += DIAG_THREADS / 32) cp_async16(Lh + r * LHP + c2, Lprev + (size_t)r * Np + half * 64 + c2);
@@ -543,10 +544,11 @@ __global__ void __launch_bounds__(GTHREADS, 1) dense_gemm_kernel(DenseParams P) 
 // the tile -- 8 us at the ~14 B/clk an SM can store -- is paid once per W panels), then j - bj*W "narrow" updates from the
 // earlier panels of its own block (K = 128), then its final operation (factor+invert if i == j, panel solve otherwise).
 // cnt[i*nb + j] counts the operations completed on the tile; ops(j) = bj + (j - bj*W) updates, final when cnt == ops(j) + 1.
-// The last narrow update of a diagonal tile is applied inside its DIAG task (fused), not as a task of its own.
+// The last update of a diagonal tile (narrow, or wide for the first panel of a block) is applied inside its DIAG task
+// (fused), not as a task of its own.
 // Task word: type << 24 | p << 16 | i << 8 | j   (p = panel, or block for WIDE).
-//   DIAG(p)       p first in its block: waits cnt[p,p] >= ops(p);  else waits cnt[p,p] >= ops(p)-1 and tile (p,p-1) final
-//                                                                                 sets cnt[p,p] = ops(p)+1
+//   DIAG(p)       p = 0: nothing to wait for;  else waits cnt[p,p] >= ops(p)-1 and tile (p,p-1) final (the last update,
+//                 narrow or wide, is fused)                                       sets cnt[p,p] = ops(p)+1
 //   PANEL(i,p)    waits cnt[p,p] >= ops(p)+1, cnt[i,p] >= ops(p)                  sets cnt[i,p] = ops(p)+1
 //   UPD(i,j,p)    (p, j in one block) waits cnt[i,p], cnt[j,p] >= ops(p)+1, cnt[i,j] >= bj + p - bj*W   sets it +1
 //   WIDE(i,j,b)   (j beyond block b, q = last panel of b) waits cnt[i,q], cnt[j,q] >= ops(q)+1, cnt[i,j] >= b   sets b+1
@@ -600,8 +602,7 @@ __global__ void __launch_bounds__(GTHREADS, 1) chol_persistent_kernel(DenseParam
         if (threadIdx.x == 0) {
             bool ok;
             if (type == CT_DIAG) {
-                if (p % W == 0) ok = chol_wait(cnt + p * nb + p, chol_ops(p, W), err);
-                else ok = chol_wait(cnt + p * nb + p, chol_ops(p, W) - 1, err) && chol_wait(cnt + p * nb + p - 1, chol_ops(p - 1, W) + 1, err);
+                ok = p == 0 || (chol_wait(cnt + p * nb + p, chol_ops(p, W) - 1, err) && chol_wait(cnt + p * nb + p - 1, chol_ops(p - 1, W) + 1, err));
             } else if (type == CT_PANEL) {
                 ok = chol_wait(cnt + p * nb + p, chol_ops(p, W) + 1, err) && chol_wait(cnt + i * nb + p, chol_ops(p, W), err);
             } else if (type == CT_UPD) {
@@ -619,8 +620,9 @@ __global__ void __launch_bounds__(GTHREADS, 1) chol_persistent_kernel(DenseParam
         int* done;
         int done_val;
         if (type == CT_DIAG) {
-            const double* Lprev = (p % W != 0) ? P.K + (size_t)p * TB * P.Np + (size_t)(p - 1) * TB : nullptr;
-            diag_block_device(P.K, P.Linv, P.Np, p, N, logdet, info, smem, Lprev);
+            const int nprev = p == 0 ? 0 : (p % W != 0 ? 1 : W);
+            const double* Lprev = nprev ? P.K + (size_t)p * TB * P.Np + (size_t)(p - nprev) * TB : nullptr;
+            diag_block_device(P.K, P.Linv, P.Np, p, N, logdet, info, smem, Lprev, nprev);
             done = cnt + p * nb + p;
             done_val = chol_ops(p, W) + 1;
         } else if (type == CT_PANEL) {
