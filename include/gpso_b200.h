@@ -129,6 +129,10 @@ int gpso_set_overlap(gpso_handle* h, int enabled);
  * launch per step (diagonal block, panel, trailing update).  Same tile arithmetic; the schedules differ in summation order
  * only (wide K = 512 updates, one update fused into the diagonal block), i.e. at rounding level. */
 int gpso_set_factor_mode(gpso_handle* h, int mode);
+/* Host-only introspection (works without a GPU): the task list of the persistent factorisation kernel for a matrix of nb
+ * 128-wide panels on nsm SMs, 16 ints per task (op, p, i, j, s, tile, 3 x dependency counter, 3 x value, counter to
+ * signal, value / 0 = increment, 2 unused).  out may be NULL to query the sizes. */
+int gpso_debug_factor_tasks(int nb, int nsm, int* out, int64_t capacity_words, int* ntasks, int* ncounters);
 /* tuning knob: candidates per rolling window (0 = automatic) */
 int gpso_set_window(gpso_handle* h, int64_t candidates);
 

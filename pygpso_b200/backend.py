@@ -84,6 +84,7 @@ def load_library():
         "gpso_predict_info": (i32, [H, _c_double_p]),
         "gpso_set_overlap": (i32, [H, i32]),
         "gpso_set_factor_mode": (i32, [H, i32]),
+        "gpso_debug_factor_tasks": (i32, [i32, i32, ctypes.POINTER(ctypes.c_int), i64, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]),
         "gpso_set_profile": (i32, [H, i32]),
         "gpso_last_windows": (i64, [H]),
     }
@@ -106,7 +107,7 @@ EXPORTED_SYMBOLS = (
     "gpso_grow_count gpso_grow_leaves_host gpso_grow_leaves_dev gpso_grow_ucb_argmax gpso_state_bytes "
     "gpso_export_state_dev gpso_import_state_dev gpso_launch_count gpso_debug_fetch gpso_last_timing gpso_set_window "
     "gpso_set_profile gpso_last_windows gpso_set_predict_mode gpso_predict_info gpso_set_overlap "
-    "gpso_set_factor_mode"
+    "gpso_set_factor_mode gpso_debug_factor_tasks"
 ).split()
 
 

@@ -109,7 +109,7 @@ struct gpso_handle {
     DevBuf resid, a, logdet, scalars, gpart, gout, info, counter;
     // persistent Cholesky scheduler: task queue (rebuilt when nb changes) and its state [next, err, cnt[nb*nb]]
     DevBuf chol_tasks, chol_state;
-    int chol_tasks_nb = 0, chol_ntasks = 0, chol_W = 4;
+    int chol_tasks_nb = 0, chol_ntasks = 0, chol_ncounters = 0, chol_W = 4;
     int chol_mode = 1;      // 1 = persistent dataflow kernel, 0 = one launch per step (reference schedule)
     // predict workspaces
     DevBuf KsT, part, blockbest, running, cand[2], leaves, omean, ovar;
@@ -276,7 +276,7 @@ static int configure_kernels() {
     CU_TRY(cudaFuncSetAttribute(dense_gemm_kernel<MODE_LAUUM>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     CU_TRY(cudaFuncSetAttribute(predict_trmm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     CU_TRY(cudaFuncSetAttribute(diag_factor_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM_BYTES));
-    CU_TRY(cudaFuncSetAttribute(chol_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM_BYTES));
+    CU_TRY(cudaFuncSetAttribute(factor_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM_BYTES));
     GP_TRY(oz_configure<5>());
     GP_TRY(oz_configure<6>());
     GP_TRY(oz_configure<7>());
@@ -323,21 +323,46 @@ static int upload_lengthscales(gpso_handle* h, cudaStream_t st) {
     return 0;
 }
 
-// Queue of the persistent Cholesky kernel (kern_dense.cuh): topological, with look-ahead.  Blocks of W panels.  Per panel p
-// of a block [p0, p1): DIAG(p) (the last update of its tile, narrow or wide, is fused in), the narrow updates of panel p-1
-// (they run beside DIAG(p)), wide updates of the previous block as cover for the time the diagonal block takes, PANEL(.,p),
-// cover for the panels.  Then the wide updates of block b: the columns of block b+1 first, the rest becomes the cover of the
-// next block's chain (the queue is popped at about nsm / T_wide tasks per microsecond).
-static int build_chol_tasks(gpso_handle* h) {
-    const int nb = h->nb, W = nb >= 48 ? 4 : 2;
-    if (h->chol_tasks_nb == nb) return 0;
-    h->chol_W = W;
-    if (nb > 255) return fail(GPSO_E_BADARG, "matrix too large for the tile scheduler (more than 255 panels)");
-    auto word = [](int type, int p, int i, int j) { return (unsigned)type << 24 | (unsigned)p << 16 | (unsigned)i << 8 | (unsigned)j; };
-    const int nsm = h->nsm > 0 ? h->nsm : 148;
+// Task list of the persistent factorisation kernel (kern_dense.cuh): topological, with look-ahead.  Cholesky in blocks of
+// W panels.  Per panel p of a block [p0, p1): DIAG(p) (the last update of its tile, narrow or wide, is fused in), the
+// narrow updates of panel p-1 (they run beside DIAG(p)), wide updates of the previous block as cover for the time the
+// diagonal block takes, PANEL(.,p), TRANSPOSE(p), cover for the panels.  Then the wide updates of block b: the columns of
+// block b+1 first, the rest becomes the cover of the next block's chain (the queue is popped at about nsm / T_wide tasks per
+// microsecond).  After the Cholesky: the recursive-doubling inverse, level by level, long tiles first; its tasks carry
+// pair-level dependencies, so the levels overlap instead of being separated by launches.
+namespace {
+struct FactorTask {
+    int w[TASK_WORDS];
+    FactorTask(int op, int p, int i, int j, int s, int tile) {
+        for (int k = 0; k < TASK_WORDS; k++) w[k] = 0;
+        w[0] = op; w[1] = p; w[2] = i; w[3] = j; w[4] = s; w[5] = tile;
+        w[6] = w[7] = w[8] = -1;
+        w[12] = 0; w[13] = 0;
+    }
+    FactorTask& dep(int idx, int val) {
+        for (int k = 0; k < 3; k++)
+            if (w[6 + k] < 0) { w[6 + k] = idx; w[9 + k] = val; return *this; }
+        return *this;  // more than three dependencies: a builder bug, caught by the host-side simulation in the tests
+    }
+    FactorTask& done(int idx, int val) { w[12] = idx; w[13] = val; return *this; }
+};
+}  // namespace
+
+static int make_factor_tasks(int nb, int nsm, std::vector<int>& flat, int& ntasks, int& ncounters_out) {
+    const int W = nb >= 48 ? 4 : 2;
+    if (nb < 1 || nb > 255) return fail(GPSO_E_BADARG, "matrix too large for the tile scheduler (more than 255 panels)");
+    const int LV = 8;  // levels of the inverse recursion: s = 1 .. 128
+    auto T = [nb](int i, int j) { return i * nb + j; };          // tile counters
+    const int TR_ALL = nb * nb;                                    // transposes completed
+    auto XTD = [nb, LV](int l, int q) { return nb * nb + 1 + l * nb + q; };
+    auto YD = [nb, LV](int l, int q) { return nb * nb + 1 + LV * nb + l * nb + q; };
+    const int ncounters = nb * nb + 1 + 2 * LV * nb;
+    auto ops = [W](int j) { return chol_ops(j, W); };
+    auto fin = [W](int j) { return chol_ops(j, W) + 1; };
+
     const double t_wide_us = 17.0 * W + 12.0;  // tile time of a wide update (DMMA at peak + tile write-back)
     const double pops_per_us = nsm / t_wide_us;
-    std::vector<unsigned> q, wide;
+    std::vector<FactorTask> q, wide;
     size_t wpos = 0;
     auto cover = [&](double us) {
         if (us <= 0) return;
@@ -346,21 +371,31 @@ static int build_chol_tasks(gpso_handle* h) {
         q.insert(q.end(), wide.begin() + wpos, wide.begin() + e);
         wpos = e;
     };
+    auto wide_task = [&](int b, int i, int j) {
+        const int p0 = b * W, p1 = std::min(nb, p0 + W), last = p1 - 1;
+        return FactorTask(CT_UPD, p0, i, j, p1 - p0, 0).dep(T(i, last), fin(last)).dep(T(j, last), fin(last)).dep(T(i, j), b).done(T(i, j), b + 1);
+    };
     const int nblk = (nb + W - 1) / W;
     for (int b = 0; b < nblk; b++) {
         const int p0 = b * W, p1 = std::min(nb, p0 + W);
         for (int p = p0; p < p1; p++) {
-            q.push_back(word(CT_DIAG, p, p, p));
+            const int nprev = p == 0 ? 0 : (p % W != 0 ? 1 : W);
+            FactorTask dg(CT_DIAG, p, p, p, nprev, 0);
+            if (p > 0) dg.dep(T(p, p), ops(p) - 1).dep(T(p, p - 1), fin(p - 1));
+            q.push_back(dg.done(T(p, p), fin(p)));
             size_t narrow = 0;
             if (p > p0)
                 for (int j = p; j < p1; j++)
                     for (int i = j; i < nb; i++)
                         if (!(i == p && j == p)) {
-                            q.push_back(word(CT_UPD, p - 1, i, j));
+                            const int at = j / W + (p - 1) % W;  // updates tile (i,j) has received before this one
+                            q.push_back(FactorTask(CT_UPD, p - 1, i, j, 1, 0).dep(T(i, p - 1), fin(p - 1)).dep(T(j, p - 1), fin(p - 1)).dep(T(i, j), at).done(T(i, j), at + 1));
                             narrow++;
                         }
-            cover((p > p0 ? 42.0 : 30.0) - narrow * 30.0 / nsm);
-            for (int i = p + 1; i < nb; i++) q.push_back(word(CT_PANEL, p, i, p));
+            cover((p > p0 ? 42.0 : 30.0 + 10.0 * nprev) - narrow * 30.0 / nsm);
+            for (int i = p + 1; i < nb; i++)
+                q.push_back(FactorTask(CT_PANEL, p, i, p, 0, 0).dep(T(p, p), fin(p)).dep(T(i, p), ops(p)).done(T(i, p), fin(p)));
+            q.push_back(FactorTask(CT_TRANSPOSE, p, p, p, 0, 0).dep(T(p, p), fin(p)).done(TR_ALL, 0));
             cover(22.0);
         }
         cover(1e30);  // flush
@@ -369,15 +404,81 @@ static int build_chol_tasks(gpso_handle* h) {
         const int next_end = std::min(nb, p1 + W);
         for (int j = p1; j < next_end; j++)
             for (int i = j; i < nb; i++)
-                if (!(i == p1 && j == p1)) q.push_back(word(CT_WIDE, b, i, j));  // tile (p1,p1): fused into DIAG(p1)
+                if (!(i == p1 && j == p1)) q.push_back(wide_task(b, i, j));  // tile (p1,p1): fused into DIAG(p1)
         for (int j = next_end; j < nb; j++)
-            for (int i = j; i < nb; i++) wide.push_back(word(CT_WIDE, b, i, j));
+            for (int i = j; i < nb; i++) wide.push_back(wide_task(b, i, j));
     }
-    GP_TRY(h->chol_tasks.ensure(q.size() * sizeof(unsigned)));
-    GP_TRY(h->chol_state.ensure((size_t)(2 + nb * nb) * sizeof(int)));
-    CU_TRY(cudaMemcpy(h->chol_tasks.p, q.data(), q.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
-    h->chol_tasks_nb = nb;
-    h->chol_ntasks = (int)q.size();
+    // ---- inverse factor: level s merges [a, a+s) and [a+s, a+s+nv), a = 2 q s
+    for (int s = 1, l = 0; s < nb; s *= 2, l++) {
+        if (l >= LV) return fail(GPSO_E_BADARG, "matrix too large for the inverse recursion of the tile scheduler");
+        std::vector<int> off;  // first tile index of pair q in the kernel's enumeration
+        int total = 0;
+        for (int qq = 0; 2 * qq * s < nb; qq++) {
+            off.push_back(total);
+            total += s * trtri_pair_vtiles(nb, s, qq);
+        }
+        for (int pass = 0; pass < 2; pass++)
+            for (int qq = 0; 2 * qq * s < nb; qq++) {
+                const int nv = trtri_pair_vtiles(nb, s, qq), a = 2 * qq * s;
+                if (nv == 0) continue;
+                if (pass == 0) {
+                    for (int u = 0; u < s; u++)  // small u = long contraction first
+                        for (int v = 0; v < nv; v++) {
+                            FactorTask t(CT_XT, 0, 0, 0, s, off[qq] + u * nv + v);
+                            t.dep(TR_ALL, nb);
+                            if (s > 1) t.dep(YD(l - 1, 2 * qq), (s / 2) * (s / 2));
+                            t.dep(T(a + s + v, a + s - 1), fin(a + s - 1));
+                            q.push_back(t.done(XTD(l, qq), 0));
+                        }
+                } else {
+                    for (int v = nv - 1; v >= 0; v--)  // large v = long contraction first
+                        for (int u = 0; u < s; u++) {
+                            FactorTask t(CT_Y, 0, 0, 0, s, off[qq] + u * nv + v);
+                            t.dep(XTD(l, qq), s * nv);
+                            if (nv == 1) {
+                                t.dep(T(a + s, a + s), fin(a + s));
+                            } else {
+                                int s2 = 1, l2 = 0;
+                                while (s2 * 2 < nv) { s2 *= 2; l2++; }
+                                t.dep(YD(l2, (a + s) / (2 * s2)), s2 * (nv - s2));
+                            }
+                            q.push_back(t.done(YD(l, qq), 0));
+                        }
+                }
+            }
+    }
+    flat.clear();
+    flat.reserve(q.size() * TASK_WORDS);
+    for (const FactorTask& t : q) flat.insert(flat.end(), t.w, t.w + TASK_WORDS);
+    ntasks = (int)q.size();
+    ncounters_out = ncounters;
+    return 0;
+}
+
+static int build_factor_tasks(gpso_handle* h) {
+    if (h->chol_tasks_nb == h->nb) return 0;
+    std::vector<int> flat;
+    int ntasks = 0, ncounters = 0;
+    GP_TRY(make_factor_tasks(h->nb, h->nsm > 0 ? h->nsm : 148, flat, ntasks, ncounters));
+    GP_TRY(h->chol_tasks.ensure(flat.size() * sizeof(int)));
+    GP_TRY(h->chol_state.ensure((size_t)(2 + ncounters) * sizeof(int)));
+    CU_TRY(cudaMemcpy(h->chol_tasks.p, flat.data(), flat.size() * sizeof(int), cudaMemcpyHostToDevice));
+    h->chol_tasks_nb = h->nb;
+    h->chol_ntasks = ntasks;
+    h->chol_ncounters = ncounters;
+    return 0;
+}
+
+// Host-only introspection (no GPU needed): the task list for a matrix of nb panels on nsm SMs, TASK_WORDS ints per task.
+// Used by the CPU tests to check that the queue is a topological order of its own dependencies.
+extern "C" int gpso_debug_factor_tasks(int nb, int nsm, int* out, int64_t capacity_words, int* ntasks, int* ncounters) {
+    if (!ntasks || !ncounters) return fail(GPSO_E_BADARG, "gpso_debug_factor_tasks: null argument");
+    std::vector<int> flat;
+    GP_TRY(make_factor_tasks(nb, nsm, flat, *ntasks, *ncounters));
+    if (out) {
+        if (capacity_words < (int64_t)flat.size()) return fail(GPSO_E_BADARG, "gpso_debug_factor_tasks: buffer too small");
+        std::copy(flat.begin(), flat.end(), out);
+    }
     return 0;
 }
 
@@ -403,41 +504,45 @@ static int factor_pipeline(gpso_handle* h, cudaStream_t st, bool need_kinv) {
     P.p = 0;
     P.s = 0;
     if (h->chol_mode == 1 && nb > 1) {
-        GP_TRY(build_chol_tasks(h));
-        int* state = h->chol_state.as<int>();
-        CU_TRY(cudaMemsetAsync(state, 0, (size_t)(2 + nb * nb) * sizeof(int), st));
-        const int grid = std::min(h->chol_ntasks, h->nsm > 0 ? h->nsm : 148);
-        chol_persistent_kernel<<<grid, GTHREADS, DIAG_SMEM_BYTES, st>>>(P, h->N, h->chol_W, h->chol_tasks.as<unsigned>(), h->chol_ntasks, state,
-                                                                         h->logdet.as<double>(), h->info.as<int>());
-        GP_TRY(check_launch(h, "chol_persistent"));
-    } else
-    for (int p = 0; p < nb; p++) {
-        diag_factor_inverse_kernel<<<1, DIAG_THREADS, DIAG_SMEM_BYTES, st>>>(P.K, P.Linv, Np, p, h->N, h->logdet.as<double>(),
-                                                                             h->info.as<int>());
-        GP_TRY(check_launch(h, "diag_factor_inverse"));
-        int nt = nb - 1 - p;
-        if (nt > 0) {
-            P.p = p;
-            dense_gemm_kernel<MODE_CHOL_PANEL><<<nt, GTHREADS, GEMM_SMEM_BYTES, st>>>(P);
-            GP_TRY(check_launch(h, "chol_panel"));
-            dense_gemm_kernel<MODE_CHOL_TRAIL><<<nt*(nt + 1) / 2, GTHREADS, GEMM_SMEM_BYTES, st>>>(P);
-            GP_TRY(check_launch(h, "chol_trailing"));
-        }
-    }
-    diag_transpose_kernel<<<nb, 256, 0, st>>>(P.Linv, P.LinvT, Np);
-    GP_TRY(check_launch(h, "diag_transpose"));
-    if (nb > 1) {
+        // one persistent launch: blocked Cholesky + L^-1 (diagonal blocks, their transposes, recursive doubling)
+        GP_TRY(build_factor_tasks(h));
         GP_TRY(h->T.ensure((size_t)Np * Np * sizeof(double), true));
         P.T = h->T.as<double>();
-        for (int s = 1; s < nb; s *= 2) {
-            int cnt = 0;
-            for (int q = 0; 2 * q * s < nb; q++) cnt += s * trtri_pair_vtiles(nb, s, q);
-            if (cnt == 0) continue;
-            P.s = s;
-            dense_gemm_kernel<MODE_TRTRI_XT><<<cnt, GTHREADS, GEMM_SMEM_BYTES, st>>>(P);
-            GP_TRY(check_launch(h, "trtri_xt"));
-            dense_gemm_kernel<MODE_TRTRI_Y><<<cnt, GTHREADS, GEMM_SMEM_BYTES, st>>>(P);
-            GP_TRY(check_launch(h, "trtri_y"));
+        int* state = h->chol_state.as<int>();
+        CU_TRY(cudaMemsetAsync(state, 0, (size_t)(2 + h->chol_ncounters) * sizeof(int), st));
+        const int grid = std::min(h->chol_ntasks, h->nsm > 0 ? h->nsm : 148);
+        factor_persistent_kernel<<<grid, GTHREADS, DIAG_SMEM_BYTES, st>>>(P, h->N, h->chol_tasks.as<int>(), h->chol_ntasks, state,
+                                                                           h->logdet.as<double>(), h->info.as<int>());
+        GP_TRY(check_launch(h, "factor_persistent"));
+    } else {
+        for (int p = 0; p < nb; p++) {
+            diag_factor_inverse_kernel<<<1, DIAG_THREADS, DIAG_SMEM_BYTES, st>>>(P.K, P.Linv, Np, p, h->N, h->logdet.as<double>(),
+                                                                                 h->info.as<int>());
+            GP_TRY(check_launch(h, "diag_factor_inverse"));
+            int nt = nb - 1 - p;
+            if (nt > 0) {
+                P.p = p;
+                dense_gemm_kernel<MODE_CHOL_PANEL><<<nt, GTHREADS, GEMM_SMEM_BYTES, st>>>(P);
+                GP_TRY(check_launch(h, "chol_panel"));
+                dense_gemm_kernel<MODE_CHOL_TRAIL><<<nt*(nt + 1) / 2, GTHREADS, GEMM_SMEM_BYTES, st>>>(P);
+                GP_TRY(check_launch(h, "chol_trailing"));
+            }
+        }
+        diag_transpose_kernel<<<nb, 256, 0, st>>>(P.Linv, P.LinvT, Np);
+        GP_TRY(check_launch(h, "diag_transpose"));
+        if (nb > 1) {
+            GP_TRY(h->T.ensure((size_t)Np * Np * sizeof(double), true));
+            P.T = h->T.as<double>();
+            for (int s = 1; s < nb; s *= 2) {
+                int cnt = 0;
+                for (int q = 0; 2 * q * s < nb; q++) cnt += s * trtri_pair_vtiles(nb, s, q);
+                if (cnt == 0) continue;
+                P.s = s;
+                dense_gemm_kernel<MODE_TRTRI_XT><<<cnt, GTHREADS, GEMM_SMEM_BYTES, st>>>(P);
+                GP_TRY(check_launch(h, "trtri_xt"));
+                dense_gemm_kernel<MODE_TRTRI_Y><<<cnt, GTHREADS, GEMM_SMEM_BYTES, st>>>(P);
+                GP_TRY(check_launch(h, "trtri_y"));
+            }
         }
     }
     if (need_kinv) {

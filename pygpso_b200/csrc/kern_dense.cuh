@@ -221,17 +221,21 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // (L_pp^-1)^T for every diagonal block, after the factorisation loop (grid = nb): LinvT_pp[r][c] = Linv_pp[c][r]
-__global__ void __launch_bounds__(256) diag_transpose_kernel(const double* __restrict__ Linv, double* __restrict__ LinvT, int Np) {
-    __shared__ double tile[32][33];
-    const size_t base = (size_t)blockIdx.x * TB * Np + (size_t)blockIdx.x * TB;
+__device__ __forceinline__ void diag_transpose_device(const double* __restrict__ Linv, double* __restrict__ LinvT, int Np, int p,
+                                                      double* tile /* 32 x 33 doubles of shared memory */) {
+    const size_t base = (size_t)p * TB * Np + (size_t)p * TB;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     for (int bi = 0; bi < 4; bi++)
         for (int bj = 0; bj <= bi; bj++) {
             __syncthreads();
-            for (int r = ty; r < 32; r += 8) tile[r][tx] = Linv[base + (size_t)(bi * 32 + r) * Np + bj * 32 + tx];
+            for (int r = ty; r < 32; r += 8) tile[r * 33 + tx] = __ldcg(Linv + base + (size_t)(bi * 32 + r) * Np + bj * 32 + tx);
             __syncthreads();
-            for (int r = ty; r < 32; r += 8) LinvT[base + (size_t)(bj * 32 + r) * Np + bi * 32 + tx] = tile[tx][r];
+            for (int r = ty; r < 32; r += 8) LinvT[base + (size_t)(bj * 32 + r) * Np + bi * 32 + tx] = tile[tx * 33 + r];
         }
+}
+__global__ void __launch_bounds__(256) diag_transpose_kernel(const double* __restrict__ Linv, double* __restrict__ LinvT, int Np) {
+    __shared__ double tile[32 * 33];
+    diag_transpose_device(Linv, LinvT, Np, blockIdx.x, tile);
 }
 
 // Lprev != nullptr: the tile still lacks its last update; it is applied here, in shared memory, before the factorisation:
@@ -538,28 +542,34 @@ __global__ void __launch_bounds__(GTHREADS, 1) dense_gemm_kernel(DenseParams P) 
     gemm_tile_device<MODE>(P, blockIdx.x, smem);
 }
 
-// ---- persistent blocked Cholesky: one CTA per SM, tile tasks pulled from two dependency-ordered queues ----------------
-// Two-level blocking: panels are grouped in blocks of W (4 for large matrices, 2 below 48 panels).  A tile (i, j) in block
+// ---- persistent factorisation: one CTA per SM, tile tasks with explicit dependencies ----------------------------------
+// One launch runs the blocked Cholesky AND the inverse factor.  The host (gpso_capi.cu: build_factor_tasks) writes every
+// task with the counters it waits for and the counter it signals; the kernel is an interpreter.
+//
+// Cholesky.  Two-level blocking: panels are grouped in blocks of W (4 from 48 panels up, else 2).  A tile (i, j) in block
 // column bj = j / W receives, in this order, bj "wide" updates (one per earlier block, K = W * 128: the read-modify-write of
 // the tile -- 8 us at the ~14 B/clk an SM can store -- is paid once per W panels), then j - bj*W "narrow" updates from the
 // earlier panels of its own block (K = 128), then its final operation (factor+invert if i == j, panel solve otherwise).
-// cnt[i*nb + j] counts the operations completed on the tile; ops(j) = bj + (j - bj*W) updates, final when cnt == ops(j) + 1.
-// The last update of a diagonal tile (narrow, or wide for the first panel of a block) is applied inside its DIAG task
-// (fused), not as a task of its own.
-// Task word: type << 24 | p << 16 | i << 8 | j   (p = panel, or block for WIDE).
-//   DIAG(p)       p = 0: nothing to wait for;  else waits cnt[p,p] >= ops(p)-1 and tile (p,p-1) final (the last update,
-//                 narrow or wide, is fused)                                       sets cnt[p,p] = ops(p)+1
-//   PANEL(i,p)    waits cnt[p,p] >= ops(p)+1, cnt[i,p] >= ops(p)                  sets cnt[i,p] = ops(p)+1
-//   UPD(i,j,p)    (p, j in one block) waits cnt[i,p], cnt[j,p] >= ops(p)+1, cnt[i,j] >= bj + p - bj*W   sets it +1
-//   WIDE(i,j,b)   (j beyond block b, q = last panel of b) waits cnt[i,q], cnt[j,q] >= ops(q)+1, cnt[i,j] >= b   sets b+1
-// Scheduling: one queue in a topological order chosen by the host (gpso_capi.cu: build_chol_tasks), tickets by atomicAdd
-// (no contention; claiming the queue head with compare-and-swap after a readiness check was tried and serialises at one
-// claim per ~3 us).  A CTA that draws a task whose inputs are not complete polls their counters.  Every dependency of a
-// task sits earlier in the queue and a CTA holds one task at a time, so the CTA that owns the oldest unfinished task can
-// always run: no deadlock as long as tasks are only taken by resident CTAs (grid <= #SMs).  The order threads the
-// factorisation chain of block b+1 through the wide updates of block b (look-ahead).
-// Tiles cross SMs through L2 only (cp.async.cg / ld.cg), flags with release / acquire at gpu scope.
-constexpr int CT_DIAG = 0, CT_PANEL = 1, CT_UPD = 2, CT_WIDE = 3;
+// A counter per tile counts the operations completed on it (ops(j) = bj + j - bj*W updates, final at ops(j) + 1).  The
+// last update of a diagonal tile (narrow, or wide for the first panel of a block) is fused into its DIAG task.
+//   DIAG(p)       waits tile (p,p) at ops(p)-1 and tile (p,p-1) final       PANEL(i,p)  waits (p,p) final, (i,p) at ops(p)
+//   UPD(i,j,p)    waits (i,p), (j,p) final, (i,j) at bj + p - bj*W          WIDE(i,j,b) waits (i,q), (j,q) final (q = last
+//                                                                            panel of b), (i,j) at b
+// Inverse factor by recursive doubling (level s merges the inverses of tile ranges [a, a+s) and [a+s, a+2s)):
+//   TRANSPOSE(p)  (L_pp^-1)^T -> LinvT                                      waits DIAG(p)
+//   XT(s,q,u,v)   T = LinvT11 L21^T            waits all transposes, the level-s/2 merge of the first half, row a+s+v of L
+//   Y(s,q,u,v)    Linv21 = -Linv22 T (+ LinvT12)  waits all XT of the pair and the inverse of the second half
+// Scheduling: tickets by atomicAdd from one queue in a topological order chosen by the host (claiming the queue head with
+// compare-and-swap after a readiness check was tried and serialises at one claim per ~3 us).  A CTA that draws a task
+// whose inputs are not complete polls their counters.  Every dependency of a task sits earlier in the queue and a CTA
+// holds one task at a time, so the CTA that owns the oldest unfinished task can always run: no deadlock as long as tasks
+// are only taken by resident CTAs (grid <= #SMs).  The order threads the factorisation chain of block b+1 through the wide
+// updates of block b (look-ahead).  Tiles cross SMs through L2 only (cp.async.cg / ld.cg), counters with release / acquire
+// at gpu scope.
+constexpr int CT_DIAG = 0, CT_PANEL = 1, CT_UPD = 2, CT_TRANSPOSE = 3, CT_XT = 4, CT_Y = 5;
+constexpr int TASK_WORDS = 16;
+// task words: 0 op | 1 p | 2 i | 3 j | 4 s | 5 tile | 6-8 dependency counter (-1: none) | 9-11 value it must reach |
+//             12 counter to signal | 13 value to store with release (0: add 1) | 14-15 unused
 __host__ __device__ inline int chol_ops(int j, int W) { return j / W + j % W; }
 constexpr long long CHOL_SPIN_LIMIT = 1LL << 24;  // polls (each >= 100 ns) before a waiter gives up and reports an error
 
@@ -582,68 +592,63 @@ __device__ __forceinline__ bool chol_wait(const int* c, int need, int* err) {
     return true;
 }
 
-// state: [0] next ticket, [1] error flag, [2...] cnt[nb*nb]
-__global__ void __launch_bounds__(GTHREADS, 1) chol_persistent_kernel(DenseParams P, int N, int W, const unsigned* __restrict__ tasks,
-                                                                      int ntasks, int* __restrict__ state, double* __restrict__ logdet,
-                                                                      int* __restrict__ info) {
+// state: [0] next ticket, [1] error flag, [2...] counters
+__global__ void __launch_bounds__(GTHREADS, 1) factor_persistent_kernel(DenseParams P, int N, const int* __restrict__ tasks, int ntasks,
+                                                                        int* __restrict__ state, double* __restrict__ logdet,
+                                                                        int* __restrict__ info) {
     extern __shared__ __align__(16) double smem[];
+    __shared__ int s_t[TASK_WORDS];
     __shared__ int s_task, s_ok;
-    const int nb = P.nb;
     int* err = state + 1;
-    int* cnt = state + 2;
+    int* ctr = state + 2;
     if (threadIdx.x == 0) s_ok = 1;
     for (;;) {
         if (threadIdx.x == 0) s_task = atomicAdd(state, 1);
         __syncthreads();
         const int t = s_task;
         if (t >= ntasks) break;
-        const unsigned w = tasks[t];
-        const int type = w >> 24, p = (w >> 16) & 255, i = (w >> 8) & 255, j = w & 255;
+        if (threadIdx.x < TASK_WORDS) s_t[threadIdx.x] = tasks[(size_t)t * TASK_WORDS + threadIdx.x];
+        __syncthreads();
         if (threadIdx.x == 0) {
-            bool ok;
-            if (type == CT_DIAG) {
-                ok = p == 0 || (chol_wait(cnt + p * nb + p, chol_ops(p, W) - 1, err) && chol_wait(cnt + p * nb + p - 1, chol_ops(p - 1, W) + 1, err));
-            } else if (type == CT_PANEL) {
-                ok = chol_wait(cnt + p * nb + p, chol_ops(p, W) + 1, err) && chol_wait(cnt + i * nb + p, chol_ops(p, W), err);
-            } else if (type == CT_UPD) {
-                ok = chol_wait(cnt + i * nb + p, chol_ops(p, W) + 1, err) && chol_wait(cnt + j * nb + p, chol_ops(p, W) + 1, err) &&
-                     chol_wait(cnt + i * nb + j, j / W + p % W, err);
-            } else {
-                const int q = min(nb, (p + 1) * W) - 1;  // last panel of block p
-                ok = chol_wait(cnt + i * nb + q, chol_ops(q, W) + 1, err) && chol_wait(cnt + j * nb + q, chol_ops(q, W) + 1, err) &&
-                     chol_wait(cnt + i * nb + j, p, err);
-            }
+            bool ok = true;
+            for (int k = 0; k < 3 && ok; k++)
+                if (s_t[6 + k] >= 0) ok = chol_wait(ctr + s_t[6 + k], s_t[9 + k], err);
             s_ok = ok;
         }
         __syncthreads();
         if (!s_ok) break;
-        int* done;
-        int done_val;
-        if (type == CT_DIAG) {
-            const int nprev = p == 0 ? 0 : (p % W != 0 ? 1 : W);
-            const double* Lprev = nprev ? P.K + (size_t)p * TB * P.Np + (size_t)(p - nprev) * TB : nullptr;
-            diag_block_device(P.K, P.Linv, P.Np, p, N, logdet, info, smem, Lprev, nprev);
-            done = cnt + p * nb + p;
-            done_val = chol_ops(p, W) + 1;
-        } else if (type == CT_PANEL) {
+        const int op = s_t[0], p = s_t[1], i = s_t[2], j = s_t[3], sx = s_t[4], tile = s_t[5], done_idx = s_t[12], done_val = s_t[13];
+        if (op == CT_DIAG) {
+            const double* Lprev = sx ? P.K + (size_t)p * TB * P.Np + (size_t)(p - sx) * TB : nullptr;
+            diag_block_device(P.K, P.Linv, P.Np, p, N, logdet, info, smem, Lprev, sx);
+        } else if (op == CT_PANEL) {
             DenseParams Q = P;
             Q.p = p;
             gemm_tile_device<MODE_CHOL_PANEL>(Q, i - p - 1, smem);
-            done = cnt + i * nb + p;
-            done_val = chol_ops(p, W) + 1;
-        } else {
+        } else if (op == CT_UPD) {
             DenseParams Q = P;
             Q.ui = i;
             Q.uj = j;
-            Q.uk0 = (type == CT_UPD) ? p : p * W;
-            Q.ukn = (type == CT_UPD) ? 1 : min(nb, (p + 1) * W) - p * W;
+            Q.uk0 = p;
+            Q.ukn = sx;
             gemm_tile_device<MODE_CHOL_UPD>(Q, 0, smem);
-            done = cnt + i * nb + j;
-            done_val = (type == CT_UPD) ? j / W + p % W + 1 : p + 1;
+        } else if (op == CT_TRANSPOSE) {
+            diag_transpose_device(P.Linv, P.LinvT, P.Np, p, smem);
+        } else if (op == CT_XT) {
+            DenseParams Q = P;
+            Q.s = sx;
+            gemm_tile_device<MODE_TRTRI_XT>(Q, tile, smem);
+        } else {
+            DenseParams Q = P;
+            Q.s = sx;
+            gemm_tile_device<MODE_TRTRI_Y>(Q, tile, smem);
         }
         __threadfence();
         __syncthreads();
-        if (threadIdx.x == 0) st_release(done, done_val);
+        if (threadIdx.x == 0) {
+            if (done_val > 0) st_release(ctr + done_idx, done_val);
+            else atomicAdd(ctr + done_idx, 1);  // after the fence above: a release increment
+        }
     }
     if (threadIdx.x == 0 && !s_ok) atomicExch(info, -1);  // a dependency never arrived: reported as a scheduler failure
 }

@@ -1,0 +1,70 @@
+"""
+Host-side check of the task list the persistent factorisation kernel executes (no GPU needed: the list is built by the
+library on the host, ``gpso_debug_factor_tasks``).  The kernel hands out tasks in queue order and a CTA waits for the
+counters its task names, so the schedule is deadlock-free exactly when the queue is a topological order of those
+dependencies: replaying it sequentially, every dependency must already be satisfied when its task comes up.  The replay
+also checks the per-tile operation counts of the blocked Cholesky and that every pair of the inverse recursion is complete.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+
+from pygpso_b200 import backend
+
+OPS = {0: "DIAG", 1: "PANEL", 2: "UPD", 3: "TRANSPOSE", 4: "XT", 5: "Y"}
+
+
+def task_list(nb, nsm=148):
+    lib = backend.load_library()
+    nt, nc = ctypes.c_int(0), ctypes.c_int(0)
+    assert lib.gpso_debug_factor_tasks(nb, nsm, None, 0, ctypes.byref(nt), ctypes.byref(nc)) == 0
+    buf = np.zeros(nt.value * 16, dtype=np.int32)
+    rc = lib.gpso_debug_factor_tasks(nb, nsm, buf.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), buf.size, ctypes.byref(nt), ctypes.byref(nc))
+    assert rc == 0
+    return buf.reshape(-1, 16), nc.value
+
+
+@pytest.mark.parametrize("nb", [2, 3, 4, 5, 7, 8, 9, 16, 31, 32, 33, 47, 48, 49, 64, 65])
+def test_queue_is_topological_and_complete(nb):
+    tasks, ncounters = task_list(nb)
+    W = 4 if nb >= 48 else 2
+    ops = lambda j: j // W + j % W
+    ctr = np.zeros(ncounters, dtype=np.int64)
+    seen = {name: 0 for name in OPS.values()}
+    for t in tasks:
+        op = OPS[int(t[0])]
+        seen[op] += 1
+        for k in range(3):
+            if t[6 + k] >= 0:
+                assert ctr[t[6 + k]] >= t[9 + k], (op, t.tolist(), int(ctr[t[6 + k]]))
+        if t[13] > 0:
+            # tile counters only ever move forward by one operation (updates are applied in order) -- except the diagonal
+            # tile, whose last update is fused into its DIAG task
+            step = t[13] - ctr[t[12]]
+            assert step == (2 if op == "DIAG" and t[1] > 0 else 1), (op, t.tolist(), int(ctr[t[12]]))
+            ctr[t[12]] = t[13]
+        else:
+            ctr[t[12]] += 1
+    # every tile of the lower triangle is final, every transpose done
+    for i in range(nb):
+        for j in range(i + 1):
+            assert ctr[i * nb + j] == ops(j) + 1, (i, j, int(ctr[i * nb + j]))
+    assert ctr[nb * nb] == nb
+    assert seen["DIAG"] == nb and seen["TRANSPOSE"] == nb and seen["PANEL"] == nb * (nb - 1) // 2
+    # the inverse recursion: XT and Y tiles of every level, s * nv per pair
+    expect = 0
+    s = 1
+    while s < nb:
+        q = 0
+        while 2 * q * s < nb:
+            rem = nb - (2 * q * s + s)
+            expect += s * max(0, min(rem, s))
+            q += 1
+        s *= 2
+    assert seen["XT"] == expect and seen["Y"] == expect
+
+
+def test_single_panel_matrix_has_no_scheduler_tasks_beyond_the_block():
+    tasks, _ = task_list(1)
+    assert [OPS[int(t[0])] for t in tasks] == ["DIAG", "TRANSPOSE"]
