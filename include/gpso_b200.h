@@ -112,6 +112,11 @@ int gpso_debug_fetch(gpso_handle* h, int which, double* out_host, int64_t count)
 int gpso_last_timing(gpso_handle* h, double* out_ms4);
 int gpso_set_profile(gpso_handle* h, int enabled);
 int64_t gpso_last_windows(gpso_handle* h);
+/* gpso_set_profile(h, 2): record a timeline of the window pipeline of the next scoring calls without giving up the stream
+ * overlap.  gpso_debug_trace copies (tag, window, ms since the first event) triples of the last call to out (capacity in
+ * doubles) and returns how many doubles the trace holds; tags: 1/2 cross-covariance start/end (side stream), 3/4
+ * variance product start/end, 5 finalise + arg-max merge end (product stream). */
+int64_t gpso_debug_trace(gpso_handle* h, double* out, int64_t capacity);
 /* Engine of the variance product V = L^-1 k* inside predict_y / ucb_argmax (takes effect at the next gpso_factorize):
  *   mode 0 automatic (int8 when the padded N >= 512), 1 = FP64 DMMA (mma.sync m8n8k4.f64), 2 = exact-integer emulation
  *   of the fp64 product on the int8 tensor cores (tcgen05.mma kind::i8, accumulators in TMEM).

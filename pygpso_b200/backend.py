@@ -87,6 +87,7 @@ def load_library():
         "gpso_debug_factor_tasks": (i32, [i32, i32, ctypes.POINTER(ctypes.c_int), i64, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]),
         "gpso_set_profile": (i32, [H, i32]),
         "gpso_last_windows": (i64, [H]),
+        "gpso_debug_trace": (i64, [H, _c_double_p, i64]),
     }
     for name, (restype, argtypes) in protos.items():
         try:
@@ -107,7 +108,7 @@ EXPORTED_SYMBOLS = (
     "gpso_grow_count gpso_grow_leaves_host gpso_grow_leaves_dev gpso_grow_ucb_argmax gpso_state_bytes "
     "gpso_export_state_dev gpso_import_state_dev gpso_launch_count gpso_debug_fetch gpso_last_timing gpso_set_window "
     "gpso_set_profile gpso_last_windows gpso_set_predict_mode gpso_predict_info gpso_set_overlap "
-    "gpso_set_factor_mode gpso_debug_factor_tasks"
+    "gpso_set_factor_mode gpso_debug_factor_tasks gpso_debug_trace"
 ).split()
 
 
@@ -226,7 +227,15 @@ class CudaSession:
         return out
 
     def set_profile(self, enabled=True):
-        _check(self._lib, self._lib.gpso_set_profile(self._h, int(bool(enabled))), "gpso_set_profile")
+        """True/1: per-stage events (windows run in order); 2: timeline trace with the stream overlap kept; 0 off."""
+        _check(self._lib, self._lib.gpso_set_profile(self._h, int(enabled)), "gpso_set_profile")
+
+    def trace(self):
+        """Timeline of the last scoring call after ``set_profile(2)``: array of (tag, window, ms) rows."""
+        n = int(self._lib.gpso_debug_trace(self._h, None, 0))
+        out = np.zeros(max(n, 1))
+        self._lib.gpso_debug_trace(self._h, _dptr(out), n)
+        return out[:n].reshape(-1, 3)
 
     def last_windows(self):
         return int(self._lib.gpso_last_windows(self._h))

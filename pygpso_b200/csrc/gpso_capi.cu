@@ -53,7 +53,7 @@ namespace {
 constexpr int MAX_LS = LEAF_MAXD;  // maximum input dimension supported
 constexpr double NOISE_FLOOR = 1.0e-6;
 constexpr long long WINDOW_BYTES = 2LL << 30;  // rolling cross-covariance window budget (2 GiB)
-constexpr int OZ_XCOV_SMEM_MAX = 112 * 1024;   // crosscov_slices_kernel dynamic shared memory at d = 64
+constexpr int OZ_XCOV_SMEM_MAX = 172 * 1024;   // crosscov_slices_kernel dynamic shared memory at d = 64 (320 d + 768 doubles)
 constexpr int OZ_MIN_NP = 512;                 // below this the int8 path is not worth its fixed costs (automatic mode)
 constexpr int OZ_MAX_NP = 16384;               // int32 accumulators stay exact: S * 2^14 * Np < 2^31
 constexpr double OZ_TARGET = 0.02;             // accepted (estimated error) / (parity tolerance 1e-8 * variance)
@@ -137,6 +137,13 @@ struct gpso_handle {
     std::vector<cudaEvent_t> prod_events;
     size_t prod_used = 0;
     long long last_windows = 0;
+    // optional timeline of the window pipeline (gpso_set_profile(h, 2)): events on the streams the kernels run on, the
+    // overlap stays in force; read back with gpso_debug_trace as (tag, window, ms since the first event) triples
+    bool trace = false;
+    std::vector<cudaEvent_t> trace_events;
+    std::vector<int> trace_tags;
+    size_t trace_used = 0;
+    std::vector<double> trace_out;
     int n_ls() const { return ard ? d : 1; }
     int n_params() const { return n_ls() + 2 + (mean_id == GPSO_MEAN_CONSTANT ? 1 : 0); }
 };
@@ -191,7 +198,7 @@ static int oz_configure() {
     return 0;
 }
 
-static size_t oz_xcov_smem(int d) { return (size_t)(OZ_NT * (d | 1) + 2 * d * 64 + 2 * 64 + 4 * 64) * sizeof(double); }
+static size_t oz_xcov_smem(int d) { return (size_t)(OZ_NT * d + 2 * d * OZ_XK + 2 * OZ_XK + 8 * OZ_NT) * sizeof(double); }
 
 template <int KID, int S>
 static void launch_oz_crosscov(gpso_handle* h, cudaStream_t st, const double* Xc, long long Mw, long long nct, double bscale,
@@ -854,6 +861,21 @@ static int prof_mark(gpso_handle* h, cudaStream_t st) {
     return 0;
 }
 
+static int trace_mark(gpso_handle* h, cudaStream_t st, int tag, long long window) {
+    if (!h->trace) return 0;
+    if (h->trace_used == h->trace_events.size()) {
+        cudaEvent_t e;
+        CU_TRY(cudaEventCreate(&e));
+        h->trace_events.push_back(e);
+        h->trace_tags.push_back(0);
+        h->trace_tags.push_back(0);
+    }
+    h->trace_tags[2 * h->trace_used] = tag;
+    h->trace_tags[2 * h->trace_used + 1] = (int)window;
+    CU_TRY(cudaEventRecord(h->trace_events[h->trace_used++], st));
+    return 0;
+}
+
 static int prod_mark(gpso_handle* h, cudaStream_t st) {
     if (h->prod_used == h->prod_events.size()) {
         cudaEvent_t e;
@@ -873,6 +895,17 @@ static void prof_collect(gpso_handle* h) {
         h->last_ms[2] += t;
     }
     h->prod_used = 0;
+    if (h->trace) {
+        h->trace_out.clear();
+        for (size_t i = 0; i < h->trace_used; i++) {
+            float t = 0;
+            cudaEventElapsedTime(&t, h->trace_events[0], h->trace_events[i]);
+            h->trace_out.push_back((double)h->trace_tags[2 * i]);
+            h->trace_out.push_back((double)h->trace_tags[2 * i + 1]);
+            h->trace_out.push_back((double)t);
+        }
+        h->trace_used = 0;
+    }
     if (!h->profile) return;
     h->last_ms[2] = 0.0;
     for (size_t i = 0; i + 3 < h->prof_used; i += 4) {
@@ -953,6 +986,7 @@ static int run_windows(gpso_handle* h, cudaStream_t st, const double* Xc_dev, co
         // ---- 2. cross-covariance (+ posterior mean)
         if (overlap && buf_busy[b]) CU_TRY(cudaStreamWaitEvent(xs, h->ev_free[b], 0));  // finalise(w-2) has read buffer b
         GP_TRY(prof_mark(h, xs));
+        GP_TRY(trace_mark(h, xs, 1, w));
         double gscale = 0.0;
         long long nct = 0;
         if (oz) {
@@ -967,6 +1001,7 @@ static int run_windows(gpso_handle* h, cudaStream_t st, const double* Xc_dev, co
             DISPATCH_KID(h, launch_crosscov, h, xs, src, Mw, Mw_pad);
             GP_TRY(check_launch(h, "crosscov"));
         }
+        GP_TRY(trace_mark(h, xs, 2, w));
         if (host) {
             CU_TRY(cudaEventRecord(h->ev_used[cb], xs));
             cand_busy[cb] = true;
@@ -978,6 +1013,7 @@ static int run_windows(gpso_handle* h, cudaStream_t st, const double* Xc_dev, co
         // ---- 3. variance product: part[I][c] = sum over the rows of block I of (L^-1 k*)^2
         GP_TRY(prof_mark(h, st));
         GP_TRY(prod_mark(h, st));
+        GP_TRY(trace_mark(h, st, 3, w));
         if (oz) {
             DISPATCH_S(h->oz_S, launch_oz_trmm, h, st, nct, Mw_pad, gscale, h->ozBb[b].as<uint8_t>());
             GP_TRY(check_launch(h, "ozaki_trmm"));
@@ -996,6 +1032,7 @@ static int run_windows(gpso_handle* h, cudaStream_t st, const double* Xc_dev, co
             GP_TRY(check_launch(h, "predict_trmm"));
         }
         GP_TRY(prod_mark(h, st));
+        GP_TRY(trace_mark(h, st, 4, w));
         GP_TRY(prof_mark(h, st));
         // ---- 4. finalise: var, ucb, window arg-max merged into the running record
         double* om = mode == 0 ? (host ? h->omean.as<double>() : mean_out + off) : nullptr;
@@ -1009,6 +1046,7 @@ static int run_windows(gpso_handle* h, cudaStream_t st, const double* Xc_dev, co
             GP_TRY(check_launch(h, "best_merge"));
         }
         GP_TRY(prof_mark(h, st));
+        GP_TRY(trace_mark(h, st, 5, w));
         if (overlap) {
             CU_TRY(cudaEventRecord(h->ev_free[b], st));
             buf_busy[b] = true;
@@ -1031,6 +1069,7 @@ static int predict_common_checks(gpso_handle* h, const void* a, long long M, con
     if (!h->factorized) return fail(GPSO_E_STATE, std::string(who) + ": call gpso_factorize first");
     h->prof_used = 0;
     h->prod_used = 0;
+    h->trace_used = 0;
     h->last_windows = 0;
     return set_device(h);
 }
@@ -1291,8 +1330,17 @@ extern "C" int gpso_last_timing(gpso_handle* h, double* out_ms4) {
 
 extern "C" int gpso_set_profile(gpso_handle* h, int enabled) {
     if (!h) return fail(GPSO_E_BADARG, "gpso_set_profile: null handle");
-    h->profile = enabled != 0;
+    h->profile = enabled == 1;  // per-stage events, windows run in order
+    h->trace = enabled == 2;    // timeline events on the side streams, overlap kept
     return 0;
+}
+
+extern "C" int64_t gpso_debug_trace(gpso_handle* h, double* out, int64_t capacity) {
+    if (!h) return -1;
+    int64_t n = (int64_t)h->trace_out.size();
+    if (out)
+        for (int64_t i = 0; i < n && i < capacity; i++) out[i] = h->trace_out[i];
+    return n;
 }
 
 extern "C" int64_t gpso_last_windows(gpso_handle* h) { return h ? h->last_windows : 0; }

@@ -194,74 +194,106 @@ __global__ void __launch_bounds__(256) linv_slices_kernel(const double* __restri
 }
 
 // ---- B digit tiles + posterior mean from the candidates -------------------------------------------------------------
-// One block = one candidate tile (64 candidates) x all training points, in super-steps of 64 training points.
-// thread: c = tid & 63 (candidate), kq = tid >> 6 (which 16 of the 64 training points).  Every candidate goes through the
-// same operation sequence (position-independent results).
+// One block = one candidate tile (64 candidates) x all training points, in super-steps of OZ_XK = 128 training points.
+// Register tile per thread: 2 candidates (cl and cl + 32, cl = lane) x 16 consecutive training points (warp w owns points
+// 16 w .. 16 w + 15 of the super-step), so that every shared-memory load feeds 16 or 32 distance updates: the training
+// coordinates are warp-wide broadcasts (LDS.128, one wavefront for two points), the candidate coordinates two conflict-free
+// LDS.64 per dimension.  ~0.1 shared-memory wavefronts per covariance element instead of 0.35 -- this kernel runs beside the
+// persistent tensor-core product kernel of the previous window, which keeps the shared-memory ports ~85 % busy with UMMA
+// operand reads and bulk-copy writes (profiles/r01s4_overlap.md); and 32 independent covariance chains per thread keep the
+// FP64 pipe fed with 8 warps.  Every candidate goes through the same operation sequence (position-independent results).
+constexpr int OZ_XK = 128;  // training points per super-step of crosscov_slices_kernel
+constexpr int XW = 4;       // covariance evaluations interleaved per thread (independent FP64 chains)
+
 template <int KID, int S>
-__global__ void __launch_bounds__(256) crosscov_slices_kernel(const double* __restrict__ Xc, long long Mw, int d,
+__global__ void __launch_bounds__(256, 2) crosscov_slices_kernel(const double* __restrict__ Xc, long long Mw, int d,
                                                               const double* __restrict__ ls, int n_ls,
                                                               const double* __restrict__ Xs, const double* __restrict__ alpha, int N,
                                                               int Np, double var, double c0, double bscale, int nks,
                                                               uint8_t* __restrict__ B, double* __restrict__ mean) {
     extern __shared__ double sm[];
-    const int dp = d | 1;
-    double* sC = sm;                    // [64][dp]   scaled candidate coordinates
-    double* sX = sC + OZ_NT * dp;       // [2][d][64] scaled training coordinates of the current / next super-step
-    double* sAl = sX + 2 * d * 64;      // [2][64]
-    double* sR = sAl + 2 * 64;          // [4][64]
-    const int tid = threadIdx.x, c = tid & 63, kq = tid >> 6;
+    double* sC = sm;                      // [d][64]       scaled candidate coordinates, dimension-major
+    double* sX = sC + d * OZ_NT;          // [2][d][128]   scaled training coordinates of the current / next super-step
+    double* sAl = sX + 2 * d * OZ_XK;     // [2][128]
+    double* sR = sAl + 2 * OZ_XK;         // [8][64]       per-warp partial means
+    const int tid = threadIdx.x, cl = tid & 31, kg = tid >> 5;
     const long long ct = blockIdx.x;
-    const long long cand = ct * OZ_NT + c;
     for (int e = tid; e < OZ_NT * d; e += 256) {
         int cc = e / d, dim = e - cc * d;
         long long cg = ct * OZ_NT + cc;
-        sC[cc * dp + dim] = (cg < Mw) ? Xc[cg * d + dim] / ls[n_ls > 1 ? dim : 0] : 0.0;
+        sC[dim * OZ_NT + cc] = (cg < Mw) ? Xc[cg * d + dim] / ls[n_ls > 1 ? dim : 0] : 0.0;
     }
-    for (int e = tid; e < d * 64; e += 256) sX[e] = Xs[(size_t)(e >> 6) * Np + (e & 63)];
-    if (tid < 64) sAl[tid] = alpha[tid];
-    const bool cvalid = cand < Mw;
-    double macc = 0.0;
-    const int nss = Np / 64;
+    for (int e = tid; e < d * OZ_XK; e += 256) sX[e] = Xs[(size_t)(e >> 7) * Np + (e & 127)];
+    if (tid < OZ_XK) sAl[tid] = alpha[tid];
+    const bool cvalid[2] = {ct * OZ_NT + cl < Mw, ct * OZ_NT + cl + 32 < Mw};
+    double macc[2] = {0.0, 0.0};
+    const int nss = Np / OZ_XK;
     for (int ss = 0; ss < nss; ss++) {
         __syncthreads();
         const int b = ss & 1;
         if (ss + 1 < nss) {
-            double* nx = sX + (b ^ 1) * d * 64;
-            for (int e = tid; e < d * 64; e += 256) nx[e] = Xs[(size_t)(e >> 6) * Np + (ss + 1) * 64 + (e & 63)];
-            if (tid < 64) sAl[(b ^ 1) * 64 + tid] = alpha[(ss + 1) * 64 + tid];
+            double* nx = sX + (b ^ 1) * d * OZ_XK;
+            for (int e = tid; e < d * OZ_XK; e += 256) nx[e] = Xs[(size_t)(e >> 7) * Np + (ss + 1) * OZ_XK + (e & 127)];
+            if (tid < OZ_XK) sAl[(b ^ 1) * OZ_XK + tid] = alpha[(ss + 1) * OZ_XK + tid];
         }
-        const double* x = sX + b * d * 64 + kq * 16;
-        double r2[16];
+        const double* x = sX + b * d * OZ_XK + kg * 16;
+        double r2[2][16];
 #pragma unroll
-        for (int i = 0; i < 16; i++) r2[i] = 0.0;
+        for (int i = 0; i < 16; i++) r2[0][i] = r2[1][i] = 0.0;
         for (int dim = 0; dim < d; dim++) {
-            const double xc = sC[c * dp + dim];
+            const double xa = sC[dim * OZ_NT + cl];
+            const double xb = sC[dim * OZ_NT + cl + 32];
+            const double2* xr = reinterpret_cast<const double2*>(x + dim * OZ_XK);
 #pragma unroll
-            for (int i = 0; i < 16; i++) {
-                double df = x[dim * 64 + i] - xc;
-                r2[i] = fma(df, df, r2[i]);
+            for (int i = 0; i < 8; i++) {
+                const double2 xv = xr[i];
+                double df = xv.x - xa;
+                r2[0][2 * i] = fma(df, df, r2[0][2 * i]);
+                df = xv.y - xa;
+                r2[0][2 * i + 1] = fma(df, df, r2[0][2 * i + 1]);
+                df = xv.x - xb;
+                r2[1][2 * i] = fma(df, df, r2[1][2 * i]);
+                df = xv.y - xb;
+                r2[1][2 * i + 1] = fma(df, df, r2[1][2 * i + 1]);
             }
         }
-        uint32_t out[S][4];
+        const int j0 = ss * OZ_XK + kg * 16;
+        const int ks = ss * 4 + (kg >> 1), half = kg & 1;
+        const double* al = sAl + b * OZ_XK + kg * 16;
 #pragma unroll
-        for (int p = 0; p < S; p++) out[p][0] = out[p][1] = out[p][2] = out[p][3] = 0u;
-        const int j0 = ss * 64 + kq * 16;
+        for (int a = 0; a < 2; a++) {
+            uint32_t out[S][4];
 #pragma unroll
-        for (int i = 0; i < 16; i++) {
-            double k = (cvalid && j0 + i < N) ? cov_from_r2<KID>(r2[i], var) : 0.0;
-            macc = fma(k, sAl[b * 64 + kq * 16 + i], macc);
-            unsigned long long z = oz_digits<S>(k, bscale);
+            for (int p = 0; p < S; p++) out[p][0] = out[p][1] = out[p][2] = out[p][3] = 0u;
 #pragma unroll
-            for (int p = 0; p < S; p++) out[p][i >> 2] = oz_put(out[p][i >> 2], z, S - 1 - p, i & 3);
+            for (int g = 0; g < 16; g += XW) {
+                double rr[XW], kk[XW];
+#pragma unroll
+                for (int i = 0; i < XW; i++) rr[i] = r2[a][g + i];
+                cov_from_r2_v<KID, XW>(rr, var, kk);
+#pragma unroll
+                for (int i = 0; i < XW; i++) {
+                    const double k = (cvalid[a] && j0 + g + i < N) ? kk[i] : 0.0;
+                    macc[a] = fma(k, al[g + i], macc[a]);
+                    unsigned long long z = oz_digits<S>(k, bscale);
+#pragma unroll
+                    for (int p = 0; p < S; p++) out[p][(g + i) >> 2] = oz_put(out[p][(g + i) >> 2], z, S - 1 - p, (g + i) & 3);
+                }
+            }
+            const int c = cl + 32 * a;
+            uint8_t* dst = B + ((size_t)ct * nks + ks) * S * OZ_B_SLICE + (c >> 3) * 256 + half * 128 + (c & 7) * 16;
+#pragma unroll
+            for (int p = 0; p < S; p++) *reinterpret_cast<uint4*>(dst + (size_t)p * OZ_B_SLICE) = make_uint4(out[p][0], out[p][1], out[p][2], out[p][3]);
         }
-        const int ks = ss * 2 + (kq >> 1), half = kq & 1;
-        uint8_t* dst = B + ((size_t)ct * nks + ks) * S * OZ_B_SLICE + (c >> 3) * 256 + half * 128 + (c & 7) * 16;
-#pragma unroll
-        for (int p = 0; p < S; p++) *reinterpret_cast<uint4*>(dst + (size_t)p * OZ_B_SLICE) = make_uint4(out[p][0], out[p][1], out[p][2], out[p][3]);
     }
-    sR[kq * 64 + c] = macc;
+    sR[kg * OZ_NT + cl] = macc[0];
+    sR[kg * OZ_NT + cl + 32] = macc[1];
     __syncthreads();
-    if (tid < 64) mean[ct * OZ_NT + tid] = ((sR[tid] + sR[64 + tid]) + (sR[128 + tid] + sR[192 + tid])) + c0;
+    if (tid < OZ_NT) {
+        const double* q = sR + tid;
+        mean[ct * OZ_NT + tid] = (((q[0] + q[OZ_NT]) + (q[2 * OZ_NT] + q[3 * OZ_NT])) +
+                                  ((q[4 * OZ_NT] + q[5 * OZ_NT]) + (q[6 * OZ_NT] + q[7 * OZ_NT]))) + c0;
+    }
 }
 
 // ---- the product kernel ---------------------------------------------------------------------------------------------
