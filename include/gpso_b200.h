@@ -123,6 +123,11 @@ int64_t gpso_debug_trace(gpso_handle* h, double* out, int64_t capacity);
  *   slices: 8-bit digits per operand for mode 2, 5..8, or 0 = chosen per fit from the row scales of L^-1 so that the
  *   estimated error stays below 2% of the parity tolerance 1e-8 * kernel variance. */
 int gpso_set_predict_mode(gpso_handle* h, int mode, int slices);
+/* Engine of K_y^-1 = L^-T L^-1 inside gpso_neg_lml_grad (the gradient's trace terms need K_y^-1 element-wise):
+ *   0 automatic (int8 when the padded N >= 1024), 1 = FP64 DMMA tiles, 2 = exact-integer product of 7-digit (54-bit)
+ *   fixed-point operands on the int8 tensor cores -- operand rounding 2^-54 relative to each row's largest entry, i.e.
+ *   the size of the fp64 rounding of those entries; the integer accumulation itself is exact. */
+int gpso_set_kinv_mode(gpso_handle* h, int mode);
 /* out[0] = engine in force after the last gpso_factorize (1 or 2), out[1] = digits per operand (0 for engine 1),
  * out[2] = estimated error of the variance / parity tolerance for that choice */
 int gpso_predict_info(gpso_handle* h, double* out3);

@@ -56,6 +56,8 @@ constexpr long long WINDOW_BYTES = 2LL << 30;  // rolling cross-covariance windo
 constexpr int OZ_XCOV_SMEM_MAX = 172 * 1024;   // crosscov_slices_kernel dynamic shared memory at d = 64 (320 d + 768 doubles)
 constexpr int OZ_MIN_NP = 512;                 // below this the int8 path is not worth its fixed costs (automatic mode)
 constexpr int OZ_MAX_NP = 16384;               // int32 accumulators stay exact: S * 2^14 * Np < 2^31
+constexpr int OZ_KINV_S = 7;                   // digits per operand of the int8 K_y^-1 = L^-T L^-1 product (54-bit fixed point per row)
+constexpr int OZ_KINV_MIN_NP = 1024;           // automatic mode: below this the DMMA tile kernel is as fast (launch-bound sizes)
 constexpr double OZ_TARGET = 0.02;             // accepted (estimated error) / (parity tolerance 1e-8 * variance)
 
 struct DevBuf {
@@ -115,6 +117,10 @@ struct gpso_handle {
     DevBuf KsT, part, blockbest, running, cand[2], leaves, omean, ovar;
     // int8 tensor-core (tcgen05) variance product: digit tiles of L^-1 and of the cross-covariance window
     DevBuf ozA, ozBb[2], wmeanb[2], rowscale, rowmax;
+    // int8 tensor-core K_y^-1 = L^-T L^-1 (fit path): digit tiles of L^-T, its row scales, the tile -> CTA table
+    DevBuf ozT, colscale, colmax, lauum_items;
+    int lauum_items_nb = 0, lauum_rounds = 0;
+    int kinv_mode = 0;      // 0 = automatic (int8 from OZ_KINV_MIN_NP), 1 = FP64 DMMA tiles, 2 = int8 tcgen05
     cudaStream_t aux_stream = nullptr;
     cudaEvent_t ev_start = nullptr, ev_xcov[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
     int overlap = 1;
@@ -183,10 +189,10 @@ static void launch_crosscov(gpso_handle* h, cudaStream_t st, const double* Xc, l
 
 template <int S>
 static int oz_configure() {
-    CU_TRY(cudaFuncSetAttribute(ozaki_trmm_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, OzCfg<S>::SMEM_BYTES));
+    CU_TRY(cudaFuncSetAttribute(ozaki_kernel<S, OZ_TRMM>, cudaFuncAttributeMaxDynamicSharedMemorySize, OzCfg<S>::SMEM_BYTES));
     // full shared-memory carve-out for both kernels: the persistent product CTA (one per SM) must leave room for a
     // cross-covariance block of the next window on the same SM (they use different pipes and overlap)
-    CU_TRY(cudaFuncSetAttribute(ozaki_trmm_kernel<S>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CU_TRY(cudaFuncSetAttribute(ozaki_kernel<S, OZ_TRMM>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CU_TRY(cudaFuncSetAttribute(crosscov_slices_kernel<KERNEL_MATERN12, S>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CU_TRY(cudaFuncSetAttribute(crosscov_slices_kernel<KERNEL_MATERN32, S>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CU_TRY(cudaFuncSetAttribute(crosscov_slices_kernel<KERNEL_MATERN52, S>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -231,15 +237,19 @@ static void launch_oz_trmm(gpso_handle* h, cudaStream_t st, long long nct, long 
     P.nks = h->Np / 32;
     P.nct = (int)nct;
     P.ldp = ldp;
+    P.items = nullptr;
+    P.rounds = 0;
+    P.out = nullptr;
+    P.Np = h->Np;
     long long units = nct * ((h->nb + 1) / 2);
     int grid = (int)std::min<long long>(h->nsm, units);
-    ozaki_trmm_kernel<S><<<grid, OZ_THREADS, OzCfg<S>::SMEM_BYTES, st>>>(P);
+    ozaki_kernel<S, OZ_TRMM><<<grid, OZ_THREADS, OzCfg<S>::SMEM_BYTES, st>>>(P);
 }
 
 template <int S>
 static void launch_oz_slices(gpso_handle* h, cudaStream_t st) {
     dim3 grid(h->Np / 32, h->nb);
-    linv_slices_kernel<S><<<grid, 256, 0, st>>>(h->Linv.as<double>(), h->rowscale.as<double>(), h->Np, h->Np / 32, h->ozA.as<uint8_t>());
+    linv_slices_kernel<S, false><<<grid, 256, 0, st>>>(h->Linv.as<double>(), h->rowscale.as<double>(), h->Np, h->Np / 32, h->ozA.as<uint8_t>());
 }
 
 #define DISPATCH_S(S_, fn, ...)                \
@@ -284,6 +294,7 @@ static int configure_kernels() {
     CU_TRY(cudaFuncSetAttribute(predict_trmm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     CU_TRY(cudaFuncSetAttribute(diag_factor_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM_BYTES));
     CU_TRY(cudaFuncSetAttribute(factor_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM_BYTES));
+    CU_TRY(cudaFuncSetAttribute(ozaki_kernel<OZ_KINV_S, OZ_LAUUM>, cudaFuncAttributeMaxDynamicSharedMemorySize, OzCfg<OZ_KINV_S>::SMEM_BYTES));
     GP_TRY(oz_configure<5>());
     GP_TRY(oz_configure<6>());
     GP_TRY(oz_configure<7>());
@@ -489,6 +500,67 @@ extern "C" int gpso_debug_factor_tasks(int nb, int nsm, int* out, int64_t capaci
     return 0;
 }
 
+// K_y^-1 = L^-T L^-1 on the int8 tensor cores (kern_ozaki.cuh, OZ_LAUUM).  The tiles (row block I, 64-wide column tile
+// ct <= 2I+1) cost nks - 4I k-steps each (the contraction runs over k >= i only); they are dealt to the nsm persistent CTAs
+// longest-first, each to the CTA with the least work so far, and stored as a [rounds][nsm] table the kernel walks by rounds.
+static int build_lauum_items(gpso_handle* h) {
+    const int nb = h->nb, nks = h->Np / 32, G = h->nsm > 0 ? h->nsm : 148;
+    if (h->lauum_items_nb == nb && h->lauum_items.p) return 0;
+    std::vector<std::vector<int>> per(G);
+    std::vector<long long> load(G, 0);
+    for (int I = 0; I < nb; I++) {  // I ascending = cost descending
+        const long long cost = (nks - 4 * I) + 6;
+        for (int ct = 0; ct <= 2 * I + 1; ct++) {
+            int best = 0;
+            for (int g = 1; g < G; g++)
+                if (load[g] < load[best]) best = g;
+            per[best].push_back((I << 16) | ct);
+            load[best] += cost;
+        }
+    }
+    size_t rounds = 0;
+    for (int g = 0; g < G; g++) rounds = std::max(rounds, per[g].size());
+    std::vector<int> flat(rounds * G, -1);
+    for (int g = 0; g < G; g++)
+        for (size_t r = 0; r < per[g].size(); r++) flat[r * G + g] = per[g][r];
+    GP_TRY(h->lauum_items.ensure(flat.size() * sizeof(int)));
+    CU_TRY(cudaMemcpy(h->lauum_items.p, flat.data(), flat.size() * sizeof(int), cudaMemcpyHostToDevice));
+    h->lauum_items_nb = nb;
+    h->lauum_rounds = (int)rounds;
+    return 0;
+}
+
+static int kinv_int8(gpso_handle* h, cudaStream_t st) {
+    constexpr int S = OZ_KINV_S;
+    const int Np = h->Np, nb = h->nb, nks = Np / 32;
+    GP_TRY(h->colscale.ensure((size_t)Np * sizeof(double)));
+    GP_TRY(h->colmax.ensure((size_t)Np * sizeof(double)));
+    GP_TRY(h->ozT.ensure((size_t)Np * Np * S));
+    GP_TRY(build_lauum_items(h));
+    linv_rowscale_kernel<true><<<(Np + 7) / 8, 256, 0, st>>>(h->LinvT.as<double>(), Np, h->colscale.as<double>(), h->colmax.as<double>());
+    GP_TRY(check_launch(h, "linvT_rowscale"));
+    linv_slices_kernel<S, true><<<dim3(nks, nb), 256, 0, st>>>(h->LinvT.as<double>(), h->colscale.as<double>(), Np, nks, h->ozT.as<uint8_t>());
+    GP_TRY(check_launch(h, "linvT_slices"));
+    OzParams P;
+    P.A = h->ozT.as<uint8_t>();
+    P.B = h->ozT.as<uint8_t>();
+    P.rowscale = h->colscale.as<double>();
+    P.part = nullptr;
+    P.gscale = ldexp(1.0, -2 * (8 * S - 2) + 8 * (S - 1));
+    P.nb = nb;
+    P.nks = nks;
+    P.nct = 2 * nb;
+    P.ldp = 0;
+    P.items = h->lauum_items.as<int>();
+    P.rounds = h->lauum_rounds;
+    P.out = h->Kinv.as<double>();
+    P.Np = Np;
+    const int grid = h->nsm > 0 ? h->nsm : 148;
+    ozaki_kernel<S, OZ_LAUUM><<<grid, OZ_THREADS, OzCfg<S>::SMEM_BYTES, st>>>(P);
+    GP_TRY(check_launch(h, "ozaki_lauum"));
+    return 0;
+}
+
 // Gram -> Cholesky -> inverse factor -> [K_y^-1] -> a, alpha -> scalars.  Uses h->ls_host/variance/noise/c0.
 static int factor_pipeline(gpso_handle* h, cudaStream_t st, bool need_kinv) {
     const int Np = h->Np, nb = h->nb;
@@ -555,8 +627,13 @@ static int factor_pipeline(gpso_handle* h, cudaStream_t st, bool need_kinv) {
     if (need_kinv) {
         GP_TRY(h->Kinv.ensure((size_t)Np * Np * sizeof(double), true));
         P.Kinv = h->Kinv.as<double>();
-        dense_gemm_kernel<MODE_LAUUM><<<nb*(nb + 1) / 2, GTHREADS, GEMM_SMEM_BYTES, st>>>(P);
-        GP_TRY(check_launch(h, "lauum"));
+        const bool int8 = Np <= OZ_MAX_NP && (h->kinv_mode == 2 || (h->kinv_mode == 0 && Np >= OZ_KINV_MIN_NP));
+        if (int8) {
+            GP_TRY(kinv_int8(h, st));
+        } else {
+            dense_gemm_kernel<MODE_LAUUM><<<nb*(nb + 1) / 2, GTHREADS, GEMM_SMEM_BYTES, st>>>(P);
+            GP_TRY(check_launch(h, "lauum"));
+        }
     }
     residual_kernel<<<(Np + 255) / 256, 256, 0, st>>>(h->y.as<double>(), h->c0, h->N, Np, h->resid.as<double>());
     GP_TRY(check_launch(h, "residual"));
@@ -605,7 +682,7 @@ static int prepare_ozaki(gpso_handle* h, cudaStream_t st) {
     const int Np = h->Np;
     GP_TRY(h->rowscale.ensure((size_t)Np * sizeof(double)));
     GP_TRY(h->rowmax.ensure((size_t)Np * sizeof(double)));
-    linv_rowscale_kernel<<<(Np + 7) / 8, 256, 0, st>>>(h->Linv.as<double>(), Np, h->rowscale.as<double>(), h->rowmax.as<double>());
+    linv_rowscale_kernel<false><<<(Np + 7) / 8, 256, 0, st>>>(h->Linv.as<double>(), Np, h->rowscale.as<double>(), h->rowmax.as<double>());
     GP_TRY(check_launch(h, "linv_rowscale"));
     std::vector<double> rs(Np);
     CU_TRY(cudaMemcpyAsync(rs.data(), h->rowscale.p, sizeof(double) * Np, cudaMemcpyDeviceToHost, st));
@@ -1363,6 +1440,12 @@ extern "C" int gpso_set_overlap(gpso_handle* h, int enabled) {
 extern "C" int gpso_set_factor_mode(gpso_handle* h, int mode) {
     if (!h || mode < 0 || mode > 1) return fail(GPSO_E_BADARG, "gpso_set_factor_mode: bad argument");
     h->chol_mode = mode;
+    return 0;
+}
+
+extern "C" int gpso_set_kinv_mode(gpso_handle* h, int mode) {
+    if (!h || mode < 0 || mode > 2) return fail(GPSO_E_BADARG, "gpso_set_kinv_mode: mode must be 0 (auto), 1 (fp64 DMMA) or 2 (int8 tcgen05)");
+    h->kinv_mode = mode;
     return 0;
 }
 

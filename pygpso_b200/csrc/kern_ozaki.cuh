@@ -52,12 +52,65 @@ struct OzCfg {
 
 struct OzParams {
     const uint8_t* A;        // [nb][nks][S][4096]
-    const uint8_t* B;        // [nct][nks][S][2048]
+    const uint8_t* B;        // [nct][nks][S][2048]   (OZ_LAUUM: the A tiles again, read as 64-row halves)
     const double* rowscale;  // [Np] 2^(e_i)
     double* part;            // [nb][ldp]
     double gscale;           // 2^(f - 2(8S-2) + 8(S-1))
     int nb, nks, nct;
     long long ldp;
+    // OZ_LAUUM only
+    const int* items;        // [rounds][gridDim.x]  (row block << 16 | 64-wide column tile), -1 = none
+    int rounds;
+    double* out;             // [Np][Np] row-major: K_y^-1 tiles with column tile <= 2 I + 1
+    int Np;
+};
+
+// What one launch of the product kernel computes
+//   OZ_TRMM   part[I][c] = sum over the 128 rows of block I of (L^-1 k*_c)^2      (posterior variance, predict path)
+//   OZ_LAUUM  K_y^-1[i][j] = sum_{k >= i} L^-T[i][k] L^-T[j][k], j <= i            (fit path: the gradient's trace terms)
+constexpr int OZ_TRMM = 0;
+constexpr int OZ_LAUUM = 1;
+
+// Sequence of work items of one persistent CTA; producer, MMA issuer and epilogue warps each walk their own copy.
+// An item = one 128 x 64 accumulator tile: row block I, column tile ct, k-steps [ks0, ks0 + n).
+template <int MODE>
+struct OzItems {
+    const OzParams& P;
+    long long u;
+    int it, r;
+    __device__ __forceinline__ OzItems(const OzParams& P_) : P(P_), u(blockIdx.x), it(0), r(0) {}
+    __device__ __forceinline__ bool next(int& I, long long& ct, int& ks0, int& n) {
+        if (MODE == OZ_TRMM) {
+            // candidate tile x PAIR of row blocks (nb-1-j, j): every unit costs nb+1 k-blocks, static round-robin is balanced
+            const int npairs = (P.nb + 1) >> 1;
+            if (u >= (long long)P.nct * npairs) return false;
+            ct = u / npairs;
+            const int j = (int)(u - ct * npairs);
+            const int items = (P.nb - 1 - j != j) ? 2 : 1;
+            I = it == 0 ? P.nb - 1 - j : j;
+            ks0 = 0;
+            n = 4 * (I + 1);
+            if (++it == items) {
+                it = 0;
+                u += gridDim.x;
+            }
+            return true;
+        } else {
+            // the host dealt the tiles to the CTAs longest-first (gpso_capi.cu: build_lauum_items)
+            while (r < P.rounds) {
+                const int code = P.items[(size_t)r * gridDim.x + blockIdx.x];
+                r++;
+                if (code >= 0) {
+                    I = code >> 16;
+                    ct = code & 0xffff;
+                    ks0 = 4 * I;
+                    n = P.nks - ks0;
+                    return true;
+                }
+            }
+            return false;
+        }
+    }
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------------------
@@ -154,13 +207,19 @@ __device__ __forceinline__ uint32_t oz_put(uint32_t w, unsigned long long z, int
 
 // ---- A digit tiles from L^-1 ----------------------------------------------------------------------------------------
 // rowscale[i] = 2^(e_i) with max_k |Linv[i,k]| < 2^(e_i - 0) (one warp per row, k <= i only)
+// UPPER: the matrix is L^-T (row i holds column i of L^-1, k >= i)
+template <bool UPPER>
 __global__ void __launch_bounds__(256) linv_rowscale_kernel(const double* __restrict__ Linv, int Np, double* __restrict__ rowscale,
                                                             double* __restrict__ rowmax) {
     int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= Np) return;
     const double* r = Linv + (size_t)row * Np;
     double m = 0.0;
-    for (int k = lane; k <= row; k += 32) m = fmax(m, fabs(r[k]));
+    if (UPPER) {
+        for (int k = row + lane; k < Np; k += 32) m = fmax(m, fabs(r[k]));
+    } else {
+        for (int k = lane; k <= row; k += 32) m = fmax(m, fabs(r[k]));
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
     if (lane == 0) {
@@ -170,11 +229,11 @@ __global__ void __launch_bounds__(256) linv_rowscale_kernel(const double* __rest
     }
 }
 
-template <int S>
+template <int S, bool UPPER>
 __global__ void __launch_bounds__(256) linv_slices_kernel(const double* __restrict__ Linv, const double* __restrict__ rowscale, int Np,
                                                           int nks, uint8_t* __restrict__ A) {
     const int ks = blockIdx.x, I = blockIdx.y;
-    if (ks >= 4 * (I + 1)) return;  // above the block diagonal: never read
+    if (UPPER ? (ks < 4 * I) : (ks >= 4 * (I + 1))) return;  // the other side of the block diagonal: never read
     const int r = threadIdx.x & 127, half = threadIdx.x >> 7;
     const int row = I * 128 + r;
     const double scale = ldexp(1.0, 8 * S - 2) / rowscale[row];
@@ -297,8 +356,8 @@ __global__ void __launch_bounds__(256, 2) crosscov_slices_kernel(const double* _
 }
 
 // ---- the product kernel ---------------------------------------------------------------------------------------------
-template <int S>
-__global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_trmm_kernel(OzParams P) {
+template <int S, int MODE>
+__global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_kernel(OzParams P) {
     using Cfg = OzCfg<S>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ __align__(1024) uint8_t oz_smem_raw[];
@@ -329,10 +388,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_trmm_kernel(OzParams P) {
     __syncthreads();
     oz_fence_after();
     const uint32_t tbase = *tmem_slot;
-
-    const int nb = P.nb, nks = P.nks;
-    const int npairs = (nb + 1) >> 1;
-    const long long units = (long long)P.nct * npairs;
+    const int nks = P.nks;
 
     if (warp == 0) {
         // ================= producer =================
@@ -340,25 +396,30 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_trmm_kernel(OzParams P) {
             int st = 0;
             uint32_t ph = 0;
             const uint64_t keep = oz_policy_evict_last();
-            for (long long u = blockIdx.x; u < units; u += gridDim.x) {
-                const long long ct = u / npairs;
-                const int j = (int)(u - ct * npairs);
-                const int items = (nb - 1 - j != j) ? 2 : 1;
-                for (int it = 0; it < items; it++) {
-                    const int I = it == 0 ? nb - 1 - j : j;
-                    const uint8_t* a = P.A + (size_t)I * nks * S * OZ_A_SLICE;
-                    const uint8_t* b = P.B + (size_t)ct * nks * S * OZ_B_SLICE;
-                    const int n = 4 * (I + 1);
-                    for (int ks = 0; ks < n; ks++) {
-                        oz_mbar_wait(&empty[st], ph ^ 1);
-                        uint8_t* dst = ring + (size_t)st * Cfg::STAGE_BYTES;
-                        oz_mbar_expect_tx(&full[st], Cfg::STAGE_BYTES);
+            OzItems<MODE> items(P);
+            int I, ks0, n;
+            long long ct;
+            while (items.next(I, ct, ks0, n)) {
+                const uint8_t* a = P.A + ((size_t)I * nks + ks0) * S * OZ_A_SLICE;
+                // OZ_TRMM: digit tiles of candidate tile ct; OZ_LAUUM: rows 64 (ct & 1) .. + 63 of row block ct >> 1
+                const uint8_t* b = MODE == OZ_TRMM ? P.B + ((size_t)ct * nks + ks0) * S * OZ_B_SLICE
+                                                   : P.B + ((size_t)(ct >> 1) * nks + ks0) * S * OZ_A_SLICE + (ct & 1) * OZ_B_SLICE;
+                for (int ks = 0; ks < n; ks++) {
+                    oz_mbar_wait(&empty[st], ph ^ 1);
+                    uint8_t* dst = ring + (size_t)st * Cfg::STAGE_BYTES;
+                    oz_mbar_expect_tx(&full[st], Cfg::STAGE_BYTES);
+                    if (MODE == OZ_TRMM) {
                         oz_bulk_g2s_hint(dst, a + (size_t)ks * S * OZ_A_SLICE, S * OZ_A_SLICE, &full[st], keep);
                         oz_bulk_g2s(dst + S * OZ_A_SLICE, b + (size_t)ks * S * OZ_B_SLICE, S * OZ_B_SLICE, &full[st]);
-                        if (++st == STAGES) {
-                            st = 0;
-                            ph ^= 1;
-                        }
+                    } else {
+                        oz_bulk_g2s(dst, a + (size_t)ks * S * OZ_A_SLICE, S * OZ_A_SLICE, &full[st]);
+#pragma unroll
+                        for (int q = 0; q < S; q++)
+                            oz_bulk_g2s(dst + S * OZ_A_SLICE + q * OZ_B_SLICE, b + ((size_t)ks * S + q) * OZ_A_SLICE, OZ_B_SLICE, &full[st]);
+                    }
+                    if (++st == STAGES) {
+                        st = 0;
+                        ph ^= 1;
                     }
                 }
             }
@@ -369,106 +430,113 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_trmm_kernel(OzParams P) {
             int st = 0;
             uint32_t ph = 0, acc_ph = 0;
             const uint32_t ring_addr = oz_smem(ring);
-            for (long long u = blockIdx.x; u < units; u += gridDim.x) {
-                const long long ct = u / npairs;
-                const int j = (int)(u - ct * npairs);
-                const int items = (nb - 1 - j != j) ? 2 : 1;
-                for (int it = 0; it < items; it++) {
-                    const int I = it == 0 ? nb - 1 - j : j;
-                    const int n = 4 * (I + 1);
-                    oz_mbar_wait(tmem_empty, acc_ph ^ 1);  // epilogue has drained the accumulators of the previous item
+            OzItems<MODE> items(P);
+            int I, ks0, n;
+            long long ct;
+            while (items.next(I, ct, ks0, n)) {
+                oz_mbar_wait(tmem_empty, acc_ph ^ 1);  // epilogue has drained the accumulators of the previous item
+                oz_fence_after();
+                for (int ks = 0; ks < n; ks++) {
+                    oz_mbar_wait(&full[st], ph);
                     oz_fence_after();
-                    for (int ks = 0; ks < n; ks++) {
-                        oz_mbar_wait(&full[st], ph);
-                        oz_fence_after();
-                        const uint32_t sa = ring_addr + (uint32_t)st * Cfg::STAGE_BYTES;
-                        const uint32_t sb = sa + S * OZ_A_SLICE;
+                    const uint32_t sa = ring_addr + (uint32_t)st * Cfg::STAGE_BYTES;
+                    const uint32_t sb = sa + S * OZ_A_SLICE;
 #pragma unroll
-                        for (int p = 0; p < S; p++) {
-                            // digit p of A against digits 0..S-1-p of B (stacked along N), level t = p+q -> columns 64 t
-                            const uint64_t ad = oz_desc(sa + p * OZ_A_SLICE);
-                            constexpr int dummy = 0;
-                            (void)dummy;
-                            const int rem = S - p;
-                            const int nch = (rem + 3) / 4;
-                            const int take = (rem + nch - 1) / nch;
+                    for (int p = 0; p < S; p++) {
+                        // digit p of A against digits 0..S-1-p of B (stacked along N), level t = p+q -> columns 64 t
+                        const uint64_t ad = oz_desc(sa + p * OZ_A_SLICE);
+                        const int rem = S - p;
+                        const int nch = (rem + 3) / 4;
+                        const int take = (rem + nch - 1) / nch;
 #pragma unroll
-                            for (int q0 = 0; q0 < rem; q0 += take) {
-                                const int nq = (rem - q0 < take) ? rem - q0 : take;
-                                oz_mma(tbase + (uint32_t)((p + q0) * OZ_NT), ad, oz_desc(sb + q0 * OZ_B_SLICE), oz_idesc(nq * OZ_NT),
-                                       (ks > 0 || p > 0) ? 1u : 0u);
-                            }
-                        }
-                        oz_commit(&empty[st]);  // frees the stage once these MMAs have read it
-                        if (++st == STAGES) {
-                            st = 0;
-                            ph ^= 1;
+                        for (int q0 = 0; q0 < rem; q0 += take) {
+                            const int nq = (rem - q0 < take) ? rem - q0 : take;
+                            oz_mma(tbase + (uint32_t)((p + q0) * OZ_NT), ad, oz_desc(sb + q0 * OZ_B_SLICE), oz_idesc(nq * OZ_NT),
+                                   (ks > 0 || p > 0) ? 1u : 0u);
                         }
                     }
-                    oz_commit(tmem_full);  // accumulators of this item are complete
-                    acc_ph ^= 1;
+                    oz_commit(&empty[st]);  // frees the stage once these MMAs have read it
+                    if (++st == STAGES) {
+                        st = 0;
+                        ph ^= 1;
+                    }
                 }
+                oz_commit(tmem_full);  // accumulators of this item are complete
+                acc_ph ^= 1;
             }
         }
     } else {
-        // ================= epilogue (warps 2..9: TMEM lane group warp & 3, candidate half (warp - 2) >> 2) =================
+        // ================= epilogue (warps 2..9: TMEM lane group warp & 3, column half (warp - 2) >> 2) =================
         const int lg = warp & 3;
         const int hsel = (warp - 2) >> 2;
         const int et = threadIdx.x - 64;  // 0..255
         uint32_t acc_ph = 0;
         constexpr int H = S / 2;  // levels folded into the low word
         const double hi_mul = ldexp(1.0, 8 * H);
-        for (long long u = blockIdx.x; u < units; u += gridDim.x) {
-            const long long ct = u / npairs;
-            const int j = (int)(u - ct * npairs);
-            const int items = (nb - 1 - j != j) ? 2 : 1;
-            for (int it = 0; it < items; it++) {
-                const int I = it == 0 ? nb - 1 - j : j;
-                const double rs = P.rowscale[I * 128 + lg * 32 + lane] * P.gscale;
-                oz_mbar_wait(tmem_full, acc_ph);
-                oz_fence_after();
-                acc_ph ^= 1;
-                double tot[4];  // this lane's share of the column sums: candidate hsel*32 + cc*8 + idx(lane)
+        OzItems<MODE> items(P);
+        int I, ks0, n;
+        long long ct;
+        while (items.next(I, ct, ks0, n)) {
+            const int row = I * 128 + lg * 32 + lane;
+            const double rs = P.rowscale[row] * P.gscale;
+            oz_mbar_wait(tmem_full, acc_ph);
+            oz_fence_after();
+            acc_ph ^= 1;
+            double tot[4];  // OZ_TRMM: this lane's share of the column sums: candidate hsel*32 + cc*8 + idx(lane)
 #pragma unroll
-                for (int cc = 0; cc < 4; cc++) {
-                    uint32_t r[S][8];
+            for (int cc = 0; cc < 4; cc++) {
+                uint32_t r[S][8];
 #pragma unroll
-                    for (int t = 0; t < S; t++)
-                        oz_tmem_ld8(tbase + ((uint32_t)(lg * 32) << 16) + (uint32_t)(t * OZ_NT + hsel * 32 + cc * 8), r[t]);
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    if (cc == 3) {
-                        // all TMEM reads of this item are done: hand the accumulators back to the issuer
-                        oz_fence_before();
-                        __syncwarp();
-                        if (lane == 0) oz_mbar_arrive(tmem_empty);
-                    }
-                    double v[8];
+                for (int t = 0; t < S; t++)
+                    oz_tmem_ld8(tbase + ((uint32_t)(lg * 32) << 16) + (uint32_t)(t * OZ_NT + hsel * 32 + cc * 8), r[t]);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (cc == 3) {
+                    // all TMEM reads of this item are done: hand the accumulators back to the issuer
+                    oz_fence_before();
+                    __syncwarp();
+                    if (lane == 0) oz_mbar_arrive(tmem_empty);
+                }
+                double v[8];
 #pragma unroll
-                    for (int i = 0; i < 8; i++) {
-                        long long whi = 0, wlo = 0;
+                for (int i = 0; i < 8; i++) {
+                    long long whi = 0, wlo = 0;
 #pragma unroll
-                        for (int t = 0; t < S - H; t++) whi += (long long)(int32_t)r[t][i] << (8 * (S - H - 1 - t));
+                    for (int t = 0; t < S - H; t++) whi += (long long)(int32_t)r[t][i] << (8 * (S - H - 1 - t));
 #pragma unroll
-                        for (int t = S - H; t < S; t++) wlo += (long long)(int32_t)r[t][i] << (8 * (S - 1 - t));
-                        double w = fma((double)whi, hi_mul, (double)wlo);
-                        double x = w * rs;
-                        v[i] = x * x;
-                    }
+                    for (int t = S - H; t < S; t++) wlo += (long long)(int32_t)r[t][i] << (8 * (S - 1 - t));
+                    double w = fma((double)whi, hi_mul, (double)wlo);
+                    v[i] = w * rs;
+                }
+                if (MODE == OZ_LAUUM) {
+                    // K_y^-1[row][col0 .. col0 + 7]: the exact integer sum, scaled by the two power-of-two row scales
+                    const int col0 = (int)ct * OZ_NT + hsel * 32 + cc * 8;
+                    const double4 c0 = *reinterpret_cast<const double4*>(P.rowscale + col0);
+                    const double4 c1 = *reinterpret_cast<const double4*>(P.rowscale + col0 + 4);
+                    double2* dst = reinterpret_cast<double2*>(P.out + (size_t)row * P.Np + col0);
+                    dst[0] = make_double2(v[0] * c0.x, v[1] * c0.y);
+                    dst[1] = make_double2(v[2] * c0.z, v[3] * c0.w);
+                    dst[2] = make_double2(v[4] * c1.x, v[5] * c1.y);
+                    dst[3] = make_double2(v[6] * c1.z, v[7] * c1.w);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; i++) v[i] = v[i] * v[i];
                     // transposed butterfly: 8 values x 32 lanes -> four lanes hold each column sum; the same fixed tree
                     // over the 32 rows for every candidate (position-independent rounding)
 #pragma unroll
-                    for (int o = 16, n = 4; o >= 4; o >>= 1, n >>= 1) {
+                    for (int o = 16, nn = 4; o >= 4; o >>= 1, nn >>= 1) {
                         const bool up = (lane & o) != 0;
 #pragma unroll
-                        for (int i = 0; i < n; i++) {
-                            double send = up ? v[i] : v[i + n];
-                            double keep = up ? v[i + n] : v[i];
+                        for (int i = 0; i < nn; i++) {
+                            double send = up ? v[i] : v[i + nn];
+                            double keep = up ? v[i + nn] : v[i];
                             v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
                         }
                     }
                     double t2 = v[0] + __shfl_xor_sync(0xffffffffu, v[0], 2);
                     tot[cc] = t2 + __shfl_xor_sync(0xffffffffu, t2, 1);
                 }
+            }
+            if (MODE == OZ_TRMM) {
                 // candidate index held by this lane within an 8-chunk: bit4 -> 4, bit3 -> 2, bit2 -> 1
                 const int idx = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
                 asm volatile("bar.sync 1, 256;" ::: "memory");  // previous item's cross-warp reduction has been consumed

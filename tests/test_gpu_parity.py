@@ -128,6 +128,38 @@ def test_neg_lml_and_grad_sizes(cuda, N, d):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+# K_y^-1 = L^-T L^-1 of the gradient: FP64 DMMA tiles against the exact-integer int8 tcgen05 product
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("N,d,noise", [(130, 3, 1e-3), (700, 4, 1e-3), (1100, 5, 1e-3), (2100, 6, 2e-5), (4096, 10, 1e-3)])
+def test_kinv_engines_agree(cuda, N, d, noise):
+    """The int8 engine (7 digits: 54-bit fixed point per row of L^-T, integer accumulation exact) must reproduce the FP64
+    DMMA tiles to the fp64 rounding level of K_y^-1, and the LML gradient must not notice the difference."""
+    X, y = synthetic(N, d, seed=5)
+    h = go.Hyper(0.25 * np.sqrt(d), 1.1, noise, 0.05)
+    u = h.pack()
+    out = {}
+    for name, mode in (("dmma", 1), ("int8", 2)):
+        s = open_session(cuda, "Matern52", X, y)
+        s.set_kinv_mode(mode)
+        f, g = s.neg_lml_and_grad(u)
+        f2, g2 = s.neg_lml_and_grad(u)  # same buffers, second call: deterministic
+        assert f2 == f and np.array_equal(g, g2)
+        out[name] = (f, g, s.debug_fetch(4))
+        s.close()
+    (f1, g1, k1), (f2, g2, k2) = out["dmma"], out["int8"]
+    assert f1 == f2  # the LML does not depend on K_y^-1
+    scale = np.abs(k1).max()
+    assert np.abs(k1 - k2).max() <= 2e-12 * scale, np.abs(k1 - k2).max() / scale
+    assert np.all(np.abs(g1 - g2) <= 1e-7 * np.maximum(np.abs(g1), 1.0)), (g1, g2)
+    if N <= 2100:
+        f_ref, g_ref = go.neg_lml_and_grad("Matern52", X, y, u, 1, True)
+        assert np.all(np.abs(g2 - g_ref) <= 1e-6 * np.maximum(np.abs(g_ref), 1.0)), (g2, g_ref)
+        K = go.kern("Matern52", X, None, h) + h.noise_variance * np.eye(N)
+        kinv_ref = np.tril(np.linalg.inv(K))
+        np.testing.assert_allclose(k2, kinv_ref, rtol=0, atol=1e-7 * np.abs(kinv_ref).max())
+
+
+# ---------------------------------------------------------------------------------------------------------------------
 # the two Cholesky schedules: persistent tile scheduler (default) and one launch per step
 # ---------------------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("N,d", [(129, 2), (300, 3), (1100, 5), (2100, 6)])
