@@ -16,6 +16,7 @@ Host-side change: the point list keeps a dense coordinate matrix next to the lis
 ``append`` / ``find_by_coords`` (tolerance 1e-12, :20, :68-101) is one vectorised distance computation instead of a
 Python loop over all points; order, replace-in-place and "evaluated wins" semantics are unchanged.
 """
+import bisect
 import json
 import logging
 import os
@@ -48,7 +49,17 @@ class GPPoint(namedtuple("GPPoint", ["normed_coord", "score_mu", "score_sigma", 
 
 
 class GPListOfPoints(list):
-    """List of :class:`GPPoint` whose ``append`` de-duplicates on coordinates (Euclidean distance < 1e-12)."""
+    """
+    List of :class:`GPPoint` whose ``append`` de-duplicates on coordinates (Euclidean distance < 1e-12, reference
+    ``gp_surrogate.py:68-101``: an evaluated point is never overwritten, a GP-based one is replaced in place).
+
+    The reference scans the whole list per lookup (O(P) per append, O(T P) per tree refresh -- the dominant cost of a
+    long run once the surrogate itself is fast).  Here the coordinates are mirrored in one array and
+    indexed by a scalar projection ``w . x`` kept sorted: two points closer than the tolerance have projections closer than
+    ``tol * |w|``, so a lookup is a bisection plus an exact distance check of the (almost always zero or one) points in
+    that window -- same hits, same order, O(log P).  ``epoch`` changes whenever positions may have moved (generic list
+    mutation); callers may cache indices against it.
+    """
 
     @classmethod
     def from_file(cls, filename):
@@ -67,13 +78,18 @@ class GPListOfPoints(list):
         super().__init__(*args, **kwargs)
         self._coords = None  # [capacity, d] mirror of the coordinates of self[0:len(self)]
         self._count = 0
+        self._weights = None  # projection direction
+        self._keys = []       # sorted projections
+        self._key_idx = []    # list positions, parallel to _keys
+        self.epoch = 0
 
-    # -- coordinate mirror --------------------------------------------------------------------------------------------
+    # -- coordinate mirror + projection index ---------------------------------------------------------------------------
     def _mirror(self):
         n = len(self)
         if self._coords is None or self._count != n:
             if n == 0:
                 self._coords, self._count = None, 0
+                self._keys, self._key_idx = [], []
                 return None
             d = np.size(self[0].normed_coord)
             cap = max(64, 2 * n)
@@ -81,20 +97,64 @@ class GPListOfPoints(list):
             for i, point in enumerate(self):
                 coords[i] = point.normed_coord
             self._coords, self._count = coords, n
+            if self._weights is None or self._weights.size != d:
+                self._weights = np.random.default_rng(12345).uniform(0.5, 1.5, d)
+            proj = coords[:n] @ self._weights
+            order = np.argsort(proj, kind="stable")
+            self._keys = proj[order].tolist()
+            self._key_idx = order.tolist()
         return self._coords[: self._count]
 
     def _invalidate(self):
         self._coords, self._count = None, 0
+        self.epoch += 1
+
+    def _window(self, coords):
+        """(projection, lo, hi): the slice of the sorted projections that can hold points within the tolerance."""
+        w = self._weights
+        key = float(np.dot(coords, w))
+        slack = DUPLICATE_TOLERANCE * float(np.sqrt(np.dot(w, w))) + 1.0e-13 * (1.0 + abs(key))
+        return key, bisect.bisect_left(self._keys, key - slack), bisect.bisect_right(self._keys, key + slack)
 
     def _matches(self, coords):
         """Indices (ascending) of the points closer than the tolerance to ``coords``."""
         mirror = self._mirror()
         if mirror is None:
             return ()
-        diff = mirror - np.asarray(coords, dtype=np.float64)
+        coords = np.asarray(coords, dtype=np.float64).reshape(-1)
+        _, lo, hi = self._window(coords)
+        if lo == hi:
+            return ()
+        cand = np.sort(np.asarray(self._key_idx[lo:hi], dtype=np.intp))
+        diff = mirror[cand] - coords
         dist2 = np.einsum("ij,ij->i", diff, diff)
-        hits = np.flatnonzero(np.sqrt(dist2) < DUPLICATE_TOLERANCE)
-        return hits
+        return cand[np.sqrt(dist2) < DUPLICATE_TOLERANCE]
+
+    def _index_insert(self, coords, position):
+        key = float(np.dot(coords, self._weights))
+        at = bisect.bisect_right(self._keys, key)
+        self._keys.insert(at, key)
+        self._key_idx.insert(at, position)
+
+    def _index_remove(self, coords, position):
+        key = float(np.dot(coords, self._weights))
+        at = bisect.bisect_left(self._keys, key)
+        while at < len(self._keys) and self._keys[at] == key:
+            if self._key_idx[at] == position:
+                del self._keys[at], self._key_idx[at]
+                return
+            at += 1
+        self._invalidate()  # not found where it should be: rebuild on the next lookup
+
+    def _store(self, position, point):
+        """Replace the point at ``position`` in place (coordinates may move within the tolerance)."""
+        list.__setitem__(self, position, point)
+        new = np.asarray(point.normed_coord, dtype=np.float64).reshape(-1)
+        if self._coords is not None and not np.array_equal(self._coords[position], new):
+            self._index_remove(self._coords[position], position)
+            if self._coords is not None:
+                self._coords[position] = new
+                self._index_insert(new, position)
 
     # -- list protocol ------------------------------------------------------------------------------------------------
     def append(self, object):
@@ -106,15 +166,23 @@ class GPListOfPoints(list):
             if self._coords is not None and self._count == n and n < self._coords.shape[0]:
                 self._coords[n] = object.normed_coord
                 self._count = n + 1
+                self._index_insert(self._coords[n], n)
             else:
-                self._invalidate()
+                # first point, or the mirror is full: rebuilt (with twice the capacity) by the next lookup; positions of
+                # the existing points do not move, so cached indices stay valid (no epoch change)
+                self._coords, self._count = None, 0
             return
         for idx in hits:
             # an evaluated point is never overwritten; a GP-based one is replaced in place
             if self[idx].label == PointLabels.evaluated:
                 continue
-            list.__setitem__(self, int(idx), object)
-            self._coords[int(idx)] = object.normed_coord
+            self._store(int(idx), object)
+
+    def replace_at(self, positions, new_points):
+        """Bulk replace-in-place of GP-based points whose positions are known (the re-prediction after a fit)."""
+        for position, point in zip(positions, new_points):
+            assert self[position].label != PointLabels.evaluated
+            self._store(int(position), point)
 
     def find_by_coords(self, coords):
         """First point (list order) within the tolerance of ``coords``, or None."""
@@ -299,10 +367,26 @@ class GPSurrogate:
     def gp_update(self):
         """Re-train on all evaluated points, then refresh every GP-based point with the new posterior."""
         x_train, y_train = self.current_training_data
-        logging.debug(f"Retraining GPR with x data: {x_train}; y data: {y_train}")
+        if logging.getLogger().isEnabledFor(logging.DEBUG):
+            logging.debug(f"Retraining GPR with x data: {x_train}; y data: {y_train}")
         self._gp_train(x=x_train, y=y_train[:, np.newaxis])
-        if self.num_gp_based > 0:
-            self.gp_predict(self.gp_based_coords)
+        # gp_predict(gp_based_coords) of the reference (gp_surrogate.py:341-342) with the positions carried along: one
+        # batched predict_y, then every GP-based point is replaced in place without the per-row duplicate search
+        positions = [i for i, point in enumerate(self.points) if point.label == PointLabels.gp_based]
+        if positions:
+            coords = np.array([self.points[i].normed_coord for i in positions])
+            mean, var = self._require_model().predict_y(coords)
+            mean = np.asarray(mean).reshape(-1)
+            var = np.asarray(var).reshape(-1)
+            ucb = mean + self.gp_varsigma * var
+            self.points.replace_at(
+                positions,
+                (
+                    GPPoint(normed_coord=coords[k], score_mu=float(mean[k]), score_sigma=float(var[k]), score_ucb=float(ucb[k]),
+                            label=PointLabels.gp_based)
+                    for k in range(len(positions))
+                ),
+            )
 
     def fit(self, x=None, y=None):
         """Alias: train on (x, y[:,None]) or, without arguments, on the evaluated points."""

@@ -210,9 +210,17 @@ class GPSOptimiser:
             logging.info("Update step: retraining GP model and updating scores...")
             self.gp_surr.gp_update()
             points = self.gp_surr.points
+            epoch = getattr(points, "epoch", None)
             for leaf in PreOrderIter(self.param_space):
-                leaf_point = points.find_by_coords(leaf.center_array())
-                assert leaf_point is not None
+                # the position of a node's point does not change while points are only appended / replaced in place
+                cached = getattr(leaf, "_point_ref", None)
+                if cached is not None and epoch is not None and cached[0] is points and cached[1] == epoch:
+                    leaf_point = points[cached[2]]
+                else:
+                    position = points.index_by_coords(leaf.center_array())
+                    assert position is not None
+                    leaf._point_ref = (points, epoch, position)
+                    leaf_point = points[position]
                 if leaf_point.label == PointLabels.gp_based:
                     leaf.score = leaf_point.score_ucb
             self._run_callbacks(callback_type=CallbackTypes.post_update)

@@ -81,3 +81,37 @@ def test_gppoint_equality():
     assert a == point([0.1, 0.2], 1.0)
     assert a != point([0.1, 0.2], 1.5)
     assert a != point([0.1, 0.25], 1.0)
+
+
+def test_projection_index_matches_literal_semantics_large():
+    """10-D, a few thousand operations: capacity growth of the mirror, replacements whose coordinates move inside the
+    tolerance (the index entry must follow), lookups against the brute-force scan."""
+    rng = np.random.default_rng(7)
+    base = rng.random((600, 10))
+    fast, slow = GPListOfPoints(), []
+    for step in range(3000):
+        coord = base[rng.integers(600)] + (rng.random(10) < 0.2) * rng.normal(0, 2.5e-13, 10)
+        label = PointLabels.evaluated if rng.random() < 0.3 else PointLabels.gp_based
+        obj = point(coord, mu=float(step), label=label)
+        fast.append(obj)
+        literal_append(slow, obj)
+    assert len(fast) == len(slow)
+    for a, b in zip(fast, slow):
+        assert a == b and a.label == b.label
+    for probe in base[:200]:
+        want = next((i for i, p in enumerate(slow) if np.linalg.norm(p.normed_coord - probe) < DUPLICATE_TOLERANCE), None)
+        assert fast.index_by_coords(probe) == want
+
+
+def test_epoch_and_replace_at():
+    pts = GPListOfPoints([point([0.1 * i, 0.2, 0.3]) for i in range(5)])
+    epoch = pts.epoch
+    pts.append(point([0.9, 0.9, 0.9]))            # appending keeps positions
+    pts.append(point([0.1, 0.2, 0.3], mu=4.0))    # so does replacing in place
+    assert pts.epoch == epoch and pts[1].score_mu == 4.0
+    pts.replace_at([0, 5], [point([0.0, 0.2, 0.3], mu=7.0), point([0.9, 0.9, 0.9 + 4e-13], mu=8.0)])
+    assert pts.epoch == epoch and pts[0].score_mu == 7.0 and pts[5].score_mu == 8.0
+    assert pts.index_by_coords(np.array([0.9, 0.9, 0.9 + 4e-13])) == 5
+    assert pts.index_by_coords(np.array([0.9, 0.9, 0.9 - 4e-13])) == 5   # still within the tolerance of the moved point
+    pts.insert(0, point([0.55, 0.55, 0.55]))       # positions move: cached indices are invalid from here on
+    assert pts.epoch != epoch and pts.index_by_coords(np.array([0.9, 0.9, 0.9 + 4e-13])) == 6
