@@ -135,10 +135,21 @@ def bench_lml_grad(cuda, go, cpu=True, shapes=((4096, 10), (8192, 20)), evals=5)
             sess.neg_lml_and_grad(u + 1e-3 * (i + 1))
             step_ms += sess.last_timing_ms()[0]
         sess.set_factor_mode(True)
+        # ... and with K_y^-1 = L^-T L^-1 on the FP64 DMMA tiles instead of the int8 tensor-core product (automatic from N=1024)
+        sess.set_kinv_mode(1)
+        sess.neg_lml_and_grad(u)
+        kinv_dmma_ms = 0.0
+        for i in range(evals):
+            sess.neg_lml_and_grad(u + 1e-3 * (i + 1))
+            kinv_dmma_ms += sess.last_timing_ms()[0]
+        sess.set_kinv_mode(0)
         rec = {"N": N, "d": d, "evals_per_s": evals / wall, "device_ms_per_eval": dev_ms / evals,
                "device_ms_per_eval_stepwise_launches": step_ms / evals,
-               "schedule": "persistent tile scheduler: blocked Cholesky as DIAG/PANEL/UPDATE tasks, one CTA per SM, "
-                           "two-level blocking + look-ahead; then L^-1 by recursive doubling and K^-1 = L^-T L^-1 (DMMA tiles)",
+               "device_ms_per_eval_kinv_on_fp64_dmma": kinv_dmma_ms / evals,
+               "schedule": "one persistent kernel (one CTA per SM, host-built task list with per-tile dependency counters): "
+                           "blocked Cholesky as DIAG/PANEL/UPDATE tile tasks on FP64 DMMA, two-level blocking + look-ahead, and "
+                           "L^-1 by recursive doubling as tasks of the same launch; then K_y^-1 = L^-T L^-1 as an exact-integer "
+                           "product of 7-digit (54-bit) fixed-point operands on the int8 tensor cores (tcgen05.mma kind::i8)",
                "library_bar_ms": {4096: {"cusolver_dpotrf": 1.675, "cusolver_dpotri": 14.005},
                                   8192: {"cusolver_dpotrf": 7.753, "cusolver_dpotri": 61.528}}.get(N),
                "fp64_tflops": (float(N) ** 3 / (dev_ms / evals * 1e-3)) / 1e12, "fp64_peak_tflops": FP64_PEAK_TFLOPS,
@@ -351,8 +362,10 @@ def main():
                 "op_kind": "int8 tensor op (2 per multiply-add); algorithmic = digit_pairs * N^2 per candidate",
                 "traffic": None,
                 "peak_source": "measured tcgen05 kind::i8 issue peak on this pool's B200 at 1965 MHz (profiles/"
-                               "r01_i8_tcgen05_probe.txt, nominal 4500); under the 1 kW cap the SM clock settles near "
-                               "1.6 GHz in this kernel (see clocks); MEASURED_PEAKS.json has no int8 entry",
+                               "r01_i8_tcgen05_probe.txt, nominal 4500); in this kernel the SM clock settles near 1.6-1.7 GHz "
+                               "(see clocks); MEASURED_PEAKS.json has no int8 entry.  The FP64 cross-covariance kernel cannot "
+                               "hide behind it: DFMA shares the tensor-core datapath on B200 (x7.9 slower beside int8 MMAs, "
+                               "profiles/r01s4_corun_probe.txt), so a step is product + cross-covariance in sequence",
                 "fp64_equivalent": {"achieved_tflops": flops64 / (product_ms * 1e-3) / 1e12, "fp64_pipe_peak_tflops": FP64_PEAK_TFLOPS,
                                     "ratio_to_fp64_peak": flops64 / (product_ms * 1e-3) / 1e12 / FP64_PEAK_TFLOPS},
                 "digits": S, "error_estimate_over_tolerance": engine["error_estimate_over_tol"],

@@ -128,6 +128,10 @@ int gpso_set_predict_mode(gpso_handle* h, int mode, int slices);
  *   fixed-point operands on the int8 tensor cores -- operand rounding 2^-54 relative to each row's largest entry, i.e.
  *   the size of the fp64 rounding of those entries; the integer accumulation itself is exact. */
 int gpso_set_kinv_mode(gpso_handle* h, int mode);
+/* Engine of the recursive-doubling inverse factor L^-1 (both gpso_factorize and gpso_neg_lml_grad):
+ *   0 automatic (int8 when the padded N >= 2048), 1 = FP64 DMMA tile tasks inside the persistent factorisation kernel,
+ *   2 = exact-integer products of 8-digit (62-bit) fixed-point operands on the int8 tensor cores, two per level. */
+int gpso_set_inverse_mode(gpso_handle* h, int mode);
 /* out[0] = engine in force after the last gpso_factorize (1 or 2), out[1] = digits per operand (0 for engine 1),
  * out[2] = estimated error of the variance / parity tolerance for that choice */
 int gpso_predict_info(gpso_handle* h, double* out3);

@@ -12,6 +12,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <array>
 #include <string>
 #include <vector>
 
@@ -58,6 +59,8 @@ constexpr int OZ_MIN_NP = 512;                 // below this the int8 path is no
 constexpr int OZ_MAX_NP = 16384;               // int32 accumulators stay exact: S * 2^14 * Np < 2^31
 constexpr int OZ_KINV_S = 7;                   // digits per operand of the int8 K_y^-1 = L^-T L^-1 product (54-bit fixed point per row)
 constexpr int OZ_KINV_MIN_NP = 1024;           // automatic mode: below this the DMMA tile kernel is as fast (launch-bound sizes)
+constexpr int OZ_INV_S = 8;                    // digits per operand of the int8 inverse-factor products (62-bit fixed point per row)
+constexpr int OZ_INV_MIN_NP = 2048;            // automatic mode: below this the DMMA tasks inside the persistent kernel win
 constexpr double OZ_TARGET = 0.02;             // accepted (estimated error) / (parity tolerance 1e-8 * variance)
 
 struct DevBuf {
@@ -121,6 +124,14 @@ struct gpso_handle {
     DevBuf ozT, colscale, colmax, lauum_items;
     int lauum_items_nb = 0, lauum_rounds = 0;
     int kinv_mode = 0;      // 0 = automatic (int8 from OZ_KINV_MIN_NP), 1 = FP64 DMMA tiles, 2 = int8 tcgen05
+    // int8 tensor-core inverse factor (recursive doubling, two products per level): digit tiles and row scales of the four
+    // operands (L, L^-T block diagonal, L^-1 block diagonal, X^T) and the per-level tile -> CTA tables
+    DevBuf ozL, ozLT, ozLI, ozXT, rsL, rsLT, rsLI, rsXT, inv_items;
+    struct InvLevel { int s; size_t xt_off; int xt_rounds; size_t y_off; int y_rounds; };
+    std::vector<InvLevel> inv_levels;
+    int inv_items_nb = 0;
+    int inverse_mode = 0;   // 0 = automatic (int8 from OZ_INV_MIN_NP), 1 = FP64 DMMA tile tasks, 2 = int8 tcgen05
+    bool chol_tasks_inv = true;  // whether the cached task list contains the inverse-factor tasks
     cudaStream_t aux_stream = nullptr;
     cudaEvent_t ev_start = nullptr, ev_xcov[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
     int overlap = 1;
@@ -295,6 +306,7 @@ static int configure_kernels() {
     CU_TRY(cudaFuncSetAttribute(diag_factor_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM_BYTES));
     CU_TRY(cudaFuncSetAttribute(factor_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM_BYTES));
     CU_TRY(cudaFuncSetAttribute(ozaki_kernel<OZ_KINV_S, OZ_LAUUM>, cudaFuncAttributeMaxDynamicSharedMemorySize, OzCfg<OZ_KINV_S>::SMEM_BYTES));
+    CU_TRY(cudaFuncSetAttribute(ozaki_kernel<OZ_INV_S, OZ_GEMM>, cudaFuncAttributeMaxDynamicSharedMemorySize, OzCfg<OZ_INV_S>::SMEM_BYTES));
     GP_TRY(oz_configure<5>());
     GP_TRY(oz_configure<6>());
     GP_TRY(oz_configure<7>());
@@ -366,7 +378,7 @@ struct FactorTask {
 };
 }  // namespace
 
-static int make_factor_tasks(int nb, int nsm, std::vector<int>& flat, int& ntasks, int& ncounters_out) {
+static int make_factor_tasks(int nb, int nsm, std::vector<int>& flat, int& ntasks, int& ncounters_out, bool with_inverse = true) {
     const int W = nb >= 48 ? 4 : 2;
     if (nb < 1 || nb > 255) return fail(GPSO_E_BADARG, "matrix too large for the tile scheduler (more than 255 panels)");
     const int LV = 8;  // levels of the inverse recursion: s = 1 .. 128
@@ -427,7 +439,7 @@ static int make_factor_tasks(int nb, int nsm, std::vector<int>& flat, int& ntask
             for (int i = j; i < nb; i++) wide.push_back(wide_task(b, i, j));
     }
     // ---- inverse factor: level s merges [a, a+s) and [a+s, a+s+nv), a = 2 q s
-    for (int s = 1, l = 0; s < nb; s *= 2, l++) {
+    for (int s = 1, l = 0; with_inverse && s < nb; s *= 2, l++) {
         if (l >= LV) return fail(GPSO_E_BADARG, "matrix too large for the inverse recursion of the tile scheduler");
         std::vector<int> off;  // first tile index of pair q in the kernel's enumeration
         int total = 0;
@@ -473,11 +485,12 @@ static int make_factor_tasks(int nb, int nsm, std::vector<int>& flat, int& ntask
     return 0;
 }
 
-static int build_factor_tasks(gpso_handle* h) {
-    if (h->chol_tasks_nb == h->nb) return 0;
+static int build_factor_tasks(gpso_handle* h, bool with_inverse) {
+    if (h->chol_tasks_nb == h->nb && h->chol_tasks_inv == with_inverse) return 0;
     std::vector<int> flat;
     int ntasks = 0, ncounters = 0;
-    GP_TRY(make_factor_tasks(h->nb, h->nsm > 0 ? h->nsm : 148, flat, ntasks, ncounters));
+    GP_TRY(make_factor_tasks(h->nb, h->nsm > 0 ? h->nsm : 148, flat, ntasks, ncounters, with_inverse));
+    h->chol_tasks_inv = with_inverse;
     GP_TRY(h->chol_tasks.ensure(flat.size() * sizeof(int)));
     GP_TRY(h->chol_state.ensure((size_t)(2 + ncounters) * sizeof(int)));
     CU_TRY(cudaMemcpy(h->chol_tasks.p, flat.data(), flat.size() * sizeof(int), cudaMemcpyHostToDevice));
@@ -561,6 +574,118 @@ static int kinv_int8(gpso_handle* h, cudaStream_t st) {
     return 0;
 }
 
+// L^-1 by recursive doubling on the int8 tensor cores (kern_ozaki.cuh, OZ_GEMM).  Level s merges the finished inverses of
+// the tile ranges [a, a+s) and [a+s, a+s+nv), a = 2 q s:   X^T = L11^-T L21^T,   L21^-1 = -(L22^-1 X)   (and its transpose into
+// L^-T).  Every operand row is cut into 8 balanced 8-bit digits of a 62-bit fixed-point number relative to the row's
+// largest entry in the range the level reads, so the operand rounding (2^-62 of the row scale) is below the fp64 rounding of
+// those entries and the integer accumulation is exact.  Tiles (128 x 64) are dealt to the persistent CTAs longest-first.
+static int build_inverse_items(gpso_handle* h) {
+    const int nb = h->nb, G = h->nsm > 0 ? h->nsm : 148;
+    if (h->inv_items_nb == nb && h->inv_items.p) return 0;
+    std::vector<int> all;
+    h->inv_levels.clear();
+    auto deal = [&](std::vector<std::array<int, 4>>& items, size_t& off, int& rounds) {
+        std::stable_sort(items.begin(), items.end(), [](const std::array<int, 4>& a, const std::array<int, 4>& b) { return a[3] > b[3]; });
+        std::vector<std::vector<int>> per(G);
+        std::vector<long long> load(G, 0);
+        for (size_t i = 0; i < items.size(); i++) {
+            int best = 0;
+            for (int g = 1; g < G; g++)
+                if (load[g] < load[best]) best = g;
+            per[best].push_back((int)i);
+            load[best] += items[i][3] + 6;
+        }
+        size_t r = 0;
+        for (int g = 0; g < G; g++) r = std::max(r, per[g].size());
+        off = all.size();
+        rounds = (int)r;
+        all.resize(off + r * G * 4, -1);
+        for (int g = 0; g < G; g++)
+            for (size_t k = 0; k < per[g].size(); k++)
+                for (int c = 0; c < 4; c++) all[off + (k * G + g) * 4 + c] = items[per[g][k]][c];
+    };
+    for (int s = 1; s < nb; s *= 2) {
+        std::vector<std::array<int, 4>> xt, y;
+        for (int q = 0; 2 * q * s < nb; q++) {
+            const int nv = trtri_pair_vtiles(nb, s, q), a = 2 * q * s;
+            for (int u = 0; u < s; u++)
+                for (int v = 0; v < nv; v++)
+                    for (int hh = 0; hh < 2; hh++) {
+                        xt.push_back({a + u, 2 * (a + s + v) + hh, 4 * (a + u), 4 * (s - u)});
+                        y.push_back({a + s + v, 2 * (a + u) + hh, 4 * (a + s), 4 * (v + 1)});
+                    }
+        }
+        gpso_handle::InvLevel lv;
+        lv.s = s;
+        deal(xt, lv.xt_off, lv.xt_rounds);
+        deal(y, lv.y_off, lv.y_rounds);
+        h->inv_levels.push_back(lv);
+    }
+    if (all.empty()) all.resize(4, -1);
+    GP_TRY(h->inv_items.ensure(all.size() * sizeof(int)));
+    CU_TRY(cudaMemcpy(h->inv_items.p, all.data(), all.size() * sizeof(int), cudaMemcpyHostToDevice));
+    h->inv_items_nb = nb;
+    return 0;
+}
+
+static int inverse_int8(gpso_handle* h, cudaStream_t st) {
+    constexpr int S = OZ_INV_S;
+    const int Np = h->Np, nb = h->nb, nks = Np / 32;
+    const size_t dig = (size_t)Np * Np * S;
+    GP_TRY(h->ozL.ensure(dig));
+    GP_TRY(h->ozLT.ensure(dig));
+    GP_TRY(h->ozLI.ensure(dig));
+    GP_TRY(h->ozXT.ensure(dig));
+    GP_TRY(h->rsL.ensure((size_t)Np * sizeof(double)));
+    GP_TRY(h->rsLT.ensure((size_t)Np * sizeof(double)));
+    GP_TRY(h->rsLI.ensure((size_t)Np * sizeof(double)));
+    GP_TRY(h->rsXT.ensure((size_t)Np * sizeof(double)));
+    GP_TRY(h->T.ensure((size_t)Np * Np * sizeof(double), true));
+    GP_TRY(build_inverse_items(h));
+    const int grid = h->nsm > 0 ? h->nsm : 148;
+    const dim3 sgrid(nks, nb);
+    auto digits = [&](const DevBuf& M, int kind, int s, DevBuf& scales, DevBuf& out, const char* what) -> int {
+        range_rowscale_kernel<<<(Np + 7) / 8, 256, 0, st>>>(M.as<double>(), Np, kind, s, nb, scales.as<double>());
+        GP_TRY(check_launch(h, what));
+        range_slices_kernel<S><<<sgrid, 256, 0, st>>>(M.as<double>(), scales.as<double>(), Np, nks, kind, s, nb, out.as<uint8_t>());
+        GP_TRY(check_launch(h, what));
+        return 0;
+    };
+    auto product = [&](const DevBuf& A, const DevBuf& rsA, const DevBuf& B, const DevBuf& rsB, size_t off, int rounds, double* out,
+                       double* out_t, double sign, const char* what) -> int {
+        OzParams P;
+        P.A = A.as<uint8_t>();
+        P.B = B.as<uint8_t>();
+        P.rowscale = rsA.as<double>();
+        P.colscale = rsB.as<double>();
+        P.part = nullptr;
+        P.gscale = ldexp(1.0, -2 * (8 * S - 2) + 8 * (S - 1));
+        P.nb = nb;
+        P.nks = nks;
+        P.nct = 2 * nb;
+        P.ldp = 0;
+        P.items = h->inv_items.as<int>() + off;
+        P.rounds = rounds;
+        P.out = out;
+        P.out_t = out_t;
+        P.sign = sign;
+        P.Np = Np;
+        ozaki_kernel<S, OZ_GEMM><<<grid, OZ_THREADS, OzCfg<S>::SMEM_BYTES, st>>>(P);
+        return check_launch(h, what);
+    };
+    GP_TRY(digits(h->K, OZR_L, 1, h->rsL, h->ozL, "digits_L"));
+    for (const gpso_handle::InvLevel& lv : h->inv_levels) {
+        if (lv.xt_rounds == 0) continue;
+        GP_TRY(digits(h->LinvT, OZR_LINVT, lv.s, h->rsLT, h->ozLT, "digits_LinvT"));
+        GP_TRY(product(h->ozLT, h->rsLT, h->ozL, h->rsL, lv.xt_off, lv.xt_rounds, h->T.as<double>(), nullptr, 1.0, "inverse_xt"));
+        GP_TRY(digits(h->T, OZR_XT, lv.s, h->rsXT, h->ozXT, "digits_XT"));
+        GP_TRY(digits(h->Linv, OZR_LINV, lv.s, h->rsLI, h->ozLI, "digits_Linv"));
+        GP_TRY(product(h->ozLI, h->rsLI, h->ozXT, h->rsXT, lv.y_off, lv.y_rounds, h->Linv.as<double>(), h->LinvT.as<double>(), -1.0,
+                       "inverse_y"));
+    }
+    return 0;
+}
+
 // Gram -> Cholesky -> inverse factor -> [K_y^-1] -> a, alpha -> scalars.  Uses h->ls_host/variance/noise/c0.
 static int factor_pipeline(gpso_handle* h, cudaStream_t st, bool need_kinv) {
     const int Np = h->Np, nb = h->nb;
@@ -582,9 +707,11 @@ static int factor_pipeline(gpso_handle* h, cudaStream_t st, bool need_kinv) {
     P.nb = nb;
     P.p = 0;
     P.s = 0;
+    const bool inv8 = nb > 1 && Np <= OZ_MAX_NP && (h->inverse_mode == 2 || (h->inverse_mode == 0 && Np >= OZ_INV_MIN_NP));
     if (h->chol_mode == 1 && nb > 1) {
-        // one persistent launch: blocked Cholesky + L^-1 (diagonal blocks, their transposes, recursive doubling)
-        GP_TRY(build_factor_tasks(h));
+        // one persistent launch: blocked Cholesky + L^-1 (diagonal blocks, their transposes and -- unless the int8 engine
+        // takes it over below -- the recursive doubling)
+        GP_TRY(build_factor_tasks(h, !inv8));
         GP_TRY(h->T.ensure((size_t)Np * Np * sizeof(double), true));
         P.T = h->T.as<double>();
         int* state = h->chol_state.as<int>();
@@ -593,6 +720,7 @@ static int factor_pipeline(gpso_handle* h, cudaStream_t st, bool need_kinv) {
         factor_persistent_kernel<<<grid, GTHREADS, DIAG_SMEM_BYTES, st>>>(P, h->N, h->chol_tasks.as<int>(), h->chol_ntasks, state,
                                                                            h->logdet.as<double>(), h->info.as<int>());
         GP_TRY(check_launch(h, "factor_persistent"));
+        if (inv8) GP_TRY(inverse_int8(h, st));
     } else {
         for (int p = 0; p < nb; p++) {
             diag_factor_inverse_kernel<<<1, DIAG_THREADS, DIAG_SMEM_BYTES, st>>>(P.K, P.Linv, Np, p, h->N, h->logdet.as<double>(),
@@ -609,7 +737,9 @@ static int factor_pipeline(gpso_handle* h, cudaStream_t st, bool need_kinv) {
         }
         diag_transpose_kernel<<<nb, 256, 0, st>>>(P.Linv, P.LinvT, Np);
         GP_TRY(check_launch(h, "diag_transpose"));
-        if (nb > 1) {
+        if (inv8) {
+            GP_TRY(inverse_int8(h, st));
+        } else if (nb > 1) {
             GP_TRY(h->T.ensure((size_t)Np * Np * sizeof(double), true));
             P.T = h->T.as<double>();
             for (int s = 1; s < nb; s *= 2) {
@@ -1446,6 +1576,13 @@ extern "C" int gpso_set_factor_mode(gpso_handle* h, int mode) {
 extern "C" int gpso_set_kinv_mode(gpso_handle* h, int mode) {
     if (!h || mode < 0 || mode > 2) return fail(GPSO_E_BADARG, "gpso_set_kinv_mode: mode must be 0 (auto), 1 (fp64 DMMA) or 2 (int8 tcgen05)");
     h->kinv_mode = mode;
+    return 0;
+}
+
+extern "C" int gpso_set_inverse_mode(gpso_handle* h, int mode) {
+    if (!h || mode < 0 || mode > 2) return fail(GPSO_E_BADARG, "gpso_set_inverse_mode: mode must be 0 (auto), 1 (fp64 DMMA) or 2 (int8 tcgen05)");
+    h->inverse_mode = mode;
+    h->factorized = false;
     return 0;
 }
 

@@ -58,18 +58,25 @@ struct OzParams {
     double gscale;           // 2^(f - 2(8S-2) + 8(S-1))
     int nb, nks, nct;
     long long ldp;
-    // OZ_LAUUM only
-    const int* items;        // [rounds][gridDim.x]  (row block << 16 | 64-wide column tile), -1 = none
+    // OZ_LAUUM / OZ_GEMM only
+    const int* items;        // OZ_LAUUM: [rounds][gridDim.x]  (row block << 16 | 64-wide column tile), -1 = none
+                             // OZ_GEMM:  [rounds][gridDim.x][4]  (row block, 64-row tile of B, first k-step, k-steps), I < 0 = none
     int rounds;
-    double* out;             // [Np][Np] row-major: K_y^-1 tiles with column tile <= 2 I + 1
+    double* out;             // [Np][Np] row-major output
     int Np;
+    const double* colscale;  // OZ_GEMM: row scales of the B operand (its rows are the output columns)
+    double* out_t;           // OZ_GEMM: optional second, transposed copy of the output (out_t[col][row])
+    double sign;             // OZ_GEMM: +1 / -1
 };
 
 // What one launch of the product kernel computes
 //   OZ_TRMM   part[I][c] = sum over the 128 rows of block I of (L^-1 k*_c)^2      (posterior variance, predict path)
 //   OZ_LAUUM  K_y^-1[i][j] = sum_{k >= i} L^-T[i][k] L^-T[j][k], j <= i            (fit path: the gradient's trace terms)
+//   OZ_GEMM   out[i][j] = sign * sum_{k in item range} A[i][k] B[j][k]                 (fit path: the two products per level of
+//             the recursive-doubling inverse factor; tiles, k-ranges and the tile -> CTA deal come from a host table)
 constexpr int OZ_TRMM = 0;
 constexpr int OZ_LAUUM = 1;
+constexpr int OZ_GEMM = 2;
 
 // Sequence of work items of one persistent CTA; producer, MMA issuer and epilogue warps each walk their own copy.
 // An item = one 128 x 64 accumulator tile: row block I, column tile ct, k-steps [ks0, ks0 + n).
@@ -95,6 +102,19 @@ struct OzItems {
                 u += gridDim.x;
             }
             return true;
+        } else if (MODE == OZ_GEMM) {
+            while (r < P.rounds) {
+                const int4 it4 = reinterpret_cast<const int4*>(P.items)[(size_t)r * gridDim.x + blockIdx.x];
+                r++;
+                if (it4.x >= 0) {
+                    I = it4.x;
+                    ct = it4.y;
+                    ks0 = it4.z;
+                    n = it4.w;
+                    return true;
+                }
+            }
+            return false;
         } else {
             // the host dealt the tiles to the CTAs longest-first (gpso_capi.cu: build_lauum_items)
             while (r < P.rounds) {
@@ -252,6 +272,68 @@ __global__ void __launch_bounds__(256) linv_slices_kernel(const double* __restri
     for (int p = 0; p < S; p++) *reinterpret_cast<uint4*>(dst + (size_t)p * OZ_A_SLICE) = make_uint4(out[p][0], out[p][1], out[p][2], out[p][3]);
 }
 
+// ---- operands of the recursive-doubling inverse (fit path, OZ_GEMM) -----------------------------------------------------
+// At level s the diagonal blocks of s tiles of L^-1 are complete.  The products of the level read, per 128-row tile I with
+// block [b0, b1) = [floor(I/s) s, min(b0+s, nb)) and pair start a = floor(I/2s) 2s:
+//   OZR_LINVT  L^-T rows, k in tiles [I, b1)          (upper part of the block: operand of X^T = L11^-T L21^T)
+//   OZR_LINV   L^-1 rows, k in tiles [b0, I]          (lower part of the block: operand of Y = L22^-1 X)
+//   OZR_XT     X^T rows of the first half of a pair,  k in tiles [a+s, min(a+2s, nb))
+//   OZR_L      rows of the Cholesky factor, k in tiles [0, I)   (strictly below the diagonal tile: the L21 blocks)
+// Each row is scaled by a power of two above its largest entry IN THAT RANGE, then cut into S balanced 8-bit digits.
+constexpr int OZR_LINVT = 0, OZR_LINV = 1, OZR_XT = 2, OZR_L = 3;
+
+__device__ __forceinline__ void ozr_tile_range(int kind, int I, int s, int nb, int& t0, int& t1) {
+    const int b0 = (I / s) * s, b1 = min(b0 + s, nb), a = (I / (2 * s)) * (2 * s);
+    if (kind == OZR_LINVT) {
+        t0 = I, t1 = b1;
+    } else if (kind == OZR_LINV) {
+        t0 = b0, t1 = I + 1;
+    } else if (kind == OZR_XT) {
+        t0 = a + s, t1 = (I < a + s) ? min(a + 2 * s, nb) : a + s;  // second-half rows: empty
+    } else {
+        t0 = 0, t1 = I;
+    }
+}
+
+__global__ void __launch_bounds__(256) range_rowscale_kernel(const double* __restrict__ M, int Np, int kind, int s, int nb,
+                                                             double* __restrict__ rowscale) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= Np) return;
+    int t0, t1;
+    ozr_tile_range(kind, row >> 7, s, nb, t0, t1);
+    const double* r = M + (size_t)row * Np;
+    double m = 0.0;
+    for (int k = t0 * 128 + lane; k < t1 * 128; k += 32) m = fmax(m, fabs(r[k]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) rowscale[row] = ldexp(1.0, (m > 0.0 && isfinite(m)) ? ilogb(m) + 1 : 0);
+}
+
+template <int S>
+__global__ void __launch_bounds__(256) range_slices_kernel(const double* __restrict__ M, const double* __restrict__ rowscale, int Np,
+                                                           int nks, int kind, int s, int nb, uint8_t* __restrict__ A) {
+    const int ks = blockIdx.x, I = blockIdx.y;
+    int t0, t1;
+    ozr_tile_range(kind, I, s, nb, t0, t1);
+    if (ks < 4 * t0 || ks >= 4 * t1) return;
+    const int r = threadIdx.x & 127, half = threadIdx.x >> 7;
+    const int row = I * 128 + r;
+    const double scale = ldexp(1.0, 8 * S - 2) / rowscale[row];
+    const double* src = M + (size_t)row * Np + ks * 32 + half * 16;
+    uint32_t out[S][4];
+#pragma unroll
+    for (int p = 0; p < S; p++) out[p][0] = out[p][1] = out[p][2] = out[p][3] = 0u;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        unsigned long long z = oz_digits<S>(src[i], scale);
+#pragma unroll
+        for (int p = 0; p < S; p++) out[p][i >> 2] = oz_put(out[p][i >> 2], z, S - 1 - p, i & 3);
+    }
+    uint8_t* dst = A + ((size_t)I * nks + ks) * S * OZ_A_SLICE + (r >> 3) * 256 + half * 128 + (r & 7) * 16;
+#pragma unroll
+    for (int p = 0; p < S; p++) *reinterpret_cast<uint4*>(dst + (size_t)p * OZ_A_SLICE) = make_uint4(out[p][0], out[p][1], out[p][2], out[p][3]);
+}
+
 // ---- B digit tiles + posterior mean from the candidates -------------------------------------------------------------
 // One block = one candidate tile (64 candidates) x all training points, in super-steps of OZ_XK = 128 training points.
 // Register tile per thread: 2 candidates (cl and cl + 32, cl = lane) x 16 consecutive training points (warp w owns points
@@ -402,6 +484,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_kernel(OzParams P) {
             while (items.next(I, ct, ks0, n)) {
                 const uint8_t* a = P.A + ((size_t)I * nks + ks0) * S * OZ_A_SLICE;
                 // OZ_TRMM: digit tiles of candidate tile ct; OZ_LAUUM: rows 64 (ct & 1) .. + 63 of row block ct >> 1
+                // (OZ_GEMM: the same with another digit buffer)
                 const uint8_t* b = MODE == OZ_TRMM ? P.B + ((size_t)ct * nks + ks0) * S * OZ_B_SLICE
                                                    : P.B + ((size_t)(ct >> 1) * nks + ks0) * S * OZ_A_SLICE + (ct & 1) * OZ_B_SLICE;
                 for (int ks = 0; ks < n; ks++) {
@@ -478,7 +561,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_kernel(OzParams P) {
         long long ct;
         while (items.next(I, ct, ks0, n)) {
             const int row = I * 128 + lg * 32 + lane;
-            const double rs = P.rowscale[row] * P.gscale;
+            const double rs = P.rowscale[row] * P.gscale * (MODE == OZ_GEMM ? P.sign : 1.0);
             oz_mbar_wait(tmem_full, acc_ph);
             oz_fence_after();
             acc_ph ^= 1;
@@ -507,16 +590,21 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_kernel(OzParams P) {
                     double w = fma((double)whi, hi_mul, (double)wlo);
                     v[i] = w * rs;
                 }
-                if (MODE == OZ_LAUUM) {
-                    // K_y^-1[row][col0 .. col0 + 7]: the exact integer sum, scaled by the two power-of-two row scales
+                if (MODE == OZ_LAUUM || MODE == OZ_GEMM) {
+                    // out[row][col0 .. col0 + 7]: the exact integer sum, scaled by the two power-of-two row scales
                     const int col0 = (int)ct * OZ_NT + hsel * 32 + cc * 8;
-                    const double4 c0 = *reinterpret_cast<const double4*>(P.rowscale + col0);
-                    const double4 c1 = *reinterpret_cast<const double4*>(P.rowscale + col0 + 4);
+                    const double* cs = MODE == OZ_GEMM ? P.colscale : P.rowscale;
+                    const double4 c0 = *reinterpret_cast<const double4*>(cs + col0);
+                    const double4 c1 = *reinterpret_cast<const double4*>(cs + col0 + 4);
+                    const double o[8] = {v[0] * c0.x, v[1] * c0.y, v[2] * c0.z, v[3] * c0.w, v[4] * c1.x, v[5] * c1.y, v[6] * c1.z, v[7] * c1.w};
                     double2* dst = reinterpret_cast<double2*>(P.out + (size_t)row * P.Np + col0);
-                    dst[0] = make_double2(v[0] * c0.x, v[1] * c0.y);
-                    dst[1] = make_double2(v[2] * c0.z, v[3] * c0.w);
-                    dst[2] = make_double2(v[4] * c1.x, v[5] * c1.y);
-                    dst[3] = make_double2(v[6] * c1.z, v[7] * c1.w);
+#pragma unroll
+                    for (int i = 0; i < 4; i++) dst[i] = make_double2(o[2 * i], o[2 * i + 1]);
+                    if (MODE == OZ_GEMM && P.out_t != nullptr) {
+                        // lanes hold consecutive rows: 256 contiguous bytes per column
+#pragma unroll
+                        for (int i = 0; i < 8; i++) P.out_t[(size_t)(col0 + i) * P.Np + row] = o[i];
+                    }
                 } else {
 #pragma unroll
                     for (int i = 0; i < 8; i++) v[i] = v[i] * v[i];

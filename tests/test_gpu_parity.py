@@ -160,6 +160,46 @@ def test_kinv_engines_agree(cuda, N, d, noise):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+# recursive-doubling inverse factor: FP64 DMMA tile tasks against the exact-integer int8 tcgen05 products
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("N,d,noise,persistent", [(200, 2, 1e-3, True), (300, 3, 1e-3, True), (700, 4, 1e-3, False), (1100, 5, 1e-3, True),
+                                                  (2100, 6, 2e-5, True), (4096, 10, 1e-3, True)])
+def test_inverse_engines_agree(cuda, N, d, noise, persistent):
+    """L^-1 from the int8 engine (8 digits: 62-bit fixed point per operand row, exact integer accumulation, two products
+    per level) against the DMMA tile tasks: same inverse to fp64 rounding, same LML, same predictions."""
+    X, y = synthetic(N, d, seed=3)
+    h = go.Hyper(0.25 * np.sqrt(d), 1.2, noise, -0.1)
+    theta = theta_of(h)
+    Xc = np.random.default_rng(9).random((3000, d))
+    out = {}
+    for name, mode in (("dmma", 1), ("int8", 2)):
+        s = open_session(cuda, "Matern52", X, y)
+        s.set_factor_mode(persistent)
+        s.set_inverse_mode(mode)
+        s.factorize(theta)
+        linv = s.debug_fetch(2)
+        lml = s.log_marginal_likelihood()
+        mean, var = s.predict_y(Xc)
+        f, g = s.neg_lml_and_grad(h.pack())
+        out[name] = (linv, lml, mean, var, f, g, s.debug_fetch(1))
+        s.close()
+    a, b = out["dmma"], out["int8"]
+    np.testing.assert_array_equal(a[6], b[6])  # the Cholesky factor itself does not depend on the engine
+    rowmax = np.abs(a[0]).max(axis=1, keepdims=True)
+    assert np.all(np.abs(a[0] - b[0]) <= 1e-11 * rowmax), float((np.abs(a[0] - b[0]) / rowmax).max())
+    np.testing.assert_allclose(b[0] @ a[6], np.eye(N), rtol=0, atol=1e-8)
+    assert abs(a[1] - b[1]) <= 1e-10 * max(abs(a[1]), N)
+    assert_predict_close(b[2], b[3], a[2], a[3], y, h.variance, rel=1e-9)
+    assert abs(a[4] - b[4]) <= 1e-10 * max(abs(a[4]), N)
+    assert np.all(np.abs(a[5] - b[5]) <= 1e-7 * np.maximum(np.abs(a[5]), 1.0)), (a[5], b[5])
+    if N <= 1100:
+        lml_ref = go.lml("Matern52", X, y, h)
+        assert abs(b[1] - lml_ref) <= 1e-9 * max(abs(lml_ref), N)
+        mean_ref, var_ref = go.predict_y("Matern52", X, y, h, Xc)
+        assert_predict_close(b[2], b[3], mean_ref[:, 0], var_ref[:, 0], y, h.variance)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
 # the two Cholesky schedules: persistent tile scheduler (default) and one launch per step
 # ---------------------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("N,d", [(129, 2), (300, 3), (1100, 5), (2100, 6)])
