@@ -132,6 +132,9 @@ int gpso_set_kinv_mode(gpso_handle* h, int mode);
  *   0 automatic (int8 when the padded N >= 2048), 1 = FP64 DMMA tile tasks inside the persistent factorisation kernel,
  *   2 = exact-integer products of 8-digit (62-bit) fixed-point operands on the int8 tensor cores, two per level. */
 int gpso_set_inverse_mode(gpso_handle* h, int mode);
+/* int8 engine only: keep the digit tiles of L^-1 in the persisting (set-aside) part of L2 through an access-policy
+ * window on the handle's product stream (default on; takes effect at the next gpso_factorize) */
+int gpso_set_l2_window(gpso_handle* h, int enabled);
 /* out[0] = engine in force after the last gpso_factorize (1 or 2), out[1] = digits per operand (0 for engine 1),
  * out[2] = estimated error of the variance / parity tolerance for that choice */
 int gpso_predict_info(gpso_handle* h, double* out3);

@@ -90,6 +90,7 @@ def load_library():
         "gpso_debug_trace": (i64, [H, _c_double_p, i64]),
         "gpso_set_kinv_mode": (i32, [H, i32]),
         "gpso_set_inverse_mode": (i32, [H, i32]),
+        "gpso_set_l2_window": (i32, [H, i32]),
     }
     for name, (restype, argtypes) in protos.items():
         try:
@@ -110,7 +111,7 @@ EXPORTED_SYMBOLS = (
     "gpso_grow_count gpso_grow_leaves_host gpso_grow_leaves_dev gpso_grow_ucb_argmax gpso_state_bytes "
     "gpso_export_state_dev gpso_import_state_dev gpso_launch_count gpso_debug_fetch gpso_last_timing gpso_set_window "
     "gpso_set_profile gpso_last_windows gpso_set_predict_mode gpso_predict_info gpso_set_overlap "
-    "gpso_set_factor_mode gpso_debug_factor_tasks gpso_debug_trace gpso_set_kinv_mode gpso_set_inverse_mode"
+    "gpso_set_factor_mode gpso_debug_factor_tasks gpso_debug_trace gpso_set_kinv_mode gpso_set_inverse_mode gpso_set_l2_window"
 ).split()
 
 
@@ -249,6 +250,10 @@ class CudaSession:
     def set_kinv_mode(self, mode=0):
         """K_y^-1 = L^-T L^-1 of the gradient: 0 automatic, 1 FP64 DMMA tiles, 2 int8 tcgen05 (54-bit fixed point)."""
         _check(self._lib, self._lib.gpso_set_kinv_mode(self._h, int(mode)), "gpso_set_kinv_mode")
+
+    def set_l2_window(self, enabled=True):
+        """int8 engine: persisting-L2 access window over the digit tiles of L^-1 (default on)."""
+        _check(self._lib, self._lib.gpso_set_l2_window(self._h, int(bool(enabled))), "gpso_set_l2_window")
 
     def set_inverse_mode(self, mode=0):
         """Recursive-doubling L^-1: 0 automatic, 1 FP64 DMMA tile tasks, 2 int8 tcgen05 (62-bit fixed point)."""

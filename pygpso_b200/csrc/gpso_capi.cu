@@ -105,6 +105,8 @@ struct gpso_handle {
     int device = 0, kernel_id = KERNEL_MATERN52, ard = 0, mean_id = GPSO_MEAN_CONSTANT;
     int N = 0, d = 0, Np = 0, nb = 0;
     int nsm = 0;
+    size_t l2_persist_max = 0, l2_window_max = 0;  // device limits for the persisting-L2 access window of the A digits
+    int l2_window = 1;                              // gpso_set_l2_window
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_used[2] = {nullptr, nullptr}, ev_t0 = nullptr, ev_t1 = nullptr;
     bool used_pending[2] = {false, false};
@@ -803,6 +805,26 @@ static double oz_beta(const gpso_handle* h) {  // 2^f with kernel variance < 2^f
     return ldexp(1.0, ilogb(h->variance) + 1);
 }
 
+// The A digits of L^-1 are re-read by every candidate tile of every window (69 GB of L2 -> SM traffic per 87k-candidate
+// window at N = 4096) while 2 GB of B digits stream through the same L2.  An access-policy window on the product stream
+// marks the A buffer as persisting (set-aside L2) so the stream cannot evict it: only the lower-triangle tiles are ever
+// touched (half of the buffer), hitRatio scales the request down when even that exceeds the set-aside.
+static int set_l2_window(gpso_handle* h, void* base, size_t bytes) {
+    if (!h->l2_window || h->l2_persist_max == 0 || h->l2_window_max == 0 || !base) return 0;
+    CU_TRY(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, h->l2_persist_max));
+    cudaStreamAttrValue attr;
+    memset(&attr, 0, sizeof attr);
+    const size_t win = std::min(bytes, h->l2_window_max);
+    const double touched = 0.5 * (double)win + 1.0;
+    attr.accessPolicyWindow.base_ptr = base;
+    attr.accessPolicyWindow.num_bytes = win;
+    attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, 0.9 * (double)h->l2_persist_max / touched);
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+    CU_TRY(cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
+    return 0;
+}
+
 // After L^-1 is known: decide whether the int8 tensor-core product is used for this fit and build its A digit tiles.
 static int prepare_ozaki(gpso_handle* h, cudaStream_t st) {
     h->oz_S = 0;
@@ -832,6 +854,7 @@ static int prepare_ozaki(gpso_handle* h, cudaStream_t st) {
     GP_TRY(check_launch(h, "linv_slices"));
     h->oz_S = S;
     h->oz_est = est;
+    GP_TRY(set_l2_window(h, h->ozA.p, (size_t)Np * Np * S));
     return 0;
 }
 
@@ -870,6 +893,8 @@ extern "C" int gpso_create(int device, int kernel_id, int ard, int mean_id, gpso
     h->ard = ard ? 1 : 0;
     h->mean_id = mean_id;
     h->nsm = prop.multiProcessorCount;
+    h->l2_persist_max = (size_t)std::max(0, prop.persistingL2CacheMaxSize);
+    h->l2_window_max = (size_t)std::max(0, prop.accessPolicyMaxWindowSize);
     // h->stream carries the tensor-core product kernels: highest priority, so that its persistent CTAs are placed before
     // the (default-priority) cross-covariance blocks of the next window when both become eligible at the same time
     int prio_least = 0, prio_greatest = 0;
@@ -1582,6 +1607,18 @@ extern "C" int gpso_set_kinv_mode(gpso_handle* h, int mode) {
 extern "C" int gpso_set_inverse_mode(gpso_handle* h, int mode) {
     if (!h || mode < 0 || mode > 2) return fail(GPSO_E_BADARG, "gpso_set_inverse_mode: mode must be 0 (auto), 1 (fp64 DMMA) or 2 (int8 tcgen05)");
     h->inverse_mode = mode;
+    h->factorized = false;
+    return 0;
+}
+
+extern "C" int gpso_set_l2_window(gpso_handle* h, int enabled) {
+    if (!h) return fail(GPSO_E_BADARG, "gpso_set_l2_window: null handle");
+    h->l2_window = enabled != 0;
+    if (!enabled && h->stream) {
+        cudaStreamAttrValue attr;
+        memset(&attr, 0, sizeof attr);
+        CU_TRY(cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
+    }
     h->factorized = false;
     return 0;
 }

@@ -92,6 +92,13 @@ def main():
     sess.set_overlap(False)
     timed(steps, "no_overlap")
     sess.set_overlap(True)
+    # persisting-L2 window over the A digits off / on again (same process, same GPU)
+    sess.set_l2_window(False)
+    sess.factorize(theta)
+    timed(steps, "l2_window_off")
+    sess.set_l2_window(True)
+    sess.factorize(theta)
+    timed(steps, "l2_window_on_again")
 
     # per-stage sums with the stages run back to back (no overlap)
     sess.set_profile(1)
@@ -127,7 +134,7 @@ def main():
     os.makedirs(os.path.dirname(out_path), exist_ok=True)
     with open(out_path, "w") as fh:
         json.dump(report, fh, indent=1)
-    print(json.dumps({k: report[k] for k in ("overlap", "no_overlap", "serialised_ms_per_window", "summary")}, indent=1))
+    print(json.dumps({k: report[k] for k in ("overlap", "no_overlap", "l2_window_off", "l2_window_on_again", "serialised_ms_per_window", "summary")}, indent=1))
     sess.close()
 
 
