@@ -186,6 +186,19 @@ static int check_launch(gpso_handle* h, const char* what) {
     return 0;
 }
 
+// The set-aside is a device-wide setting and shrinks the L2 left to everything else (the factorisation kernels pass their
+// tiles between SMs through L2: LML+grad at N = 4096 went from 3.8 to 4.6 ms with the set-aside left on), so it is only in
+// force between a factorisation for scoring and the next fit evaluation.
+static size_t g_l2_setaside[64] = {0};
+static int l2_setaside(gpso_handle* h, size_t bytes) {
+    const int dev = h->device & 63;
+    if (g_l2_setaside[dev] == bytes) return 0;
+    if (bytes == 0) CU_TRY(cudaCtxResetPersistingL2Cache());
+    CU_TRY(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, bytes));
+    g_l2_setaside[dev] = bytes;
+    return 0;
+}
+
 template <int KID>
 static void launch_gram(gpso_handle* h, cudaStream_t st) {
     dim3 grid(h->Np / CT, h->Np / CT);
@@ -691,6 +704,7 @@ static int inverse_int8(gpso_handle* h, cudaStream_t st) {
 // Gram -> Cholesky -> inverse factor -> [K_y^-1] -> a, alpha -> scalars.  Uses h->ls_host/variance/noise/c0.
 static int factor_pipeline(gpso_handle* h, cudaStream_t st, bool need_kinv) {
     const int Np = h->Np, nb = h->nb;
+    GP_TRY(l2_setaside(h, 0));  // the whole L2 for the tile traffic of the factorisation (see set_l2_window)
     GP_TRY(upload_lengthscales(h, st));
     CU_TRY(cudaMemsetAsync(h->info.p, 0, sizeof(int), st));
     scale_inputs_kernel<<<(Np + 255) / 256, 256, 0, st>>>(h->X.as<double>(), h->ls.as<double>(), h->n_ls(), h->N, h->d, Np,
@@ -811,7 +825,7 @@ static double oz_beta(const gpso_handle* h) {  // 2^f with kernel variance < 2^f
 // touched (half of the buffer), hitRatio scales the request down when even that exceeds the set-aside.
 static int set_l2_window(gpso_handle* h, void* base, size_t bytes) {
     if (!h->l2_window || h->l2_persist_max == 0 || h->l2_window_max == 0 || !base) return 0;
-    CU_TRY(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, h->l2_persist_max));
+    GP_TRY(l2_setaside(h, h->l2_persist_max));
     cudaStreamAttrValue attr;
     memset(&attr, 0, sizeof attr);
     const size_t win = std::min(bytes, h->l2_window_max);
