@@ -22,7 +22,8 @@
 //   linv_slices_kernel      L^-1 (fp64, lower)  -> A digit tiles  [I][ks][p][128 rows x 32 k]  canonical UMMA K-major,
 //                                                   no-swizzle core matrices (8 rows x 16 B), once per factorisation
 //   crosscov_slices_kernel  candidates -> k*(fp64, registers) -> B digit tiles [ct][ks][q][64 cand x 32 k] + posterior mean
-//   ozaki_trmm_kernel<S>    warp-specialised persistent kernel, one CTA per SM:
+//   ozaki_kernel<S, MODE>   warp-specialised persistent kernel, one CTA per SM (MODE: OZ_TRMM below; OZ_LAUUM / OZ_GEMM reuse the
+//                           mainloop for K_y^-1 = L^-T L^-1 and the inverse factor of the fit path, see OzItems and the epilogue):
 //        warp 0   producer : cp.async.bulk (UBLKCP) of one k-step (S*4 KB of A, S*2 KB of B) per stage, mbarrier tx
 //        warp 1   issuer   : tcgen05.mma.cta_group::1.kind::i8, M=128, N up to 256: digit p of A against digits
 //                            0..S-1-p of B stacked along N, accumulating level t=p+q into TMEM columns [64t, 64t+64)
