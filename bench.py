@@ -36,6 +36,7 @@ WORKLOADS = {
 FP64_PEAK_TFLOPS = 37.03  # measured DMMA.8x8x4 issue peak of this pool's B200 (profiles/r01_fp64_probe.txt)
 INT8_PEAK_TOPS = 4528.7   # measured tcgen05.mma kind::i8 issue peak, M=128 N=256, 148 SMs (profiles/r01_i8_tcgen05_probe.txt)
 CPU_SAMPLE = 8192         # candidates per CPU-baseline step (bounded sample of the same workload)
+LOGICAL_SHARDS = 64       # the candidate matrix is generated in 64 seeded pieces, so it is the same for every GPU count
 
 
 def synthetic_training(N, d):
@@ -43,6 +44,17 @@ def synthetic_training(N, d):
     X = rng.random((N, d))
     y = np.sin(3.0 * X.sum(axis=1)) + 0.01 * rng.standard_normal(N)
     return X, y[:, None]
+
+
+def fill_candidates(out, start, stop, M, d):
+    """Rows [start, stop) of the M x d synthetic candidate matrix into ``out``.  Logical shard s (rows s*ceil(M/64) ...) comes
+    from ``default_rng([SEED, s])``, whatever the number of ranks: every GPU count scores the same matrix."""
+    per = -(-M // LOGICAL_SHARDS)
+    for s in range(start // per, (stop - 1) // per + 1 if stop > start else 0):
+        lo, hi = s * per, min(M, (s + 1) * per)
+        block = np.random.default_rng([SEED, s]).random((hi - lo, d))
+        a, b = max(lo, start), min(hi, stop)
+        out[a - start:b - start] = block[a - lo:b - lo]
 
 
 def fixed_theta(d):
@@ -174,7 +186,8 @@ def run_reference(args, rank):
     X, y = synthetic_training(N, d)
     theta = fixed_theta(d)
     sample = min(M, CPU_SAMPLE)
-    Xc = np.random.default_rng([SEED, 0]).random((sample, d))
+    Xc = np.empty((sample, d))
+    fill_candidates(Xc, 0, sample, M, d)
     for _ in range(args.warmup):
         cpu_reference_step(X, y, theta, Xc, go.VARSIGMA_DEFAULT)
     t0 = time.perf_counter()
@@ -272,7 +285,7 @@ def main():
     m_local = stop - start
     host = torch.empty((max(m_local, 1), d), dtype=torch.float64, pin_memory=True)
     xc_host = host.numpy()[:m_local]
-    np.random.default_rng([SEED, rank]).random(out=xc_host)
+    fill_candidates(xc_host, start, stop, M, d)
     xc_dev = host[:m_local].to("cuda", non_blocking=False)
     stream = torch.cuda.current_stream().cuda_stream
 

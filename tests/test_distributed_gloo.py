@@ -109,3 +109,22 @@ def test_world_size_2_gloo(tmp_path):
     y = np.sin(3 * X.sum(1))[:, None]
     single = go.OracleGPR(X, y, "Matern52", 0.25, 1.0, 1e-3, 0.0).fit(options={"maxiter": 30})
     assert fs[0] == pytest.approx(single.fun, rel=1e-12)
+
+
+def test_bench_candidate_matrix_is_the_same_for_every_world_size():
+    """bench.py generates the synthetic candidates in 64 seeded logical shards: 1, 2, 4 or 8 ranks score the same matrix,
+    so the selected candidate (index and UCB) can be compared across GPU counts."""
+    import bench
+    from pygpso_b200.distributed import shard_bounds
+
+    M, d = 10_007, 4
+    full = np.empty((M, d))
+    bench.fill_candidates(full, 0, M, M, d)
+    for world in (2, 3, 8):
+        parts = []
+        for rank in range(world):
+            start, stop = shard_bounds(M, world, rank)
+            part = np.empty((stop - start, d))
+            bench.fill_candidates(part, start, stop, M, d)
+            parts.append(part)
+        assert np.array_equal(np.vstack(parts), full)
