@@ -371,12 +371,19 @@ __global__ void __launch_bounds__(256, 2) crosscov_slices_kernel(const double* _
     double macc[2] = {0.0, 0.0};
     const int nss = Np / OZ_XK;
     for (int ss = 0; ss < nss; ss++) {
+        cp_async_wait<0>();
         __syncthreads();
         const int b = ss & 1;
         if (ss + 1 < nss) {
+            // next slab of training coordinates / alpha: asynchronous 16-byte copies (LDGSTS), no registers and no
+            // scoreboard stall in front of the FP64 work (13 % of the issue stalls when these were plain loads)
             double* nx = sX + (b ^ 1) * d * OZ_XK;
-            for (int e = tid; e < d * OZ_XK; e += 256) nx[e] = Xs[(size_t)(e >> 7) * Np + (ss + 1) * OZ_XK + (e & 127)];
-            if (tid < OZ_XK) sAl[(b ^ 1) * OZ_XK + tid] = alpha[(ss + 1) * OZ_XK + tid];
+            for (int e = tid; e < d * (OZ_XK / 2); e += 256) {
+                const int dim = e >> 6, pr = (e & 63) * 2;
+                cp_async16(nx + dim * OZ_XK + pr, Xs + (size_t)dim * Np + (ss + 1) * OZ_XK + pr);
+            }
+            if (tid < OZ_XK / 2) cp_async16(sAl + (b ^ 1) * OZ_XK + tid * 2, alpha + (ss + 1) * OZ_XK + tid * 2);
+            cp_async_commit();
         }
         const double* x = sX + b * d * OZ_XK + kg * 16;
         double r2[2][16];
