@@ -118,7 +118,7 @@ int64_t gpso_last_windows(gpso_handle* h);
  * variance product start/end, 5 finalise + arg-max merge end (product stream). */
 int64_t gpso_debug_trace(gpso_handle* h, double* out, int64_t capacity);
 /* Engine of the variance product V = L^-1 k* inside predict_y / ucb_argmax (takes effect at the next gpso_factorize):
- *   mode 0 automatic (int8 when the padded N >= 512), 1 = FP64 DMMA (mma.sync m8n8k4.f64), 2 = exact-integer emulation
+ *   mode 0 automatic (int8 when the padded N >= 256), 1 = FP64 DMMA (mma.sync m8n8k4.f64), 2 = exact-integer emulation
  *   of the fp64 product on the int8 tensor cores (tcgen05.mma kind::i8, accumulators in TMEM).
  *   slices: 8-bit digits per operand for mode 2, 5..8, or 0 = chosen per fit from the row scales of L^-1 so that the
  *   estimated error stays below 2% of the parity tolerance 1e-8 * kernel variance. */

@@ -55,7 +55,8 @@ constexpr int MAX_LS = LEAF_MAXD;  // maximum input dimension supported
 constexpr double NOISE_FLOOR = 1.0e-6;
 constexpr long long WINDOW_BYTES = 2LL << 30;  // rolling cross-covariance window budget (2 GiB)
 constexpr int OZ_XCOV_SMEM_MAX = 172 * 1024;   // crosscov_slices_kernel dynamic shared memory at d = 64 (320 d + 768 doubles)
-constexpr int OZ_MIN_NP = 512;                 // below this the int8 path is not worth its fixed costs (automatic mode)
+constexpr int OZ_MIN_NP = 256;                 // below this the int8 path is not worth its fixed costs (automatic mode); config C5
+                                               // (N = 21..500, 265 720 candidates per call): 9.6 s wall with 512, 7.0 s with 256, 7.0 s with 128
 constexpr int OZ_MAX_NP = 16384;               // int32 accumulators stay exact: S * 2^14 * Np < 2^31
 constexpr int OZ_KINV_S = 7;                   // digits per operand of the int8 K_y^-1 = L^-T L^-1 product (54-bit fixed point per row)
 constexpr int OZ_KINV_MIN_NP = 1024;           // automatic mode: below this the DMMA tile kernel is as fast (launch-bound sizes)
@@ -843,7 +844,8 @@ static int set_l2_window(gpso_handle* h, void* base, size_t bytes) {
 static int prepare_ozaki(gpso_handle* h, cudaStream_t st) {
     h->oz_S = 0;
     h->oz_est = 0.0;
-    bool want = h->predict_mode == 2 || (h->predict_mode == 0 && h->Np >= OZ_MIN_NP);
+    static const int min_np = getenv("GPSO_OZ_MIN_NP") ? atoi(getenv("GPSO_OZ_MIN_NP")) : OZ_MIN_NP;  // tuning experiments only
+    bool want = h->predict_mode == 2 || (h->predict_mode == 0 && h->Np >= min_np);
     if (!want || h->Np > OZ_MAX_NP) return 0;
     const int Np = h->Np;
     GP_TRY(h->rowscale.ensure((size_t)Np * sizeof(double)));
