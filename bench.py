@@ -147,7 +147,7 @@ def bench_lml_grad(cuda, go, cpu=True, shapes=((4096, 10), (8192, 20)), evals=5)
             sess.neg_lml_and_grad(u + 1e-3 * (i + 1))
             step_ms += sess.last_timing_ms()[0]
         sess.set_factor_mode(True)
-        # ... and with K_y^-1 = L^-T L^-1 on the FP64 DMMA tiles instead of the int8 tensor-core product (automatic from N=1024)
+        # ... and with K_y^-1 = L^-T L^-1 on the FP64 DMMA tiles instead of the int8 tensor-core product (automatic from N=512)
         sess.set_kinv_mode(1)
         sess.neg_lml_and_grad(u)
         kinv_dmma_ms = 0.0

@@ -124,12 +124,12 @@ int64_t gpso_debug_trace(gpso_handle* h, double* out, int64_t capacity);
  *   estimated error stays below 2% of the parity tolerance 1e-8 * kernel variance. */
 int gpso_set_predict_mode(gpso_handle* h, int mode, int slices);
 /* Engine of K_y^-1 = L^-T L^-1 inside gpso_neg_lml_grad (the gradient's trace terms need K_y^-1 element-wise):
- *   0 automatic (int8 when the padded N >= 1024), 1 = FP64 DMMA tiles, 2 = exact-integer product of 7-digit (54-bit)
+ *   0 automatic (int8 when the padded N >= 512), 1 = FP64 DMMA tiles, 2 = exact-integer product of 7-digit (54-bit)
  *   fixed-point operands on the int8 tensor cores -- operand rounding 2^-54 relative to each row's largest entry, i.e.
  *   the size of the fp64 rounding of those entries; the integer accumulation itself is exact. */
 int gpso_set_kinv_mode(gpso_handle* h, int mode);
 /* Engine of the recursive-doubling inverse factor L^-1 (both gpso_factorize and gpso_neg_lml_grad):
- *   0 automatic (int8 when the padded N >= 2048), 1 = FP64 DMMA tile tasks inside the persistent factorisation kernel,
+ *   0 automatic (int8 when the padded N >= 512), 1 = FP64 DMMA tile tasks inside the persistent factorisation kernel,
  *   2 = exact-integer products of 8-digit (62-bit) fixed-point operands on the int8 tensor cores, two per level. */
 int gpso_set_inverse_mode(gpso_handle* h, int mode);
 /* int8 engine only: keep the digit tiles of L^-1 in the persisting (set-aside) part of L2 through an access-policy

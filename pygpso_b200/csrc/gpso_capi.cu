@@ -59,9 +59,9 @@ constexpr int OZ_MIN_NP = 256;                 // below this the int8 path is no
                                                // (N = 21..500, 265 720 candidates per call): 9.6 s wall with 512, 7.0 s with 256, 7.0 s with 128
 constexpr int OZ_MAX_NP = 16384;               // int32 accumulators stay exact: S * 2^14 * Np < 2^31
 constexpr int OZ_KINV_S = 7;                   // digits per operand of the int8 K_y^-1 = L^-T L^-1 product (54-bit fixed point per row)
-constexpr int OZ_KINV_MIN_NP = 1024;           // automatic mode: below this the DMMA tile kernel is as fast (launch-bound sizes)
+constexpr int OZ_KINV_MIN_NP = 512;            // automatic mode; measured down to N = 512 (LML+grad 0.553 -> 0.498 ms there, 1.13 -> 1.01 ms at 1024)
 constexpr int OZ_INV_S = 8;                    // digits per operand of the int8 inverse-factor products (62-bit fixed point per row)
-constexpr int OZ_INV_MIN_NP = 2048;            // automatic mode: below this the DMMA tasks inside the persistent kernel win
+constexpr int OZ_INV_MIN_NP = 512;             // automatic mode; measured down to N = 512 (0.498 -> 0.474 ms there, 2.05 -> 1.75 ms at 2048)
 constexpr double OZ_TARGET = 0.02;             // accepted (estimated error) / (parity tolerance 1e-8 * variance)
 
 struct DevBuf {

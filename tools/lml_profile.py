@@ -35,6 +35,10 @@ def main():
         s.set_kinv_mode(1)
     if "--kinv-int8" in sys.argv:
         s.set_kinv_mode(2)
+    if "--inv-dmma" in sys.argv:
+        s.set_inverse_mode(1)
+    if "--inv-int8" in sys.argv:
+        s.set_inverse_mode(2)
     theta = np.array([0.25 * np.sqrt(d), 1.0, 1e-3, 0.0])
     u = np.array([softplus_inv(theta[0]), softplus_inv(theta[1]), softplus_inv(theta[2] - 1e-6), 0.0])
     if "--factorize" in sys.argv:
