@@ -128,6 +128,12 @@ int gpso_set_predict_mode(gpso_handle* h, int mode, int slices);
  *   fixed-point operands on the int8 tensor cores -- operand rounding 2^-54 relative to each row's largest entry, i.e.
  *   the size of the fp64 rounding of those entries; the integer accumulation itself is exact. */
 int gpso_set_kinv_mode(gpso_handle* h, int mode);
+/* Host-only (no GPU): the tile -> CTA tables of the int8 fit-path products for a matrix of nb panels on nsm SMs, for the
+ * CPU tests.  kind 0 = K_y^-1 (one int per slot: row block << 16 | 64-wide column tile, -1 = empty; info = {rounds});
+ * kind 1 = inverse factor (four ints per slot: row block, 64-row tile of the second operand, first k-step, k-steps;
+ * info = per level {s, xt offset, xt rounds, y offset, y rounds}, offsets in ints).  Returns the table size in ints. */
+int64_t gpso_debug_product_items(int kind, int nb, int nsm, int* out, int64_t capacity, int* info, int info_capacity,
+                                 int* levels_out);
 /* Engine of the recursive-doubling inverse factor L^-1 (both gpso_factorize and gpso_neg_lml_grad):
  *   0 automatic (int8 when the padded N >= 512), 1 = FP64 DMMA tile tasks inside the persistent factorisation kernel,
  *   2 = exact-integer products of 8-digit (62-bit) fixed-point operands on the int8 tensor cores, two per level. */

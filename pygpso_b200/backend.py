@@ -91,6 +91,8 @@ def load_library():
         "gpso_set_kinv_mode": (i32, [H, i32]),
         "gpso_set_inverse_mode": (i32, [H, i32]),
         "gpso_set_l2_window": (i32, [H, i32]),
+        "gpso_debug_product_items": (i64, [i32, i32, i32, ctypes.POINTER(ctypes.c_int), i64, ctypes.POINTER(ctypes.c_int), i32,
+                                           ctypes.POINTER(ctypes.c_int)]),
     }
     for name, (restype, argtypes) in protos.items():
         try:
@@ -111,7 +113,7 @@ EXPORTED_SYMBOLS = (
     "gpso_grow_count gpso_grow_leaves_host gpso_grow_leaves_dev gpso_grow_ucb_argmax gpso_state_bytes "
     "gpso_export_state_dev gpso_import_state_dev gpso_launch_count gpso_debug_fetch gpso_last_timing gpso_set_window "
     "gpso_set_profile gpso_last_windows gpso_set_predict_mode gpso_predict_info gpso_set_overlap "
-    "gpso_set_factor_mode gpso_debug_factor_tasks gpso_debug_trace gpso_set_kinv_mode gpso_set_inverse_mode gpso_set_l2_window"
+    "gpso_set_factor_mode gpso_debug_factor_tasks gpso_debug_trace gpso_set_kinv_mode gpso_set_inverse_mode gpso_set_l2_window gpso_debug_product_items"
 ).split()
 
 

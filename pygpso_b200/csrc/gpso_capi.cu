@@ -532,9 +532,8 @@ extern "C" int gpso_debug_factor_tasks(int nb, int nsm, int* out, int64_t capaci
 // K_y^-1 = L^-T L^-1 on the int8 tensor cores (kern_ozaki.cuh, OZ_LAUUM).  The tiles (row block I, 64-wide column tile
 // ct <= 2I+1) cost nks - 4I k-steps each (the contraction runs over k >= i only); they are dealt to the nsm persistent CTAs
 // longest-first, each to the CTA with the least work so far, and stored as a [rounds][nsm] table the kernel walks by rounds.
-static int build_lauum_items(gpso_handle* h) {
-    const int nb = h->nb, nks = h->Np / 32, G = h->nsm > 0 ? h->nsm : 148;
-    if (h->lauum_items_nb == nb && h->lauum_items.p) return 0;
+static void make_lauum_items(int nb, int G, std::vector<int>& flat, int& rounds_out) {
+    const int nks = nb * 4;
     std::vector<std::vector<int>> per(G);
     std::vector<long long> load(G, 0);
     for (int I = 0; I < nb; I++) {  // I ascending = cost descending
@@ -549,9 +548,18 @@ static int build_lauum_items(gpso_handle* h) {
     }
     size_t rounds = 0;
     for (int g = 0; g < G; g++) rounds = std::max(rounds, per[g].size());
-    std::vector<int> flat(rounds * G, -1);
+    flat.assign(rounds * G, -1);
     for (int g = 0; g < G; g++)
         for (size_t r = 0; r < per[g].size(); r++) flat[r * G + g] = per[g][r];
+    rounds_out = (int)rounds;
+}
+
+static int build_lauum_items(gpso_handle* h) {
+    const int nb = h->nb, G = h->nsm > 0 ? h->nsm : 148;
+    if (h->lauum_items_nb == nb && h->lauum_items.p) return 0;
+    std::vector<int> flat;
+    int rounds = 0;
+    make_lauum_items(nb, G, flat, rounds);
     GP_TRY(h->lauum_items.ensure(flat.size() * sizeof(int)));
     CU_TRY(cudaMemcpy(h->lauum_items.p, flat.data(), flat.size() * sizeof(int), cudaMemcpyHostToDevice));
     h->lauum_items_nb = nb;
@@ -595,11 +603,12 @@ static int kinv_int8(gpso_handle* h, cudaStream_t st) {
 // L^-T).  Every operand row is cut into 8 balanced 8-bit digits of a 62-bit fixed-point number relative to the row's
 // largest entry in the range the level reads, so the operand rounding (2^-62 of the row scale) is below the fp64 rounding of
 // those entries and the integer accumulation is exact.  Tiles (128 x 64) are dealt to the persistent CTAs longest-first.
-static int build_inverse_items(gpso_handle* h) {
-    const int nb = h->nb, G = h->nsm > 0 ? h->nsm : 148;
-    if (h->inv_items_nb == nb && h->inv_items.p) return 0;
-    std::vector<int> all;
-    h->inv_levels.clear();
+namespace {
+struct InvLevelInfo { int s; size_t xt_off; int xt_rounds; size_t y_off; int y_rounds; };
+}
+static void make_inverse_items(int nb, int G, std::vector<int>& all, std::vector<InvLevelInfo>& levels) {
+    all.clear();
+    levels.clear();
     auto deal = [&](std::vector<std::array<int, 4>>& items, size_t& off, int& rounds) {
         std::stable_sort(items.begin(), items.end(), [](const std::array<int, 4>& a, const std::array<int, 4>& b) { return a[3] > b[3]; });
         std::vector<std::vector<int>> per(G);
@@ -631,13 +640,23 @@ static int build_inverse_items(gpso_handle* h) {
                         y.push_back({a + s + v, 2 * (a + u) + hh, 4 * (a + s), 4 * (v + 1)});
                     }
         }
-        gpso_handle::InvLevel lv;
+        InvLevelInfo lv;
         lv.s = s;
         deal(xt, lv.xt_off, lv.xt_rounds);
         deal(y, lv.y_off, lv.y_rounds);
-        h->inv_levels.push_back(lv);
+        levels.push_back(lv);
     }
     if (all.empty()) all.resize(4, -1);
+}
+
+static int build_inverse_items(gpso_handle* h) {
+    const int nb = h->nb, G = h->nsm > 0 ? h->nsm : 148;
+    if (h->inv_items_nb == nb && h->inv_items.p) return 0;
+    std::vector<int> all;
+    std::vector<InvLevelInfo> levels;
+    make_inverse_items(nb, G, all, levels);
+    h->inv_levels.clear();
+    for (const InvLevelInfo& lv : levels) h->inv_levels.push_back({lv.s, lv.xt_off, lv.xt_rounds, lv.y_off, lv.y_rounds});
     GP_TRY(h->inv_items.ensure(all.size() * sizeof(int)));
     CU_TRY(cudaMemcpy(h->inv_items.p, all.data(), all.size() * sizeof(int), cudaMemcpyHostToDevice));
     h->inv_items_nb = nb;
@@ -1612,6 +1631,41 @@ extern "C" int gpso_set_factor_mode(gpso_handle* h, int mode) {
     if (!h || mode < 0 || mode > 1) return fail(GPSO_E_BADARG, "gpso_set_factor_mode: bad argument");
     h->chol_mode = mode;
     return 0;
+}
+
+// Host-only introspection (no GPU needed) of the tile -> CTA tables of the int8 fit-path products.  kind 0: K_y^-1 (one
+// int per slot: row block << 16 | column tile, -1 empty; levels = 1, info = {rounds});  kind 1: inverse factor (four ints
+// per slot: row block, 64-row tile of B, first k-step, k-steps; info = per level {s, xt_offset, xt_rounds, y_offset, y_rounds},
+// offsets in ints).  Returns the number of ints of the table; copies min(capacity, that) ints.
+extern "C" int64_t gpso_debug_product_items(int kind, int nb, int nsm, int* out, int64_t capacity, int* info, int info_capacity,
+                                            int* levels_out) {
+    if (nb < 1 || nb > 255 || nsm < 1) return fail(GPSO_E_BADARG, "gpso_debug_product_items: bad argument");
+    std::vector<int> flat;
+    std::vector<int> meta;
+    if (kind == 0) {
+        int rounds = 0;
+        make_lauum_items(nb, nsm, flat, rounds);
+        meta.push_back(rounds);
+        if (levels_out) *levels_out = 1;
+    } else if (kind == 1) {
+        std::vector<InvLevelInfo> levels;
+        make_inverse_items(nb, nsm, flat, levels);
+        for (const InvLevelInfo& lv : levels) {
+            meta.push_back(lv.s);
+            meta.push_back((int)lv.xt_off);
+            meta.push_back(lv.xt_rounds);
+            meta.push_back((int)lv.y_off);
+            meta.push_back(lv.y_rounds);
+        }
+        if (levels_out) *levels_out = (int)levels.size();
+    } else {
+        return fail(GPSO_E_BADARG, "gpso_debug_product_items: kind must be 0 or 1");
+    }
+    if (out)
+        for (int64_t i = 0; i < (int64_t)flat.size() && i < capacity; i++) out[i] = flat[i];
+    if (info)
+        for (int i = 0; i < (int)meta.size() && i < info_capacity; i++) info[i] = meta[i];
+    return (int64_t)flat.size();
 }
 
 extern "C" int gpso_set_kinv_mode(gpso_handle* h, int mode) {

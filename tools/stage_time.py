@@ -1,3 +1,5 @@
+"""Per-window stage times (cross-covariance, variance product) of the scoring pipeline at config C3 with the stages run back to
+back (gpso_set_profile 1); used for same-box A/B runs of kernel variants.  usage: python tools/stage_time.py [label]"""
 import sys, os
 sys.path.insert(0, os.getcwd())
 import numpy as np, torch, bench
