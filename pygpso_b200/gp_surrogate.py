@@ -178,11 +178,15 @@ class GPListOfPoints(list):
                 continue
             self._store(int(idx), object)
 
-    def replace_at(self, positions, new_points):
-        """Bulk replace-in-place of GP-based points whose positions are known (the re-prediction after a fit)."""
+    def replace_at(self, positions, new_points, coords_unchanged=False):
+        """Bulk replace-in-place of GP-based points whose positions are known (the re-prediction after a fit).  With
+        ``coords_unchanged`` the caller guarantees that every new point carries the coordinates already stored there."""
         for position, point in zip(positions, new_points):
             assert self[position].label != PointLabels.evaluated
-            self._store(int(position), point)
+            if coords_unchanged:
+                list.__setitem__(self, position, point)
+            else:
+                self._store(int(position), point)
 
     def find_by_coords(self, coords):
         """First point (list order) within the tolerance of ``coords``, or None."""
@@ -386,6 +390,7 @@ class GPSurrogate:
                             label=PointLabels.gp_based)
                     for k in range(len(positions))
                 ),
+                coords_unchanged=True,
             )
 
     def fit(self, x=None, y=None):

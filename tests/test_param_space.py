@@ -126,3 +126,41 @@ def test_grow_split_dimension_varies_per_node():
     level3, level4 = rows[13:40], rows[40:121]
     changed = {int(np.flatnonzero(level4[3 * i] != level3[i])[0]) for i in range(27)}
     assert len(changed) > 1
+
+
+def test_incremental_depth_index_equals_a_fresh_preorder_walk():
+    """Splitting leaves in random order: the per-depth lists maintained by insertion must equal the lists a fresh pre-order
+    traversal gives (this order decides ties in get_best_score_leaf), also after detaching a subtree."""
+    from pygpso_b200.param_space import PreOrderIter
+
+    rng = np.random.default_rng(3)
+    space = ParameterSpace(parameter_names=["a", "b", "c"], parameter_bounds=[[0, 1], [-1, 1], [2, 5]])
+
+    def fresh():
+        by_depth = {}
+        for node in PreOrderIter(space):
+            by_depth.setdefault(node.depth, []).append(node)
+        return by_depth
+
+    assert space.max_depth == 0
+    for step in range(120):
+        leaves = [n for n in PreOrderIter(space) if n.is_leaf]
+        leaf = leaves[rng.integers(len(leaves))]
+        for child in leaf.ternary_split():
+            child.score = float(rng.integers(4))  # many ties
+        got, want = space._depth_index(), fresh()
+        assert set(got) == set(want)
+        for depth in want:
+            assert [id(n) for n in got[depth]] == [id(n) for n in want[depth]]
+        for depth in want:
+            cands = [n for n in want[depth] if not n.sampled]
+            best = space.get_best_score_leaf(depth)
+            if cands:
+                top = max(n.score for n in cands)
+                assert best is next(n for n in cands if n.score == top)
+        if step == 60:  # a structural change that is not an append: the index must rebuild itself
+            victim = next(n for n in PreOrderIter(space) if n.depth == 2 and not n.is_leaf)
+            victim.parent = None
+            got, want = space._depth_index(), fresh()
+            for depth in want:
+                assert [id(n) for n in got[depth]] == [id(n) for n in want[depth]]
