@@ -743,7 +743,9 @@ static int factor_pipeline(gpso_handle* h, cudaStream_t st, bool need_kinv) {
     P.nb = nb;
     P.p = 0;
     P.s = 0;
-    const bool inv8 = nb > 1 && Np <= OZ_MAX_NP && (h->inverse_mode == 2 || (h->inverse_mode == 0 && Np >= OZ_INV_MIN_NP));
+    static const int inv_min_np = getenv("GPSO_INV_MIN_NP") ? atoi(getenv("GPSO_INV_MIN_NP")) : OZ_INV_MIN_NP;     // tuning experiments only
+    static const int kinv_min_np = getenv("GPSO_KINV_MIN_NP") ? atoi(getenv("GPSO_KINV_MIN_NP")) : OZ_KINV_MIN_NP;
+    const bool inv8 = nb > 1 && Np <= OZ_MAX_NP && (h->inverse_mode == 2 || (h->inverse_mode == 0 && Np >= inv_min_np));
     if (h->chol_mode == 1 && nb > 1) {
         // one persistent launch: blocked Cholesky + L^-1 (diagonal blocks, their transposes and -- unless the int8 engine
         // takes it over below -- the recursive doubling)
@@ -793,7 +795,7 @@ static int factor_pipeline(gpso_handle* h, cudaStream_t st, bool need_kinv) {
     if (need_kinv) {
         GP_TRY(h->Kinv.ensure((size_t)Np * Np * sizeof(double), true));
         P.Kinv = h->Kinv.as<double>();
-        const bool int8 = Np <= OZ_MAX_NP && (h->kinv_mode == 2 || (h->kinv_mode == 0 && Np >= OZ_KINV_MIN_NP));
+        const bool int8 = Np <= OZ_MAX_NP && (h->kinv_mode == 2 || (h->kinv_mode == 0 && Np >= kinv_min_np));
         if (int8) {
             GP_TRY(kinv_int8(h, st));
         } else {
