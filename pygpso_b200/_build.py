@@ -50,7 +50,8 @@ def build_library(force=False, verbose=False):
     if proc.returncode != 0:
         raise RuntimeError("nvcc failed building libgpso_b200.so")
     with open(os.path.join(HERE, "csrc", "ptxas_report.txt"), "w") as handle:
-        handle.write(proc.stdout + proc.stderr)
+        # registers / spills / shared memory per kernel; the compile times would change the file on every build
+        handle.write("".join(line for line in (proc.stdout + proc.stderr).splitlines(True) if "Compile time" not in line))
     return LIB_PATH
 
 
