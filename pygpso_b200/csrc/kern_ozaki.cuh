@@ -276,8 +276,8 @@ __global__ void __launch_bounds__(256) linv_slices_kernel(const double* __restri
 // ---- operands of the recursive-doubling inverse (fit path, OZ_GEMM) -----------------------------------------------------
 // At level s the diagonal blocks of s tiles of L^-1 are complete.  The products of the level read, per 128-row tile I with
 // block [b0, b1) = [floor(I/s) s, min(b0+s, nb)) and pair start a = floor(I/2s) 2s:
-//   OZR_LINVT  L^-T rows, k in tiles [I, b1)          (upper part of the block: operand of X^T = L11^-T L21^T)
-//   OZR_LINV   L^-1 rows, k in tiles [b0, I]          (lower part of the block: operand of Y = L22^-1 X)
+//   OZR_LINVT  L^-T rows of the first half of a pair,  k in tiles [I, b1)   (upper part of the block: operand of X^T = L11^-T L21^T)
+//   OZR_LINV   L^-1 rows of the second half of a pair, k in tiles [b0, I]   (lower part of the block: operand of Y = L22^-1 X)
 //   OZR_XT     X^T rows of the first half of a pair,  k in tiles [a+s, min(a+2s, nb))
 //   OZR_L      rows of the Cholesky factor, k in tiles [0, I)   (strictly below the diagonal tile: the L21 blocks)
 // Each row is scaled by a power of two above its largest entry IN THAT RANGE, then cut into S balanced 8-bit digits.
@@ -286,9 +286,9 @@ constexpr int OZR_LINVT = 0, OZR_LINV = 1, OZR_XT = 2, OZR_L = 3;
 __device__ __forceinline__ void ozr_tile_range(int kind, int I, int s, int nb, int& t0, int& t1) {
     const int b0 = (I / s) * s, b1 = min(b0 + s, nb), a = (I / (2 * s)) * (2 * s);
     if (kind == OZR_LINVT) {
-        t0 = I, t1 = b1;
+        t0 = I, t1 = (I < a + s) ? b1 : I;          // only first-half rows are read (operand of X^T)
     } else if (kind == OZR_LINV) {
-        t0 = b0, t1 = I + 1;
+        t0 = b0, t1 = (I >= a + s) ? I + 1 : b0;    // only second-half rows are read (operand of Y)
     } else if (kind == OZR_XT) {
         t0 = a + s, t1 = (I < a + s) ? min(a + 2 * s, nb) : a + s;  // second-half rows: empty
     } else {
