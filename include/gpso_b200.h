@@ -81,6 +81,13 @@ int gpso_ucb_argmax_host(gpso_handle* h, const double* Xc_host, int64_t M, doubl
 /* Device-resident candidates.  Synchronous on `stream` at return (the 4 result doubles are copied back). */
 int gpso_ucb_argmax_dev(gpso_handle* h, const double* Xc_dev, int64_t M, double varsigma, double* result_host,
                         void* stream);
+/* Top-k variant (the multi-GPU path gathers k records per rank): the k candidates with the highest UCB in the order
+ * np.argsort(-ucb, kind="stable") would visit them (first NaN, larger UCB, lowest index on ties), 1 <= k <= 64.
+ * result_host[4*i + 0..3] = (index, mean, var, ucb) of the i-th best; *found = min(k, M).  Record 0 equals
+ * gpso_ucb_argmax_* bit for bit. */
+int gpso_ucb_topk_host(gpso_handle* h, const double* Xc_host, int64_t M, double varsigma, int k, double* result_host, int* found);
+int gpso_ucb_topk_dev(gpso_handle* h, const double* Xc_dev, int64_t M, double varsigma, int k, double* result_host, int* found,
+                      void* stream);
 
 /* ---- leaf-coordinate batching: LeafNode.grow(depth), param_space.py:175-200 (+ ternary_split :257-307) -------- */
 /* bounds_host[d,2] = (lo,hi) per dimension of the leaf; out[(3^depth-1)/2, d] = centres in the reference's order

@@ -69,6 +69,8 @@ def load_library():
         "gpso_predict_y_dev": (i32, [H, ctypes.c_void_p, i64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
         "gpso_ucb_argmax_host": (i32, [H, _c_double_p, i64, dbl, _c_double_p]),
         "gpso_ucb_argmax_dev": (i32, [H, ctypes.c_void_p, i64, dbl, _c_double_p, ctypes.c_void_p]),
+        "gpso_ucb_topk_host": (i32, [H, _c_double_p, i64, dbl, i32, _c_double_p, ctypes.POINTER(ctypes.c_int)]),
+        "gpso_ucb_topk_dev": (i32, [H, ctypes.c_void_p, i64, dbl, i32, _c_double_p, ctypes.POINTER(ctypes.c_int), ctypes.c_void_p]),
         "gpso_grow_count": (i64, [i32]),
         "gpso_grow_leaves_host": (i32, [i32, _c_double_p, i32, i32, _c_double_p]),
         "gpso_grow_leaves_dev": (i32, [i32, _c_double_p, i32, i32, ctypes.c_void_p, ctypes.c_void_p]),
@@ -110,6 +112,7 @@ def load_library():
 EXPORTED_SYMBOLS = (
     "gpso_version gpso_last_error gpso_device_count gpso_create gpso_destroy gpso_set_data gpso_neg_lml_grad "
     "gpso_factorize gpso_factor_lml gpso_predict_y_host gpso_predict_y_dev gpso_ucb_argmax_host gpso_ucb_argmax_dev "
+    "gpso_ucb_topk_host gpso_ucb_topk_dev "
     "gpso_grow_count gpso_grow_leaves_host gpso_grow_leaves_dev gpso_grow_ucb_argmax gpso_state_bytes "
     "gpso_export_state_dev gpso_import_state_dev gpso_launch_count gpso_debug_fetch gpso_last_timing gpso_set_window "
     "gpso_set_profile gpso_last_windows gpso_set_predict_mode gpso_predict_info gpso_set_overlap "
@@ -192,6 +195,22 @@ class CudaSession:
         _check(self._lib, self._lib.gpso_ucb_argmax_host(self._h, _dptr(xnew), xnew.shape[0], float(varsigma), _dptr(out)),
                "gpso_ucb_argmax_host")
         return int(out[0]), float(out[1]), float(out[2]), float(out[3])
+
+    def ucb_topk(self, xnew, varsigma, k):
+        """The k best candidates in arg-max order: array [found, 4] of (index, mean, var, ucb); row 0 == ``ucb_argmax``."""
+        xnew = np.ascontiguousarray(xnew, dtype=np.float64)
+        out = np.zeros((int(k), 4))
+        found = ctypes.c_int(0)
+        _check(self._lib, self._lib.gpso_ucb_topk_host(self._h, _dptr(xnew), xnew.shape[0], float(varsigma), int(k), _dptr(out),
+                                                       ctypes.byref(found)), "gpso_ucb_topk_host")
+        return out[: found.value]
+
+    def ucb_topk_dev(self, xc_ptr, m, varsigma, k, stream=0):
+        out = np.zeros((int(k), 4))
+        found = ctypes.c_int(0)
+        _check(self._lib, self._lib.gpso_ucb_topk_dev(self._h, xc_ptr, m, float(varsigma), int(k), _dptr(out), ctypes.byref(found),
+                                                      stream), "gpso_ucb_topk_dev")
+        return out[: found.value]
 
     def grow_ucb_argmax(self, bounds, depth, varsigma):
         bounds = np.ascontiguousarray(bounds, dtype=np.float64)

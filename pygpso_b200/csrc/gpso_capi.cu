@@ -120,7 +120,8 @@ struct gpso_handle {
     int chol_tasks_nb = 0, chol_ntasks = 0, chol_ncounters = 0, chol_W = 4;
     int chol_mode = 1;      // 1 = persistent dataflow kernel, 0 = one launch per step (reference schedule)
     // predict workspaces
-    DevBuf KsT, part, blockbest, running, cand[2], leaves, omean, ovar;
+    DevBuf KsT, part, blockbest, running, cand[2], leaves, omean, ovar, topk;
+    int topk_k = 0;         // records per window of the top-k pass in flight
     // int8 tensor-core (tcgen05) variance product: digit tiles of L^-1 and of the cross-covariance window
     DevBuf ozA, ozBb[2], wmeanb[2], rowscale, rowmax;
     // int8 tensor-core K_y^-1 = L^-T L^-1 (fit path): digit tiles of L^-T, its row scales, the tile -> CTA table
@@ -1221,6 +1222,11 @@ static int run_windows(gpso_handle* h, cudaStream_t st, const double* Xc_dev, co
             GP_TRY(h->ovar.ensure((size_t)W * sizeof(double)));
         }
     }
+    if (mode == 2) {  // top-k: finalised mean/var of the window stay on the device, k records per window
+        GP_TRY(h->omean.ensure((size_t)W * sizeof(double)));
+        GP_TRY(h->ovar.ensure((size_t)W * sizeof(double)));
+        GP_TRY(h->topk.ensure((size_t)nwin * h->topk_k * sizeof(BestRec)));
+    }
     cudaStream_t user_st = st;
     cudaStream_t xs = overlap ? h->aux_stream : st;  // stream of the cross-covariance kernels
     cudaStream_t cs = h->copy_stream;
@@ -1304,12 +1310,17 @@ static int run_windows(gpso_handle* h, cudaStream_t st, const double* Xc_dev, co
         GP_TRY(trace_mark(h, st, 4, w));
         GP_TRY(prof_mark(h, st));
         // ---- 4. finalise: var, ucb, window arg-max merged into the running record
-        double* om = mode == 0 ? (host ? h->omean.as<double>() : mean_out + off) : nullptr;
-        double* ov = mode == 0 ? (host ? h->ovar.as<double>() : var_out + off) : nullptr;
+        double* om = mode == 0 ? (host ? h->omean.as<double>() : mean_out + off) : mode == 2 ? h->omean.as<double>() : nullptr;
+        double* ov = mode == 0 ? (host ? h->ovar.as<double>() : var_out + off) : mode == 2 ? h->ovar.as<double>() : nullptr;
         int fb = (int)((Mw + 255) / 256);
         predict_finalize_kernel<<<fb, 256, 0, st>>>(h->part.as<double>(), h->wmeanb[b].as<double>(), h->nb, (int)Mw_pad, Mw, off,
-                                                    h->variance, h->noise, varsigma, mode, om, ov, h->blockbest.as<BestRec>());
+                                                    h->variance, h->noise, varsigma, mode == 2 ? 0 : mode, om, ov,
+                                                    h->blockbest.as<BestRec>());
         GP_TRY(check_launch(h, "predict_finalize"));
+        if (mode == 2) {
+            topk_window_kernel<<<1, 1024, 0, st>>>(om, ov, Mw, off, varsigma, h->topk_k, h->topk.as<BestRec>() + w * h->topk_k);
+            GP_TRY(check_launch(h, "topk_window"));
+        }
         if (mode == 1) {
             best_merge_kernel<<<1, 256, 0, st>>>(h->blockbest.as<BestRec>(), fb, h->running.as<BestRec>(), w == 0 ? 1 : 0);
             GP_TRY(check_launch(h, "best_merge"));
@@ -1402,6 +1413,57 @@ extern "C" int gpso_ucb_argmax_host(gpso_handle* h, const double* Xc_host, int64
     cudaEventElapsedTime(&ms, h->ev_t0, h->ev_t1);
     h->last_ms[0] = ms;
     return 0;
+}
+
+// Top-k variant of the fused scoring call: the k candidates with the highest UCB in arg-max order (first NaN, larger UCB,
+// lowest index on ties).  Per window a k-pass block arg-max on the device, the per-window lists are merged on the host.
+static int topk_common(gpso_handle* h, cudaStream_t st, const double* Xc_dev, const double* Xc_host, int64_t M, double varsigma, int k,
+                       double* result_host, int* found) {
+    if (k < 1 || k > TOPK_MAX) return fail(GPSO_E_BADARG, "gpso_ucb_topk: k must be in 1..64");
+    h->topk_k = k;
+    CU_TRY(cudaEventRecord(h->ev_t0, st));
+    GP_TRY(run_windows(h, st, Xc_dev, Xc_host, M, 2, varsigma, nullptr, nullptr));
+    CU_TRY(cudaEventRecord(h->ev_t1, st));
+    const size_t nrec = (size_t)h->last_windows * k;
+    std::vector<BestRec> rec(nrec);
+    CU_TRY(cudaMemcpyAsync(rec.data(), h->topk.p, nrec * sizeof(BestRec), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    prof_collect(h);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, h->ev_t0, h->ev_t1);
+    h->last_ms[0] = ms;
+    std::vector<BestRec> live;
+    for (const BestRec& r : rec)
+        if (r.idx != 0x7fffffffffffffffLL) live.push_back(r);
+    auto better = [](const BestRec& a, const BestRec& b) {
+        const bool an = a.ucb != a.ucb, bn = b.ucb != b.ucb;
+        if (an || bn) return an && bn ? a.idx < b.idx : an;
+        if (a.ucb != b.ucb) return a.ucb > b.ucb;
+        return a.idx < b.idx;
+    };
+    std::sort(live.begin(), live.end(), better);
+    const int n = (int)std::min<size_t>(live.size(), (size_t)k);
+    for (int i = 0; i < n; i++) {
+        result_host[4 * i + 0] = (double)live[i].idx;
+        result_host[4 * i + 1] = live[i].mean;
+        result_host[4 * i + 2] = live[i].var;
+        result_host[4 * i + 3] = live[i].ucb;
+    }
+    if (found) *found = n;
+    return 0;
+}
+
+extern "C" int gpso_ucb_topk_dev(gpso_handle* h, const double* Xc_dev, int64_t M, double varsigma, int k, double* result_host, int* found,
+                                 void* stream) {
+    GP_TRY(predict_common_checks(h, Xc_dev, M, "gpso_ucb_topk_dev"));
+    if (!result_host) return fail(GPSO_E_BADARG, "gpso_ucb_topk_dev: null output");
+    return topk_common(h, (cudaStream_t)stream, Xc_dev, nullptr, M, varsigma, k, result_host, found);
+}
+
+extern "C" int gpso_ucb_topk_host(gpso_handle* h, const double* Xc_host, int64_t M, double varsigma, int k, double* result_host, int* found) {
+    GP_TRY(predict_common_checks(h, Xc_host, M, "gpso_ucb_topk_host"));
+    if (!result_host) return fail(GPSO_E_BADARG, "gpso_ucb_topk_host: null output");
+    return topk_common(h, h->stream, nullptr, Xc_host, M, varsigma, k, result_host, found);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

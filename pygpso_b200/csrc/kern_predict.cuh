@@ -185,4 +185,53 @@ __global__ void __launch_bounds__(256) best_merge_kernel(const BestRec* __restri
     }
 }
 
+// ---- top-k --------------------------------------------------------------------------------------------------------------
+// The k best candidates of one window in arg-max order (first NaN, then the larger UCB, the lowest index on ties): k passes of
+// a block-wide arg-max that skips the winners of the earlier passes.  mean/var are the window's finalised values; the UCB is
+// formed exactly as in predict_finalize_kernel, so record 0 equals the fused arg-max bit for bit.  Slots beyond the number
+// of candidates keep idx = LLONG_MAX.
+constexpr int TOPK_MAX = 64;
+
+__global__ void __launch_bounds__(1024) topk_window_kernel(const double* __restrict__ mean, const double* __restrict__ var, long long Mw,
+                                                           long long idx0, double varsigma, int k, BestRec* __restrict__ out) {
+    __shared__ long long taken[TOPK_MAX];
+    __shared__ BestRec sb[32];
+    const int tid = threadIdx.x, w = tid >> 5, l = tid & 31;
+    for (int pass = 0; pass < k; pass++) {
+        double bu = -INFINITY, bm = 0.0, bv = 0.0;
+        long long bi = 0x7fffffffffffffffLL;
+        for (long long c = tid; c < Mw; c += 1024) {
+            const long long gi = idx0 + c;
+            bool skip = false;
+            for (int t = 0; t < pass; t++) skip |= (taken[t] == gi);
+            if (skip) continue;
+            const double m = mean[c], v = var[c];
+            const double u = __dadd_rn(m, __dmul_rn(varsigma, v));
+            if (best_better(u, gi, bu, bi)) {
+                bu = u; bm = m; bv = v; bi = gi;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            double ou = __shfl_xor_sync(0xffffffffu, bu, o);
+            double om = __shfl_xor_sync(0xffffffffu, bm, o);
+            double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (best_better(ou, oi, bu, bi)) {
+                bu = ou; bm = om; bv = ov; bi = oi;
+            }
+        }
+        if (l == 0) sb[w] = BestRec{bu, bm, bv, bi};
+        __syncthreads();
+        if (tid == 0) {
+            BestRec b = sb[0];
+            for (int i = 1; i < 32; i++)
+                if (best_better(sb[i].ucb, sb[i].idx, b.ucb, b.idx)) b = sb[i];
+            out[pass] = b;
+            taken[pass] = b.idx;
+        }
+        __syncthreads();
+    }
+}
+
 }  // namespace gpso

@@ -52,6 +52,20 @@ def pick_best(records):
     return best[1], best[2], best[3], best[0]
 
 
+def merge_topk(records, k):
+    """
+    The k best of per-shard top-k lists (rows ``[ucb, global_idx, mean, var]``; ``global_idx < 0`` = padding) in arg-max
+    order: NaNs first (by index), then descending UCB, the lowest global index on ties.  Returns rows
+    ``[global_idx, mean, var, ucb]`` like ``session.ucb_topk``.
+    """
+    rows = np.asarray(records, dtype=np.float64).reshape(-1, RECORD_LEN)
+    rows = rows[rows[:, 1] >= 0]
+    nan = np.isnan(rows[:, 0])
+    order = np.lexsort((rows[:, 1], -np.where(nan, np.inf, rows[:, 0]), ~nan))
+    best = rows[order[:k]]
+    return best[:, [1, 2, 3, 0]]
+
+
 def _dist():
     import torch.distributed as dist
 
@@ -69,16 +83,17 @@ def _comm_device(group=None):
 
 
 def gather_records(record, group=None):
-    """All-gather one RECORD_LEN-double record per rank; returns an array [world, RECORD_LEN] on every rank."""
+    """All-gather the same number of RECORD_LEN-double records from every rank (one, or k for the top-k path); returns
+    an array [world * records_per_rank, RECORD_LEN] on every rank, rank-major."""
     import torch
 
     dist = _dist()
     world = dist.get_world_size(group)
     dev = _comm_device(group)
-    mine = torch.tensor(np.asarray(record, dtype=np.float64), dtype=torch.float64, device=dev)
-    parts = [torch.empty(RECORD_LEN, dtype=torch.float64, device=dev) for _ in range(world)]
+    mine = torch.tensor(np.asarray(record, dtype=np.float64).reshape(-1), dtype=torch.float64, device=dev)
+    parts = [torch.empty_like(mine) for _ in range(world)]
     dist.all_gather(parts, mine, group=group)
-    return torch.stack(parts).cpu().numpy()
+    return torch.stack(parts).cpu().numpy().reshape(-1, RECORD_LEN)
 
 
 class ShardedScorer:
@@ -122,6 +137,14 @@ class ShardedScorer:
         """Score this rank's shard (rows ``global_offset ...`` of the full candidate list) and agree on the winner."""
         records = gather_records(self.local_record(x_local, global_offset, varsigma), self.group)
         return pick_best(records)
+
+    def ucb_topk(self, x_local, global_offset, varsigma, k):
+        """Top-k over all shards: k records per rank are gathered (32 k bytes each) and merged identically on every rank."""
+        mine = np.full((k, RECORD_LEN), [-np.inf, -1.0, 0.0, 0.0])
+        if len(x_local):
+            local = np.asarray(self.session.ucb_topk(x_local, varsigma, k), dtype=np.float64).reshape(-1, 4)
+            mine[: len(local)] = np.column_stack([local[:, 3], local[:, 0] + global_offset, local[:, 1], local[:, 2]])
+        return merge_topk(gather_records(mine, self.group), k)
 
     def ucb_argmax_full(self, x_all, varsigma):
         """Convenience: every rank holds the full candidate matrix and scores only its own contiguous shard."""

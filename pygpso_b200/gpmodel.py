@@ -307,6 +307,11 @@ class GPR(GPModel):
         self._ensure_factor()
         return self._session.ucb_argmax(Xnew, float(varsigma))
 
+    def ucb_topk(self, Xnew, varsigma, k):
+        """The k candidates with the highest ``mean + varsigma * var`` in arg-max order: rows (index, mean, var, ucb)."""
+        self._ensure_factor()
+        return self._session.ucb_topk(np.asarray(Xnew, dtype=np.float64), varsigma, k)
+
     def grow_ucb_argmax(self, bounds, depth, varsigma):
         """Generate the ``grow(depth)`` leaf-centre batch of the box ``bounds[d,2]`` on the device and score it."""
         self._ensure_factor()

@@ -48,6 +48,14 @@ class OracleSession:
         mean, var = go.predict_y(self.kernel, self.X, self.y, self.h, xnew)
         return go.ucb_argmax(mean, var, varsigma)
 
+    def ucb_topk(self, xnew, varsigma, k):
+        mean, var = go.predict_y(self.kernel, self.X, self.y, self.h, xnew)
+        mean, var = mean[:, 0], var[:, 0]
+        ucb = mean + varsigma * var
+        nan = np.isnan(ucb)
+        order = np.lexsort((np.arange(len(ucb)), -np.where(nan, np.inf, ucb), ~nan))[:k]
+        return np.column_stack([order.astype(float), mean[order], var[order], ucb[order]])
+
     def grow_ucb_argmax(self, bounds, depth, varsigma):
         return self.ucb_argmax(grow_oracle.grow_by_level(bounds, depth), varsigma)
 

@@ -54,7 +54,7 @@ def _worker(rank, world, port, out_dir):
     import torch.distributed as dist
 
     from oracle import gpr_oracle as go
-    from pygpso_b200.distributed import ShardedScorer, sharded_multistart_fit
+    from pygpso_b200.distributed import ShardedScorer, shard_bounds, sharded_multistart_fit
     from tests.oracle_backend import OracleSession
 
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -79,6 +79,13 @@ def _worker(rank, world, port, out_dir):
         # ragged: fewer candidates than ranks
         got_one = scorer.ucb_argmax_full(Xc[:1], go.VARSIGMA_DEFAULT)
 
+        # top-k gathered back: k records per rank, merged identically everywhere; ragged shard (fewer rows than k)
+        start, stop = shard_bounds(len(Xd), world, rank)
+        top = scorer.ucb_topk(Xd[start:stop], start, go.VARSIGMA_DEFAULT, 7)
+        s3, e3 = shard_bounds(3, world, rank)
+        top_small = scorer.ucb_topk(Xc[s3:e3], s3, go.VARSIGMA_DEFAULT, 7)
+        np.save(os.path.join(out_dir, f"top{rank}.npy"), np.vstack([top, np.full((1, 4), -7.0), top_small]))
+
         model = go.OracleGPR(X, y, "Matern52", 0.25, 1.0, 1e-3, 0.0)
         u_best, f_best, rid, table = sharded_multistart_fit(model.training_loss, model.h.pack(), 5, maxiter=30)
         np.save(os.path.join(out_dir, f"r{rank}.npy"),
@@ -97,6 +104,30 @@ def test_world_size_2_gloo(tmp_path):
     assert got[0] == want[0] and got[1] == want[1] and got[2] == want[2] and got[3] == want[3]
     assert got_dup[0] == want[0]  # duplicate appended at the end loses the tie to the earlier row
     assert got_one[0] == 0
+    # top-k: identical on both ranks, equal to the stable descending order of the full UCB vector (duplicates: lower index first)
+    t0, t1 = np.load(tmp_path / "top0.npy"), np.load(tmp_path / "top1.npy")
+    assert np.array_equal(t0, t1)
+    top, top_small = t0[:7], t0[8:]
+    from oracle import gpr_oracle as go
+    from tests.oracle_backend import OracleSession
+
+    rng = np.random.default_rng(0)
+    X = rng.random((30, 2))
+    y = np.sin(3 * X.sum(1))[:, None]
+    sess = OracleSession("Matern52", 1, True)
+    sess.set_data(X, y)
+    sess.factorize(np.array([0.3, 1.0, 1e-3, 0.0]))
+    Xc = rng.random((1001, 2))
+    Xc[700] = Xc[100]
+    Xd = np.vstack([Xc, Xc[int(want[0])][None, :]])
+    ref = sess.ucb_topk(Xd, go.VARSIGMA_DEFAULT, 7)
+    # (the oracle's BLAS results depend on the shard shape in the last bits, so values are compared to 1e-12 and the
+    # order of the exact-duplicate pair -- a genuine tie only on the GPU, where results are position independent -- is free)
+    assert sorted(top[:, 0]) == sorted(ref[:, 0]) and {int(top[0, 0]), int(top[1, 0])} == {int(want[0]), len(Xd) - 1}
+    np.testing.assert_allclose(np.sort(top[:, 3])[::-1], ref[:, 3], rtol=1e-12)
+    assert np.all(np.diff(top[:, 3]) <= 0)
+    small_ref = sess.ucb_topk(Xc[:3], go.VARSIGMA_DEFAULT, 7)
+    assert len(top_small) == 3 and list(top_small[:, 0]) == list(small_ref[:, 0])
     f_best, rid, fs = r0[16], int(r0[17]), r0[22:27]
     assert f_best == fs.min() and rid == int(np.argmin(fs)) and np.all(np.isfinite(fs))
     # restart 0 (the warm start) must reproduce the single-process fit

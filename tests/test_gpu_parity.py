@@ -303,6 +303,32 @@ def test_predict_y_and_argmax(cuda, engine, kernel, N, d, M):
 
 
 @pytest.mark.parametrize("engine", ["dmma", "int8"])
+def test_ucb_topk_equals_stable_sort_of_predict_y(cuda, engine):
+    """gpso_ucb_topk: the k best in arg-max order (descending UCB, lowest index on ties -- duplicated rows included), over
+    several windows, with k larger than a window's share and than M."""
+    N, d, M = 300, 3, 5000
+    X, y = synthetic(N, d, seed=13)
+    h = go.Hyper(0.4, 1.1, 1e-3, 0.1)
+    s = open_session(cuda, "Matern52", X, y, engine=engine)
+    s.factorize(theta_of(h))
+    Xc = np.random.default_rng(8).random((M, d))
+    Xc[4000:4100] = Xc[100:200]          # exact duplicates in a later window
+    s.set_window(1024)                    # several windows even at this size
+    mean, var = s.predict_y(Xc)
+    ucb = mean + VARSIGMA * var
+    for k in (1, 5, 64):
+        top = s.ucb_topk(Xc, VARSIGMA, k)
+        order = np.lexsort((np.arange(M), -ucb))[:k]
+        assert top.shape == (k, 4)
+        assert np.array_equal(top[:, 0].astype(int), order)
+        assert np.array_equal(top[:, 1], mean[order]) and np.array_equal(top[:, 2], var[order]) and np.array_equal(top[:, 3], ucb[order])
+    assert tuple(s.ucb_topk(Xc, VARSIGMA, 1)[0]) == tuple(float(v) for v in s.ucb_argmax(Xc, VARSIGMA))
+    few = s.ucb_topk(Xc[:3], VARSIGMA, 8)
+    assert few.shape == (3, 4) and sorted(few[:, 0].astype(int)) == [0, 1, 2]
+    s.close()
+
+
+@pytest.mark.parametrize("engine", ["dmma", "int8"])
 @pytest.mark.parametrize("d", [1, 20, 33, 64])
 def test_predict_input_dimensions(cuda, engine, d):
     """Smallest and largest supported input dimension (the cross-covariance kernels stage d x 128 training coordinates per
