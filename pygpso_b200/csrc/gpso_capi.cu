@@ -396,7 +396,9 @@ struct FactorTask {
 }  // namespace
 
 static int make_factor_tasks(int nb, int nsm, std::vector<int>& flat, int& ntasks, int& ncounters_out, bool with_inverse = true) {
-    const int W = nb >= 48 ? 4 : 2;
+    // panels per block of the two-level blocking; GPSO_CHOL_W overrides it for scheduling experiments (tools/factor_sim.py)
+    static const int w_env = getenv("GPSO_CHOL_W") ? atoi(getenv("GPSO_CHOL_W")) : 0;
+    const int W = w_env > 0 ? w_env : (nb >= 48 ? 4 : 2);
     if (nb < 1 || nb > 255) return fail(GPSO_E_BADARG, "matrix too large for the tile scheduler (more than 255 panels)");
     const int LV = 8;  // levels of the inverse recursion: s = 1 .. 128
     auto T = [nb](int i, int j) { return i * nb + j; };          // tile counters
