@@ -68,3 +68,22 @@ def test_queue_is_topological_and_complete(nb):
 def test_single_panel_matrix_has_no_scheduler_tasks_beyond_the_block():
     tasks, _ = task_list(1)
     assert [OPS[int(t[0])] for t in tasks] == ["DIAG", "TRANSPOSE"]
+
+
+@pytest.mark.parametrize("nb,chain_slack,work_slack", [(16, 1.03, None), (32, 1.03, None), (64, None, 1.30)])
+def test_schedule_quality_in_the_discrete_event_replay(nb, chain_slack, work_slack):
+    """tools/factor_sim.py replays the queue with the measured task durations on 148 workers.  Up to N = 4096 the
+    factorisation is bound by the DIAG -> PANEL chain and the queue must not add to it; at N = 8192 the makespan has to stay
+    within 30 % of the work bound (its chain-bound tail costs ~20 %).  Guards the look-ahead ordering of the host builder."""
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import factor_sim
+
+    r = factor_sim.simulate(nb)
+    assert r["makespan_us"] >= max(r["chain_us"], r["work_bound_us"]) * 0.999
+    if chain_slack:
+        assert r["makespan_us"] <= chain_slack * r["chain_us"], r
+    if work_slack:
+        assert r["makespan_us"] <= work_slack * r["work_bound_us"], r
