@@ -23,6 +23,7 @@ import threading
 import time
 
 import numpy as np
+from scipy.special import erfcinv
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -35,6 +36,7 @@ WORKLOADS = {
 }
 FP64_PEAK_TFLOPS = 37.03  # measured DMMA.8x8x4 issue peak of this pool's B200 (profiles/r01_fp64_probe.txt)
 INT8_PEAK_TOPS = 4528.7   # measured tcgen05.mma kind::i8 issue peak, M=128 N=256, 148 SMs (profiles/r01_i8_tcgen05_probe.txt)
+VARSIGMA = float(erfcinv(0.01))  # UCB multiplier of the reference (gp_surrogate.py:397)
 CPU_SAMPLE = 8192         # candidates per CPU-baseline step (bounded sample of the same workload)
 LOGICAL_SHARDS = 64       # the candidate matrix is generated in 64 seeded pieces, so it is the same for every GPU count
 
@@ -55,6 +57,13 @@ def fill_candidates(out, start, stop, M, d):
         block = np.random.default_rng([SEED, s]).random((hi - lo, d))
         a, b = max(lo, start), min(hi, stop)
         out[a - start:b - start] = block[a - lo:b - lo]
+
+
+def pack_unconstrained(ls, variance, noise, c):
+    """Unconstrained L-BFGS-B variables of (lengthscale, kernel variance, noise variance, constant mean): softplus^-1, with
+    GPflow's 1e-6 floor under the noise variance."""
+    inv = lambda v: float(np.log(np.expm1(v)))
+    return np.array([inv(ls), inv(variance), inv(noise - 1.0e-6), c])
 
 
 def fixed_theta(d):
@@ -122,14 +131,13 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm)}
 
 
-def bench_lml_grad(cuda, go, cpu=True, shapes=((4096, 10), (8192, 20)), evals=5):
+def bench_lml_grad(cuda, cpu=True, shapes=((4096, 10), (8192, 20)), evals=5):
     """LML + gradient evaluations per second through the C ABI (gpso_neg_lml_grad: Gram -> Cholesky -> L^-1 -> K_y^-1 ->
     fused gradient reduction), host in / host out, at the shapes of configs C3 and C4.  Algorithmic work: N^3 flops."""
     out = []
     for N, d in shapes:
         X, y = synthetic_training(N, d)
-        h = go.Hyper(0.25 * np.sqrt(d), 1.0, 1.0e-3, 0.0)
-        u = h.pack()
+        u = pack_unconstrained(0.25 * np.sqrt(d), 1.0, 1.0e-3, 0.0)
         sess = cuda.open_session("Matern52", 1, True)
         sess.set_data(X, y)
         f, g = sess.neg_lml_and_grad(u)  # warm-up (allocations)
@@ -158,15 +166,19 @@ def bench_lml_grad(cuda, go, cpu=True, shapes=((4096, 10), (8192, 20)), evals=5)
         rec = {"N": N, "d": d, "evals_per_s": evals / wall, "device_ms_per_eval": dev_ms / evals,
                "device_ms_per_eval_stepwise_launches": step_ms / evals,
                "device_ms_per_eval_kinv_on_fp64_dmma": kinv_dmma_ms / evals,
-               "schedule": "one persistent kernel (one CTA per SM, host-built task list with per-tile dependency counters): "
-                           "blocked Cholesky as DIAG/PANEL/UPDATE tile tasks on FP64 DMMA, two-level blocking + look-ahead, and "
-                           "L^-1 by recursive doubling as tasks of the same launch; then K_y^-1 = L^-T L^-1 as an exact-integer "
-                           "product of 7-digit (54-bit) fixed-point operands on the int8 tensor cores (tcgen05.mma kind::i8)",
+               "schedule": "blocked Cholesky as ONE persistent kernel on FP64 DMMA (one CTA per SM, host-built task list with "
+                           "per-tile dependency counters, two-level blocking + look-ahead); then L^-1 by recursive doubling (two "
+                           "products per level, 8-digit / 62-bit fixed-point operands) and K_y^-1 = L^-T L^-1 (7 digits / 54 bit) as "
+                           "exact-integer products on the int8 tensor cores (tcgen05.mma kind::i8)",
+               "fp64_tflops_note": "N^3 fp64-equivalent flops per evaluation / device time: N^3/3 (Cholesky) run on the FP64 pipe, "
+                                   "2N^3/3 (L^-1, K_y^-1) as int8 tensor-core products, so the ratio to the FP64 pipe peak can exceed 1",
                "library_bar_ms": {4096: {"cusolver_dpotrf": 1.675, "cusolver_dpotri": 14.005},
                                   8192: {"cusolver_dpotrf": 7.753, "cusolver_dpotri": 61.528}}.get(N),
                "fp64_tflops": (float(N) ** 3 / (dev_ms / evals * 1e-3)) / 1e12, "fp64_peak_tflops": FP64_PEAK_TFLOPS,
                "frac_of_fp64_peak": (float(N) ** 3 / (dev_ms / evals * 1e-3)) / 1e12 / FP64_PEAK_TFLOPS, "neg_lml": f}
         if cpu and N <= 4096:
+            from oracle import gpr_oracle as go  # CPU leg of the LML side measurement (checker + baseline)
+
             t0 = time.perf_counter()
             f_ref, g_ref = go.neg_lml_and_grad("Matern52", X, y, u + 1e-3 * evals, 1, True)
             rec["cpu_evals_per_s"] = 1.0 / (time.perf_counter() - t0)
@@ -180,8 +192,6 @@ def run_reference(args, rank):
     """--impl reference: the CPU path on the host cores (rank 0 only)."""
     if rank != 0:
         return
-    from oracle import gpr_oracle as go
-
     N, d, M, desc = WORKLOADS[args.workload]
     X, y = synthetic_training(N, d)
     theta = fixed_theta(d)
@@ -189,10 +199,10 @@ def run_reference(args, rank):
     Xc = np.empty((sample, d))
     fill_candidates(Xc, 0, sample, M, d)
     for _ in range(args.warmup):
-        cpu_reference_step(X, y, theta, Xc, go.VARSIGMA_DEFAULT)
+        cpu_reference_step(X, y, theta, Xc, VARSIGMA)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_reference_step(X, y, theta, Xc, go.VARSIGMA_DEFAULT)
+        cpu_reference_step(X, y, theta, Xc, VARSIGMA)
     dt = time.perf_counter() - t0
     cores, blas = blas_threads()
     value = sample * args.steps / dt
@@ -238,7 +248,6 @@ def main():
     import torch
     import torch.distributed as dist
 
-    from oracle import gpr_oracle as go  # checker + cpu_baseline leg only
     from pygpso_b200 import backend, gpmodel
     from pygpso_b200.distributed import ShardedScorer, gather_records, pick_best, shard_bounds
 
@@ -252,7 +261,7 @@ def main():
     N, d, M, desc = WORKLOADS[args.workload]
     if args.candidates:
         M = args.candidates
-    varsigma = go.VARSIGMA_DEFAULT
+    varsigma = VARSIGMA
     X, y = synthetic_training(N, d)
     theta = fixed_theta(d)
 
@@ -423,7 +432,7 @@ def main():
         }
         # ---- second half of the BASELINE metric: LML + gradient evaluations per second (the L-BFGS-B closure) ---------
         if world == 1 and not args.no_lml:
-            line["lml_grad"] = bench_lml_grad(backend.CudaBackend(device=local_rank), go, cpu=not args.no_cpu_baseline)
+            line["lml_grad"] = bench_lml_grad(backend.CudaBackend(device=local_rank), cpu=not args.no_cpu_baseline)
         # ---- CPU baseline beside it (bounded sample, rank 0, single GPU runs only) -----------------------------------
         if world == 1 and not args.no_cpu_baseline:
             sample = min(M, CPU_SAMPLE)

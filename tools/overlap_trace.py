@@ -51,7 +51,6 @@ class PowerSampler(threading.Thread):
 def main():
     import torch
 
-    from oracle import gpr_oracle as go
     from pygpso_b200 import backend
 
     M = int(float(sys.argv[1])) if len(sys.argv) > 1 else 1_200_000
@@ -65,7 +64,7 @@ def main():
     sess.factorize(theta)
     xc = torch.from_numpy(np.random.default_rng([bench.SEED, 0]).random((M, d))).cuda()
     stream = torch.cuda.current_stream().cuda_stream
-    vs = go.VARSIGMA_DEFAULT
+    vs = bench.VARSIGMA
     report = {"M": M, "N": N, "d": d, "engine": sess.predict_info()}
 
     def timed(steps, label):
