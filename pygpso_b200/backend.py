@@ -36,6 +36,21 @@ def library_path():
 
 
 _lib = None
+_cuda_touched = False
+
+
+def cuda_initialised():
+    """True once this process has opened a CUDA context through this package or through torch (fork safety of the
+    objective worker pool, optimisation.py)."""
+    if _cuda_touched:
+        return True
+    import sys
+
+    torch = sys.modules.get("torch")
+    try:
+        return bool(torch is not None and torch.cuda.is_initialized())
+    except Exception:
+        return False
 
 
 def load_library():
@@ -130,7 +145,7 @@ def _check(lib, rc, what):
 
 
 def default_device():
-    """GPU index for this process: LOCAL_RANK under torchrun, else GPSO_DEVICE, else 0."""
+    """GPU index for this process: GPSO_DEVICE if set, else LOCAL_RANK (torchrun), else 0."""
     for var in ("GPSO_DEVICE", "LOCAL_RANK"):
         if var in os.environ:
             return int(os.environ[var])
@@ -153,11 +168,15 @@ class CudaSession:
                "gpso_create")
         self._h = handle
         self.N = self.d = 0
+        # mirrors the handle's own flag: every call that overwrites the device factor (a loss evaluation, new data, an engine
+        # switch) clears it, so the model re-factorises before the next prediction even at unchanged hyper-parameters
+        self.factorized = False
 
     # -- fit ----------------------------------------------------------------------------------------------------------
     def set_data(self, x, y):
         x = np.ascontiguousarray(x, dtype=np.float64)
         y = np.ascontiguousarray(y, dtype=np.float64).reshape(-1)
+        self.factorized = False
         _check(self._lib, self._lib.gpso_set_data(self._h, _dptr(x), _dptr(y), x.shape[0], x.shape[1]), "gpso_set_data")
         self.N, self.d = x.shape
 
@@ -165,13 +184,16 @@ class CudaSession:
         u = np.ascontiguousarray(u, dtype=np.float64)
         f = ctypes.c_double()
         grad = np.empty_like(u)
+        self.factorized = False
         _check(self._lib, self._lib.gpso_neg_lml_grad(self._h, _dptr(u), u.size, ctypes.byref(f), _dptr(grad)),
                "gpso_neg_lml_grad")
         return float(f.value), grad
 
     def factorize(self, theta):
         theta = np.ascontiguousarray(theta, dtype=np.float64)
+        self.factorized = False
         _check(self._lib, self._lib.gpso_factorize(self._h, _dptr(theta), theta.size), "gpso_factorize")
+        self.factorized = True
 
     def log_marginal_likelihood(self):
         v = ctypes.c_double()
@@ -238,8 +260,10 @@ class CudaSession:
         _check(self._lib, self._lib.gpso_export_state_dev(self._h, dst_ptr, nbytes, stream), "gpso_export_state_dev")
 
     def import_state_dev(self, src_ptr, nbytes, n, d, stream=0):
+        self.factorized = False
         _check(self._lib, self._lib.gpso_import_state_dev(self._h, src_ptr, nbytes, n, d, stream), "gpso_import_state_dev")
         self.N, self.d = n, d
+        self.factorized = True
 
     # -- introspection ------------------------------------------------------------------------------------------------
     def launch_count(self):
@@ -266,22 +290,27 @@ class CudaSession:
 
     def set_predict_mode(self, mode=0, slices=0):
         """0 automatic, 1 FP64 DMMA, 2 int8 tcgen05 (``slices`` 8-bit digits per operand, 0 = automatic)."""
+        self.factorized = False
         _check(self._lib, self._lib.gpso_set_predict_mode(self._h, int(mode), int(slices)), "gpso_set_predict_mode")
 
     def set_kinv_mode(self, mode=0):
         """K_y^-1 = L^-T L^-1 of the gradient: 0 automatic, 1 FP64 DMMA tiles, 2 int8 tcgen05 (54-bit fixed point)."""
+        self.factorized = False
         _check(self._lib, self._lib.gpso_set_kinv_mode(self._h, int(mode)), "gpso_set_kinv_mode")
 
     def set_l2_window(self, enabled=True):
         """int8 engine: persisting-L2 access window over the digit tiles of L^-1 (default on)."""
+        self.factorized = False
         _check(self._lib, self._lib.gpso_set_l2_window(self._h, int(bool(enabled))), "gpso_set_l2_window")
 
     def set_inverse_mode(self, mode=0):
         """Recursive-doubling L^-1: 0 automatic, 1 FP64 DMMA tile tasks, 2 int8 tcgen05 (62-bit fixed point)."""
+        self.factorized = False
         _check(self._lib, self._lib.gpso_set_inverse_mode(self._h, int(mode)), "gpso_set_inverse_mode")
 
     def set_factor_mode(self, persistent=True):
         """Cholesky schedule: persistent dataflow kernel (default) or one launch per step; bit-identical results."""
+        self.factorized = False
         _check(self._lib, self._lib.gpso_set_factor_mode(self._h, int(bool(persistent))), "gpso_set_factor_mode")
 
     def set_overlap(self, enabled=True):
@@ -319,7 +348,9 @@ class CudaBackend:
     name = "cuda-sm100a"
 
     def __init__(self, device=None):
+        global _cuda_touched
         self._lib = load_library()
+        _cuda_touched = True
         n = self._lib.gpso_device_count()
         if n <= 0:
             raise GpsoBackendError(

@@ -57,7 +57,8 @@ constexpr long long WINDOW_BYTES = 2LL << 30;  // rolling cross-covariance windo
 constexpr int OZ_XCOV_SMEM_MAX = 172 * 1024;   // crosscov_slices_kernel dynamic shared memory at d = 64 (320 d + 768 doubles)
 constexpr int OZ_MIN_NP = 256;                 // below this the int8 path is not worth its fixed costs (automatic mode); config C5
                                                // (N = 21..500, 265 720 candidates per call): 9.6 s wall with 512, 7.0 s with 256, 7.0 s with 128
-constexpr int OZ_MAX_NP = 16384;               // int32 accumulators stay exact: S * 2^14 * Np < 2^31
+constexpr int OZ_MAX_NP = 8192;                // int32 accumulators stay exact: pairs per level (<= S = 8) * 2^14 * Np <= 2^30 < 2^31
+                                               // (16384 would reach exactly 2^31); larger problems stay on the FP64 DMMA engines
 constexpr int OZ_KINV_S = 7;                   // digits per operand of the int8 K_y^-1 = L^-T L^-1 product (54-bit fixed point per row)
 constexpr int OZ_KINV_MIN_NP = 512;            // automatic mode; measured down to N = 512 (LML+grad 0.553 -> 0.498 ms there, 1.13 -> 1.01 ms at 1024)
 constexpr int OZ_INV_S = 8;                    // digits per operand of the int8 inverse-factor products (62-bit fixed point per row)
@@ -91,6 +92,10 @@ struct DevBuf {
         p = nullptr;
         cap = 0;
     }
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }  // every buffer of a handle goes with it (gpso_destroy sets the device first)
     template <class T>
     T* as() const {
         return reinterpret_cast<T*>(p);
@@ -961,11 +966,6 @@ extern "C" int gpso_destroy(gpso_handle* h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     cudaStreamSynchronize(h->copy_stream);
-    DevBuf* bufs[] = {&h->X, &h->y, &h->Xs, &h->ls, &h->alpha, &h->K, &h->Linv, &h->LinvT, &h->T, &h->Kinv, &h->resid, &h->a,
-                      &h->logdet, &h->scalars, &h->gpart, &h->gout, &h->info, &h->counter, &h->KsT, &h->part,
-                      &h->blockbest, &h->running, &h->cand[0], &h->cand[1], &h->leaves, &h->omean, &h->ovar,
-                      &h->ozA, &h->ozBb[0], &h->ozBb[1], &h->wmeanb[0], &h->wmeanb[1], &h->rowscale, &h->rowmax};
-    for (DevBuf* b : bufs) b->release();
     cudaStreamSynchronize(h->aux_stream);
     for (int i = 0; i < 2; i++) {
         cudaEventDestroy(h->ev_copy[i]);
@@ -979,9 +979,10 @@ extern "C" int gpso_destroy(gpso_handle* h) {
     cudaEventDestroy(h->ev_t1);
     for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
     for (cudaEvent_t e : h->prod_events) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->trace_events) cudaEventDestroy(e);
     cudaStreamDestroy(h->stream);
     cudaStreamDestroy(h->copy_stream);
-    delete h;
+    delete h;  // ~DevBuf releases every device buffer of the handle
     return 0;
 }
 

@@ -181,9 +181,12 @@ def sharded_multistart_fit(objective, u0, n_restarts, group=None, seed=20240517,
         except np.linalg.LinAlgError:
             mine[i, 0], mine[i, 1:] = on_error, starts[i]
     dev = _comm_device(group)
-    local = torch.tensor(np.nan_to_num(mine, nan=0.0), dtype=torch.float64, device=dev)
-    dist.all_reduce(local, op=dist.ReduceOp.SUM, group=group)  # each row is non-zero on exactly one rank
-    table = local.cpu().numpy()
-    f = table[:, 0]
+    local = torch.tensor(mine, dtype=torch.float64, device=dev)
+    parts = [torch.empty_like(local) for _ in range(world)]
+    dist.all_gather(parts, local, group=group)
+    # row i is taken verbatim from its owner (rank i mod W): a restart whose own optimum is NaN/inf stays non-finite here and
+    # is ranked last below, instead of turning into a spurious f = 0 under a SUM reduction
+    table = np.stack([parts[i % world][i].cpu().numpy() for i in range(n_restarts)])
+    f = np.where(np.isfinite(table[:, 0]), table[:, 0], np.inf)
     best = int(np.argmin(f))  # first minimum = lowest restart id on ties
     return table[best, 1:].copy(), float(f[best]), best, table

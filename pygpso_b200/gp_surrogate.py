@@ -17,6 +17,7 @@ Host-side change: the point list keeps a dense coordinate matrix next to the lis
 Python loop over all points; order, replace-in-place and "evaluated wins" semantics are unchanged.
 """
 import bisect
+import itertools
 import json
 import logging
 import os
@@ -76,12 +77,22 @@ class GPListOfPoints(list):
         if args:
             assert all(isinstance(it, GPPoint) for it in args[0])
         super().__init__(*args, **kwargs)
+        self._reset_index()
+
+    _uids = itertools.count(1)
+
+    def _reset_index(self):
         self._coords = None  # [capacity, d] mirror of the coordinates of self[0:len(self)]
         self._count = 0
         self._weights = None  # projection direction
         self._keys = []       # sorted projections
         self._key_idx = []    # list positions, parallel to _keys
         self.epoch = 0
+        self.uid = next(GPListOfPoints._uids)  # identity of this list for position caches (never pickled)
+
+    def __reduce__(self):
+        # pickle as the plain list of points (the reference class is a bare list subclass); the index is rebuilt lazily
+        return (type(self), (list(self),))
 
     # -- coordinate mirror + projection index ---------------------------------------------------------------------------
     def _mirror(self):
@@ -107,7 +118,7 @@ class GPListOfPoints(list):
 
     def _invalidate(self):
         self._coords, self._count = None, 0
-        self.epoch += 1
+        self.epoch = getattr(self, "epoch", 0) + 1
 
     def _window(self, coords):
         """(projection, lo, hi): the slice of the sorted projections that can hold points within the tolerance."""

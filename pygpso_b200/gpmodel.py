@@ -53,12 +53,14 @@ class _Shape(tuple):
 class Parameter:
     """
     A (possibly positive-constrained) hyper-parameter.  The constrained value is stored verbatim, so a value that is
-    assigned (e.g. when loading a saved model) is used bit-for-bit; the unconstrained image is derived on demand for
-    the optimiser.
+    assigned (e.g. when loading a saved model) is used bit-for-bit.  The unconstrained image an optimiser assigned is kept
+    beside it (a noise variance that rounds to exactly its 1e-6 floor still has a finite unconstrained value); after an
+    explicit ``assign`` it is derived on demand, clamped away from softplus^-1(0) = -inf.
     """
 
     def __init__(self, value, positive=False, lower=0.0, trainable=True, name=""):
         self._value = np.array(value, dtype=np.float64)
+        self._unconstrained = None
         self.positive = positive
         self.lower = float(lower)
         self.trainable = trainable
@@ -92,15 +94,21 @@ class Parameter:
         if self.positive and np.any(value <= self.lower):
             raise ValueError(f"parameter {self.name} must be > {self.lower}")
         self._value = value
+        self._unconstrained = None
 
     @property
     def unconstrained(self):
+        if self._unconstrained is not None:
+            return self._unconstrained.copy()
         flat = self._value.reshape(-1)
-        return _softplus_inv(flat - self.lower) if self.positive else flat.copy()
+        if not self.positive:
+            return flat.copy()
+        return _softplus_inv(np.maximum(flat - self.lower, np.finfo(np.float64).tiny))
 
     def assign_unconstrained(self, u):
-        u = np.asarray(u, dtype=np.float64).reshape(self._value.shape)
+        u = np.array(u, dtype=np.float64).reshape(self._value.shape)
         self._value = np.array(self.lower + _softplus(u) if self.positive else u, dtype=np.float64)
+        self._unconstrained = u.reshape(-1).copy()
 
     def __repr__(self):
         return f"Parameter({self.name}={self._value!r})"
@@ -272,6 +280,7 @@ class GPR(GPModel):
     def neg_log_marginal_likelihood_and_grad(self, u):
         """(-LML, d(-LML)/du) at the packed unconstrained vector ``u``; evaluated on the device."""
         self.n_loss_evaluations += 1
+        self._factor_key = None  # the evaluation overwrites the device factor
         return self._session.neg_lml_and_grad(np.ascontiguousarray(u, dtype=np.float64))
 
     def training_loss(self):
@@ -284,7 +293,8 @@ class GPR(GPModel):
     def _ensure_factor(self):
         theta = self._theta()
         key = theta.tobytes()
-        if key != self._factor_key:
+        # the session drops its factor whenever a loss evaluation or an engine switch overwrote it (same theta or not)
+        if key != self._factor_key or not getattr(self._session, "factorized", True):
             self._session.factorize(theta)
             self._factor_key = key
 
@@ -336,11 +346,26 @@ class Scipy:
         model = getattr(closure, "__self__", None)
         if not isinstance(model, GPR):
             raise TypeError("Scipy.minimize expects the bound method `model.training_loss` of a GPR model")
-        u0 = model._pack()
-        result = scipy.optimize.minimize(
-            model.neg_log_marginal_likelihood_and_grad, u0, jac=True, method=method, **scipy_kwargs
-        )
-        model._unpack(result.x)
+        u_full = model._pack()
+        # optimise over `variables` only (GPflow passes model.trainable_variables): entries of the packed vector that belong
+        # to parameters outside that set (or with trainable=False) stay at their current values
+        wanted = {id(v) for v in variables} if variables is not None else None
+        free = np.zeros(u_full.size, dtype=bool)
+        pos = 0
+        for p in model._ordered_parameters:
+            free[pos:pos + p.size] = p.trainable and (wanted is None or id(p) in wanted)
+            pos += p.size
+        if free.all():
+            objective = model.neg_log_marginal_likelihood_and_grad
+        else:
+            def objective(u_free):
+                u = u_full.copy()
+                u[free] = u_free
+                f, g = model.neg_log_marginal_likelihood_and_grad(u)
+                return f, g[free]
+        result = scipy.optimize.minimize(objective, u_full[free], jac=True, method=method, **scipy_kwargs)
+        u_full[free] = result.x
+        model._unpack(u_full)
         return result
 
 

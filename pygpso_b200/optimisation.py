@@ -48,13 +48,25 @@ class GPSOCallback:
         logging.info(f"Running {self.__class__.__name__} callback...")
 
 
+def _pool_start_method():
+    """``fork`` while this process has not touched CUDA (the usual case: the pool of a run is created by the initial design,
+    before the first fit opens the device session), else ``forkserver`` -- a forked child of a CUDA-initialised,
+    multi-threaded parent can inherit locked driver state.  ``GPSO_POOL_START`` overrides."""
+    forced = os.environ.get("GPSO_POOL_START")
+    if forced:
+        return forced
+    from . import backend
+
+    return "forkserver" if backend.cuda_initialised() else "fork"
+
+
 def _make_pool(n_workers):
     """Process pool for objective evaluations (children never touch CUDA)."""
     try:
         import multiprocess as mp  # dill-based: handles lambdas / local functions like pathos does
     except ImportError:  # pragma: no cover
         import multiprocessing as mp
-    return mp.get_context(os.environ.get("GPSO_POOL_START", "fork")).Pool(n_workers)
+    return mp.get_context(_pool_start_method()).Pool(n_workers)
 
 
 class GPSOptimiser:
@@ -155,6 +167,20 @@ class GPSOptimiser:
         self.saver = saver
         if saver is not None:
             assert callable(getattr(self.saver, "save_runs", None))
+        self._pool = None
+
+    def _close_pool(self):
+        """The worker pool lives for one ``run`` / ``resume_run`` (the reference builds one per evaluation call)."""
+        pool, self._pool = getattr(self, "_pool", None), None
+        if pool is not None:
+            pool.close()
+            pool.join()
+
+    def __del__(self):
+        try:
+            self._close_pool()
+        except Exception:
+            pass
 
     # -----------------------------------------------------------------------------------------------------------------
     def _run_callbacks(self, callback_type):
@@ -210,16 +236,17 @@ class GPSOptimiser:
             logging.info("Update step: retraining GP model and updating scores...")
             self.gp_surr.gp_update()
             points = self.gp_surr.points
-            epoch = getattr(points, "epoch", None)
+            epoch, uid = getattr(points, "epoch", None), getattr(points, "uid", None)
             for leaf in PreOrderIter(self.param_space):
-                # the position of a node's point does not change while points are only appended / replaced in place
+                # the position of a node's point does not change while points are only appended / replaced in place; the
+                # cache names the list by its uid (not by reference: a pickled tree must not drag the point list along)
                 cached = getattr(leaf, "_point_ref", None)
-                if cached is not None and epoch is not None and cached[0] is points and cached[1] == epoch:
+                if cached is not None and epoch is not None and cached[0] == uid and cached[1] == epoch:
                     leaf_point = points[cached[2]]
                 else:
                     position = points.index_by_coords(leaf.center_array())
                     assert position is not None
-                    leaf._point_ref = (points, epoch, position)
+                    leaf._point_ref = (uid, epoch, position)
                     leaf_point = points[position]
                 if leaf_point.label == PointLabels.gp_based:
                     leaf.score = leaf_point.score_ucb
@@ -310,12 +337,13 @@ class GPSOptimiser:
         assert orig_coords.shape[1] == self.param_space.ndim
         repeated = np.vstack(self.eval_repeats * [orig_coords])
         if self.n_workers > 1 and (self.eval_repeats * orig_coords.shape[0]) > 1:
-            pool = _make_pool(self.n_workers)
+            if getattr(self, "_pool", None) is None:
+                self._pool = _make_pool(self.n_workers)
             try:
-                scores = list(pool.map(self.obj_func, repeated))
-            finally:
-                pool.close()
-                pool.join()
+                scores = list(self._pool.map(self.obj_func, repeated))
+            except BaseException:
+                self._close_pool()
+                raise
         else:
             scores = [self.obj_func(coords) for coords in repeated]
         self.n_eval_counter += orig_coords.shape[0]  # repeats are not charged to the budget
@@ -342,6 +370,12 @@ class GPSOptimiser:
     # -----------------------------------------------------------------------------------------------------------------
     def _iterate(self, explore_levels, update_idx):
         """The explore / select / update loop shared by ``run`` and ``resume_run``."""
+        try:
+            return self._iterate_loop(explore_levels, update_idx)
+        finally:
+            self._close_pool()
+
+    def _iterate_loop(self, explore_levels, update_idx):
         keep_going = True
         while keep_going:
             self._run_callbacks(callback_type=CallbackTypes.pre_iteration)
