@@ -165,6 +165,27 @@ int gpso_set_factor_mode(gpso_handle* h, int mode);
 int gpso_debug_factor_tasks(int nb, int nsm, int* out, int64_t capacity_words, int* ntasks, int* ncounters);
 /* tuning knob: candidates per rolling window (0 = automatic) */
 int gpso_set_window(gpso_handle* h, int64_t candidates);
+/* Screen-and-refine form of the fused arg-max calls (gpso_ucb_argmax_*, gpso_grow_ucb_argmax; replaces the same reference call
+ * sites, gpso/gp_surrogate.py:313-328): all candidates are first scored with `digits` 8-bit digits per operand and an fp32
+ * cross-covariance, the candidates whose screened UCB is within 2E of the best one (E = modelled error bound, checked on the
+ * survivors) are re-scored by the full-precision engine, and the record of that engine is returned -- bit-identical to the
+ * unscreened call.  mode 0 = off, 1 = automatic (default; from N >= 1024 and M >= 65536, digits adapt to the survivor
+ * fraction), 2..4 = forced digit count.  Takes effect at the next gpso_factorize.  gpso_predict_y_* and gpso_ucb_topk_* never
+ * screen. */
+int gpso_set_screen_mode(gpso_handle* h, int mode);
+/* last fused arg-max call: out[0] path (0 unscreened, 1 screened, 2 full pass: too many survivors, 3 full pass: bound check
+ * failed), out[1] screening digits, out[2] survivors, out[3] error bound E, out[4] largest |refined - screened| UCB over
+ * the survivors, out[5] best screened UCB, out[6] screening windows, out[7] summed duration (ms) of the screening product
+ * launches, out[8] refine windows, out[9] E_var, out[10] E_mean, out[11] unused */
+int gpso_screen_info(gpso_handle* h, double* out12);
+/* Host-only (works without a GPU): the error bound E of the screening pass and its variance / mean parts,
+ * out3 = {E, E_var, E_mean}, for N training points, kernel variance, noise variance, the largest power-of-two row scale of
+ * L^-1, the sum of the squared row scales, |alpha|_2, the screening digit count (2..4) and the UCB multiplier. */
+/* Pipe peaks of GPU `device`, measured now (~0.2 s): out4 = {int8 tensor TOP/s (tcgen05 kind::i8 issue rate), FP64 TFLOP/s
+ * (DMMA.8x8x4 issue rate), L2 -> shared-memory bulk-copy GB/s, number of SMs}.  bench.py divides by these. */
+int gpso_probe_peaks(int device, double* out4);
+int gpso_debug_screen_bound(int N, double variance, double noise, double rho_max, double rho_l2sq, double alpha_l2, int digits,
+                            double varsigma, double* out3);
 
 #ifdef __cplusplus
 }

@@ -108,6 +108,10 @@ def load_library():
         "gpso_set_kinv_mode": (i32, [H, i32]),
         "gpso_set_inverse_mode": (i32, [H, i32]),
         "gpso_set_l2_window": (i32, [H, i32]),
+        "gpso_set_screen_mode": (i32, [H, i32]),
+        "gpso_screen_info": (i32, [H, _c_double_p]),
+        "gpso_probe_peaks": (i32, [i32, _c_double_p]),
+        "gpso_debug_screen_bound": (i32, [i32, dbl, dbl, dbl, dbl, dbl, i32, dbl, _c_double_p]),
         "gpso_debug_product_items": (i64, [i32, i32, i32, ctypes.POINTER(ctypes.c_int), i64, ctypes.POINTER(ctypes.c_int), i32,
                                            ctypes.POINTER(ctypes.c_int)]),
     }
@@ -131,7 +135,8 @@ EXPORTED_SYMBOLS = (
     "gpso_grow_count gpso_grow_leaves_host gpso_grow_leaves_dev gpso_grow_ucb_argmax gpso_state_bytes "
     "gpso_export_state_dev gpso_import_state_dev gpso_launch_count gpso_debug_fetch gpso_last_timing gpso_set_window "
     "gpso_set_profile gpso_last_windows gpso_set_predict_mode gpso_predict_info gpso_set_overlap "
-    "gpso_set_factor_mode gpso_debug_factor_tasks gpso_debug_trace gpso_set_kinv_mode gpso_set_inverse_mode gpso_set_l2_window gpso_debug_product_items"
+    "gpso_set_factor_mode gpso_debug_factor_tasks gpso_debug_trace gpso_set_kinv_mode gpso_set_inverse_mode gpso_set_l2_window gpso_debug_product_items "
+    "gpso_set_screen_mode gpso_screen_info gpso_debug_screen_bound gpso_probe_peaks"
 ).split()
 
 
@@ -321,6 +326,19 @@ class CudaSession:
         _check(self._lib, self._lib.gpso_predict_info(self._h, _dptr(out)), "gpso_predict_info")
         return {"engine": "int8-tcgen05" if out[0] == 2 else "fp64-dmma", "slices": int(out[1]), "error_estimate_over_tol": float(out[2])}
 
+    def set_screen_mode(self, mode=1):
+        """Screen-and-refine arg-max: 0 off, 1 automatic (default), 2..4 forced screening digits; results are bit-identical."""
+        self.factorized = False
+        _check(self._lib, self._lib.gpso_set_screen_mode(self._h, int(mode)), "gpso_set_screen_mode")
+
+    def screen_info(self):
+        out = np.zeros(12)
+        _check(self._lib, self._lib.gpso_screen_info(self._h, _dptr(out)), "gpso_screen_info")
+        path = {0: "unscreened", 1: "screened", 2: "full pass (too many survivors)", 3: "full pass (bound check failed)"}[int(out[0])]
+        return {"path": path, "digits": int(out[1]), "survivors": int(out[2]), "error_bound": float(out[3]),
+                "max_observed_deviation": float(out[4]), "best_screened_ucb": float(out[5]), "screen_windows": int(out[6]),
+                "screen_product_ms": float(out[7]), "refine_windows": int(out[8]), "e_var": float(out[9]), "e_mean": float(out[10])}
+
     def set_window(self, candidates):
         _check(self._lib, self._lib.gpso_set_window(self._h, int(candidates)), "gpso_set_window")
 
@@ -361,6 +379,12 @@ class CudaBackend:
 
     def open_session(self, kernel, n_lengthscales, has_mean):
         return CudaSession(self._lib, self.device, kernel, n_lengthscales, has_mean)
+
+    def probe_peaks(self):
+        """Pipe peaks of this GPU measured now: int8 tensor TOP/s, FP64 DMMA TFLOP/s, L2 -> shared memory GB/s."""
+        out = np.zeros(4)
+        _check(self._lib, self._lib.gpso_probe_peaks(self.device, _dptr(out)), "gpso_probe_peaks")
+        return {"int8_tops": float(out[0]), "fp64_tflops": float(out[1]), "l2_to_smem_gbs": float(out[2]), "sms": int(out[3])}
 
     def grow_count(self, depth):
         return int(self._lib.gpso_grow_count(int(depth)))

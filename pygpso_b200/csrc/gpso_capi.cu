@@ -23,6 +23,8 @@
 #include "kern_leaves.cuh"
 #include "kern_ozaki.cuh"
 #include "kern_predict.cuh"
+#include "kern_screen.cuh"
+#include "kern_probe.cuh"
 
 using namespace gpso;
 
@@ -64,6 +66,12 @@ constexpr int OZ_KINV_MIN_NP = 512;            // automatic mode; measured down 
 constexpr int OZ_INV_S = 8;                    // digits per operand of the int8 inverse-factor products (62-bit fixed point per row)
 constexpr int OZ_INV_MIN_NP = 512;             // automatic mode; measured down to N = 512 (0.498 -> 0.474 ms there, 2.05 -> 1.75 ms at 2048)
 constexpr double OZ_TARGET = 0.02;             // accepted (estimated error) / (parity tolerance 1e-8 * variance)
+// screen-and-refine arg-max (kern_screen.cuh)
+constexpr int SCREEN_MIN_NP = 1024;            // below this the full-precision product is cheap: no screening
+constexpr long long SCREEN_MIN_M = 65536;      // fewer candidates than this: no screening
+constexpr double SCREEN_SAFETY = 4.0;          // error bound E = SAFETY * (model estimate); the refine pass must observe <= E / 4
+constexpr unsigned SCREEN_LIST_CAP = 1u << 20; // survivor list capacity; more survivors than this or than M / 16 -> full pass
+constexpr int SCREEN_S_MIN = 2, SCREEN_S_MAX = 4;
 
 struct DevBuf {
     void* p = nullptr;
@@ -149,6 +157,21 @@ struct gpso_handle {
     int oz_S = 0;           // digits per operand chosen at the last factorisation (0: DMMA path in force)
     double oz_est = 0.0;    // error estimate / tolerance for the chosen S
     long long window_override = 0;
+    // screen-and-refine arg-max: fp32 copies of the scaled inputs / alpha, low-digit tiles of L^-1, per-candidate screened UCB,
+    // {max key, survivor count, max |refined - screened|}, survivor index list and gathered survivor coordinates
+    DevBuf Xs32, alpha32, ozAs, part32, scr_ucb, scr_state, surv_list, surv_X;
+    int screen_mode = 1;        // 0 off, 1 automatic (digits adapt to the survivor fraction), 2..4 forced digits
+    int screen_S_cur = SCREEN_S_MIN;
+    int screen_built_S = 0;     // digits of the tiles in ozAs (0: stale)
+    bool screen_ready = false;  // fp32 copies and norms valid for the factor in force
+    double alpha_l2 = 0.0, rho_max = 0.0, rho_l2sq = 0.0;
+    // last call: [0] path (0 unscreened, 1 screened, 2 fallback: too many survivors, 3 fallback: check failed), [1] digits,
+    // [2] survivors, [3] E, [4] max |refined - screened| over the survivors, [5] best screened UCB, [6] screen windows,
+    // [7] screening product ms, [8] refine windows, [9] E_var, [10] E_mean
+    double scr_info[12] = {0};
+    const long long* rw_idx_map = nullptr;  // run_windows: global indices of the (gathered) candidates
+    bool rw_check = false;                  // run_windows: compare refined and screened UCB of every candidate
+    size_t scr_prod_marks = 0;
     // host copies of the hyper-parameters in force
     double ls_host[MAX_LS] = {0}, variance = 1.0, noise = 1.0, c0 = 0.0;
     bool have_data = false, factorized = false;
@@ -236,6 +259,72 @@ static int oz_configure() {
     CU_TRY(cudaFuncSetAttribute(crosscov_slices_kernel<KERNEL_SE, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_XCOV_SMEM_MAX));
     return 0;
 }
+
+template <int S>
+static int screen_configure() {
+    CU_TRY(cudaFuncSetAttribute(ozaki_screen_kernel<S, SCR_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, ScrCfg<S, SCR_NT>::SMEM_BYTES));
+    CU_TRY(cudaFuncSetAttribute(ozaki_screen_kernel<S, SCR_NT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CU_TRY(cudaFuncSetAttribute(crosscov_screen_kernel<KERNEL_MATERN12, S, SCR_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_XCOV_SMEM_MAX));
+    CU_TRY(cudaFuncSetAttribute(crosscov_screen_kernel<KERNEL_MATERN32, S, SCR_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_XCOV_SMEM_MAX));
+    CU_TRY(cudaFuncSetAttribute(crosscov_screen_kernel<KERNEL_MATERN52, S, SCR_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_XCOV_SMEM_MAX));
+    CU_TRY(cudaFuncSetAttribute(crosscov_screen_kernel<KERNEL_SE, S, SCR_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_XCOV_SMEM_MAX));
+    CU_TRY(cudaFuncSetAttribute(crosscov_screen_kernel<KERNEL_MATERN12, S, SCR_NT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CU_TRY(cudaFuncSetAttribute(crosscov_screen_kernel<KERNEL_MATERN32, S, SCR_NT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CU_TRY(cudaFuncSetAttribute(crosscov_screen_kernel<KERNEL_MATERN52, S, SCR_NT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CU_TRY(cudaFuncSetAttribute(crosscov_screen_kernel<KERNEL_SE, S, SCR_NT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    return 0;
+}
+
+static size_t screen_xcov_smem(int d) { return (size_t)(64 * d + 2 * d * OZ_XK + 2 * OZ_XK) * sizeof(float) + 8 * 64 * sizeof(double); }
+
+template <int KID, int S>
+static void launch_screen_crosscov(gpso_handle* h, cudaStream_t st, const double* Xc, long long Mw, long long ngroups, float bscale,
+                                   uint8_t* B, double* wmean) {
+    crosscov_screen_kernel<KID, S, SCR_NT><<<(unsigned)ngroups, 256, screen_xcov_smem(h->d), st>>>(
+        Xc, Mw, h->d, h->ls.as<double>(), h->n_ls(), h->Xs32.as<float>(), h->alpha32.as<float>(), h->N, h->Np, (float)h->variance, h->c0,
+        bscale, h->Np / 32, B, wmean);
+}
+
+template <int S>
+static void launch_screen_crosscov_s(gpso_handle* h, cudaStream_t st, const double* Xc, long long Mw, long long ngroups, float bscale,
+                                     uint8_t* B, double* wmean) {
+    switch (h->kernel_id) {
+        case KERNEL_MATERN12: launch_screen_crosscov<KERNEL_MATERN12, S>(h, st, Xc, Mw, ngroups, bscale, B, wmean); break;
+        case KERNEL_MATERN32: launch_screen_crosscov<KERNEL_MATERN32, S>(h, st, Xc, Mw, ngroups, bscale, B, wmean); break;
+        case KERNEL_MATERN52: launch_screen_crosscov<KERNEL_MATERN52, S>(h, st, Xc, Mw, ngroups, bscale, B, wmean); break;
+        default: launch_screen_crosscov<KERNEL_SE, S>(h, st, Xc, Mw, ngroups, bscale, B, wmean); break;
+    }
+}
+
+template <int S>
+static void launch_screen_product(gpso_handle* h, cudaStream_t st, long long nct, long long ldp, double gscale, const uint8_t* B) {
+    ScrParams P;
+    P.A = h->ozAs.as<uint8_t>();
+    P.B = B;
+    P.rowscale = h->rowscale.as<double>();
+    P.part = h->part32.as<float>();
+    P.gscale = gscale;
+    P.nb = h->nb;
+    P.nks = h->Np / 32;
+    P.nct = (int)nct;
+    P.ldp = ldp;
+    const long long units = nct * ((h->nb + 1) / 2);
+    const int grid = (int)std::min<long long>(h->nsm, units);
+    ozaki_screen_kernel<S, SCR_NT><<<grid, OZ_THREADS, ScrCfg<S, SCR_NT>::SMEM_BYTES, st>>>(P);
+}
+
+template <int S>
+static void launch_screen_slices(gpso_handle* h, cudaStream_t st) {
+    dim3 grid(h->Np / 32, h->nb);
+    linv_slices_kernel<S, false><<<grid, 256, 0, st>>>(h->Linv.as<double>(), h->rowscale.as<double>(), h->Np, h->Np / 32, h->ozAs.as<uint8_t>());
+}
+
+#define DISPATCH_SCREEN_S(S_, fn, ...)         \
+    switch (S_) {                              \
+        case 2: fn<2>(__VA_ARGS__); break;     \
+        case 3: fn<3>(__VA_ARGS__); break;     \
+        default: fn<4>(__VA_ARGS__); break;    \
+    }
 
 static size_t oz_xcov_smem(int d) { return (size_t)(OZ_NT * d + 2 * d * OZ_XK + 2 * OZ_XK + 8 * OZ_NT) * sizeof(double); }
 
@@ -329,6 +418,9 @@ static int configure_kernels() {
     CU_TRY(cudaFuncSetAttribute(factor_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM_BYTES));
     CU_TRY(cudaFuncSetAttribute(ozaki_kernel<OZ_KINV_S, OZ_LAUUM>, cudaFuncAttributeMaxDynamicSharedMemorySize, OzCfg<OZ_KINV_S>::SMEM_BYTES));
     CU_TRY(cudaFuncSetAttribute(ozaki_kernel<OZ_INV_S, OZ_GEMM>, cudaFuncAttributeMaxDynamicSharedMemorySize, OzCfg<OZ_INV_S>::SMEM_BYTES));
+    GP_TRY(screen_configure<2>());
+    GP_TRY(screen_configure<3>());
+    GP_TRY(screen_configure<4>());
     GP_TRY(oz_configure<5>());
     GP_TRY(oz_configure<6>());
     GP_TRY(oz_configure<7>());
@@ -873,6 +965,8 @@ static int set_l2_window(gpso_handle* h, void* base, size_t bytes) {
 static int prepare_ozaki(gpso_handle* h, cudaStream_t st) {
     h->oz_S = 0;
     h->oz_est = 0.0;
+    h->screen_ready = false;
+    h->screen_built_S = 0;
     static const int min_np = getenv("GPSO_OZ_MIN_NP") ? atoi(getenv("GPSO_OZ_MIN_NP")) : OZ_MIN_NP;  // tuning experiments only
     bool want = h->predict_mode == 2 || (h->predict_mode == 0 && h->Np >= min_np);
     if (!want || h->Np > OZ_MAX_NP) return 0;
@@ -900,6 +994,25 @@ static int prepare_ozaki(gpso_handle* h, cudaStream_t st) {
     h->oz_S = S;
     h->oz_est = est;
     GP_TRY(set_l2_window(h, h->ozA.p, (size_t)Np * Np * S));
+    // screening state of the factor in force: fp32 copies of the scaled inputs and alpha, |alpha|_2 and the largest row scale
+    // (both enter the error bound); the low-digit tiles of L^-1 are built by the first screened call (their digit count adapts)
+    h->rho_max = rho_max;
+    h->rho_l2sq = 0.0;
+    for (int i = 0; i < h->N; i++) h->rho_l2sq += rs[i] * rs[i];
+    if (h->screen_mode != 0 && Np >= SCREEN_MIN_NP) {
+        GP_TRY(h->Xs32.ensure((size_t)h->d * Np * sizeof(float)));
+        GP_TRY(h->alpha32.ensure((size_t)Np * sizeof(float)));
+        screen_convert_kernel<<<(h->d * Np + 255) / 256, 256, 0, st>>>(h->Xs.as<double>(), h->alpha.as<double>(), h->d, Np,
+                                                                       h->Xs32.as<float>(), h->alpha32.as<float>());
+        GP_TRY(check_launch(h, "screen_convert"));
+        std::vector<double> al(Np);
+        CU_TRY(cudaMemcpyAsync(al.data(), h->alpha.p, sizeof(double) * Np, cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaStreamSynchronize(st));
+        double s2 = 0.0;
+        for (int i = 0; i < h->N; i++) s2 += al[i] * al[i];
+        h->alpha_l2 = sqrt(s2);
+        h->screen_ready = std::isfinite(h->alpha_l2);
+    }
     return 0;
 }
 
@@ -1162,11 +1275,15 @@ static int prod_mark(gpso_handle* h, cudaStream_t st) {
 // sums the per-window stage times recorded by prof_mark (call after the stream has been synchronised)
 static void prof_collect(gpso_handle* h) {
     h->last_ms[1] = h->last_ms[2] = h->last_ms[3] = 0.0;
+    double screen_ms = 0.0;
     for (size_t i = 0; i + 1 < h->prod_used; i += 2) {
         float t = 0;
         cudaEventElapsedTime(&t, h->prod_events[i], h->prod_events[i + 1]);
         h->last_ms[2] += t;
+        if (i < h->scr_prod_marks) screen_ms += t;  // the launches of the screening pass come first
     }
+    if (h->scr_prod_marks) h->scr_info[7] = screen_ms;
+    h->scr_prod_marks = 0;
     h->prod_used = 0;
     if (h->trace) {
         h->trace_out.clear();
@@ -1224,6 +1341,11 @@ static int run_windows(gpso_handle* h, cudaStream_t st, const double* Xc_dev, co
             GP_TRY(h->omean.ensure((size_t)W * sizeof(double)));
             GP_TRY(h->ovar.ensure((size_t)W * sizeof(double)));
         }
+    }
+    const bool check = mode == 1 && h->rw_check && h->rw_idx_map != nullptr;
+    if (check) {  // refine pass of the screened arg-max: the finalised mean/var of the window are compared with the screened UCB
+        GP_TRY(h->omean.ensure((size_t)W * sizeof(double)));
+        GP_TRY(h->ovar.ensure((size_t)W * sizeof(double)));
     }
     if (mode == 2) {  // top-k: finalised mean/var of the window stay on the device, k records per window
         GP_TRY(h->omean.ensure((size_t)W * sizeof(double)));
@@ -1313,13 +1435,18 @@ static int run_windows(gpso_handle* h, cudaStream_t st, const double* Xc_dev, co
         GP_TRY(trace_mark(h, st, 4, w));
         GP_TRY(prof_mark(h, st));
         // ---- 4. finalise: var, ucb, window arg-max merged into the running record
-        double* om = mode == 0 ? (host ? h->omean.as<double>() : mean_out + off) : mode == 2 ? h->omean.as<double>() : nullptr;
-        double* ov = mode == 0 ? (host ? h->ovar.as<double>() : var_out + off) : mode == 2 ? h->ovar.as<double>() : nullptr;
+        double* om = mode == 0 ? (host ? h->omean.as<double>() : mean_out + off) : (mode == 2 || check) ? h->omean.as<double>() : nullptr;
+        double* ov = mode == 0 ? (host ? h->ovar.as<double>() : var_out + off) : (mode == 2 || check) ? h->ovar.as<double>() : nullptr;
         int fb = (int)((Mw + 255) / 256);
         predict_finalize_kernel<<<fb, 256, 0, st>>>(h->part.as<double>(), h->wmeanb[b].as<double>(), h->nb, (int)Mw_pad, Mw, off,
                                                     h->variance, h->noise, varsigma, mode == 2 ? 0 : mode, om, ov,
-                                                    h->blockbest.as<BestRec>());
+                                                    h->blockbest.as<BestRec>(), mode == 1 ? h->rw_idx_map : nullptr);
         GP_TRY(check_launch(h, "predict_finalize"));
+        if (check) {
+            screen_check_kernel<<<fb, 256, 0, st>>>(om, ov, Mw, h->rw_idx_map + off, varsigma, h->scr_ucb.as<double>(),
+                                                    h->scr_state.as<unsigned long long>());
+            GP_TRY(check_launch(h, "screen_check"));
+        }
         if (mode == 2) {
             topk_window_kernel<<<1, 1024, 0, st>>>(om, ov, Mw, off, varsigma, h->topk_k, h->topk.as<BestRec>() + w * h->topk_k);
             GP_TRY(check_launch(h, "topk_window"));
@@ -1369,6 +1496,247 @@ static int fetch_best(gpso_handle* h, cudaStream_t st, double* result_host) {
     return 0;
 }
 
+// ---- screen-and-refine arg-max (kern_screen.cuh) ------------------------------------------------------------------------
+// Error bound of the screened UCB against the full-precision one.  Variance: pick_slices' model of the digit rounding and of
+// the neglected digit-pair levels at S digits (absolute: 6 sigma_f beta 2^-8S sqrt(N) max_i rho_i; measured deviations are
+// ~30x below it, profiles/r01_engine_error_c3.txt), plus the fp32 covariance evaluation seen through
+// d var = 2 dk^T K_y^-1 k*  with  |K_y^-1 k*|_2 <= sigma_f / sigma_n, plus the fp32 epilogue.  Mean: dk^T alpha with independent
+// fp32 errors of the covariance values and of the 16-term fp32 partial sums.  Everything times SCREEN_SAFETY; the refine pass
+// checks the bound on every survivor with another factor 4 of margin.
+static void screen_error_model(int N, double variance, double noise, double rho_max, double rho_l2sq, double alpha_l2, int S,
+                               double varsigma, double* e_total, double* e_var_out, double* e_mean_out) {
+    const double sigma_f = sqrt(variance), beta = ldexp(1.0, ilogb(variance) + 1);
+    // per-row standard deviation of the product error: 3 rho_i beta 2^-8S sqrt(N) (operand rounding + neglected levels)
+    const double unit = 3.0 * beta * ldexp(1.0, -8 * S) * sqrt((double)N);
+    const double est_var1 = 2.0 * sigma_f * unit * rho_max;   // first order:  2 sum_i v_i dv_i,  |v|_2 <= sigma_f
+    const double est_var2 = unit * unit * rho_l2sq;           // second order: sum_i dv_i^2 (a bias; matters at 2 digits only)
+    const double eps_k32 = 2.0e-6 * variance;
+    const double var_b = 2.0 * eps_k32 * sigma_f / sqrt(noise);
+    const double var_epi = 1.0e-6 * variance;
+    const double e_var = SCREEN_SAFETY * (est_var1 + est_var2 + var_b + var_epi);
+    const double e_mean = SCREEN_SAFETY * (eps_k32 + 1.0e-6 * variance) * alpha_l2;
+    *e_var_out = e_var;
+    *e_mean_out = e_mean;
+    *e_total = e_mean + fabs(varsigma) * e_var;
+}
+
+static void screen_error_bound(const gpso_handle* h, int S, double varsigma, double* e_total, double* e_var_out, double* e_mean_out) {
+    screen_error_model(h->N, h->variance, h->noise, h->rho_max, h->rho_l2sq, h->alpha_l2, S, varsigma, e_total, e_var_out, e_mean_out);
+}
+
+// automatic mode: the fewest digits whose variance bound is a screening-grade 5 % of the kernel variance, never below the
+// count the survivor feedback of earlier calls asked for
+static int screen_pick_digits(const gpso_handle* h) {
+    for (int S = std::max(SCREEN_S_MIN, h->screen_S_cur); S <= SCREEN_S_MAX; S++) {
+        double e = 0.0, ev = 0.0, em = 0.0;
+        screen_error_bound(h, S, 0.0, &e, &ev, &em);
+        if (ev <= 0.05 * h->variance) return S;
+    }
+    return 0;
+}
+
+// Host-only (no GPU needed): the error bound of the screening pass for a fit with N training points, the given kernel / noise
+// variance, largest power-of-two row scale of L^-1, sum of the squared row scales and |alpha|_2.  out3 = {E, E_var, E_mean}.
+// tests/test_screen_model.py checks it against a numpy emulation of the screening arithmetic.
+extern "C" int gpso_debug_screen_bound(int N, double variance, double noise, double rho_max, double rho_l2sq, double alpha_l2, int digits,
+                                       double varsigma, double* out3) {
+    if (!out3 || N <= 0 || digits < SCREEN_S_MIN || digits > SCREEN_S_MAX) return fail(GPSO_E_BADARG, "gpso_debug_screen_bound: bad argument");
+    screen_error_model(N, variance, noise, rho_max, rho_l2sq, alpha_l2, digits, varsigma, &out3[0], &out3[1], &out3[2]);
+    return 0;
+}
+
+static bool screen_applicable(const gpso_handle* h, long long M) {
+    if (h->screen_mode == 0 || !h->screen_ready || h->oz_S == 0 || h->profile || h->trace) return false;
+    if (h->Np < SCREEN_MIN_NP || M < SCREEN_MIN_M) return false;
+    // the fp32 path needs the kernel variance and the lengthscales well inside the float range
+    if (!(h->variance > 1e-30 && h->variance < 1e30)) return false;
+    for (int i = 0; i < h->n_ls(); i++)
+        if (!(h->ls_host[i] > 1e-30 && h->ls_host[i] < 1e30)) return false;
+    return true;
+}
+
+// The screening pass over all candidates: per window [H2D] -> fp32 cross-covariance digits (+ mean) on the side stream ->
+// low-digit tensor-core product -> screened UCB per candidate + running maximum.  Same stream / event choreography as
+// run_windows.  Leaves scr_ucb[0..M) and scr_state[0] (key of the maximum) on the device.
+static int run_screen_windows(gpso_handle* h, cudaStream_t st, const double* Xc_dev, const double* Xc_host, long long M, int S,
+                              double varsigma, cudaStream_t* product_stream_out) {
+    const bool host = Xc_host != nullptr;
+    const int d = h->d;
+    const long long per_cand = (long long)h->Np * S;
+    long long W = (WINDOW_BYTES / per_cand) / 1024 * 1024;
+    if (h->window_override > 0) W = std::max<long long>(1024, h->window_override / 1024 * 1024);
+    W = std::min(W, ((M + SCR_NT - 1) / SCR_NT) * SCR_NT);
+    const long long nwin = (M + W - 1) / W;
+    const bool overlap = h->overlap && nwin > 1;
+    const int nbuf = overlap ? 2 : 1;
+    GP_TRY(h->part32.ensure((size_t)W * h->nb * sizeof(float)));
+    GP_TRY(h->scr_ucb.ensure((size_t)M * sizeof(double)));
+    GP_TRY(h->scr_state.ensure(4 * sizeof(unsigned long long)));
+    for (int b = 0; b < nbuf; b++) {
+        GP_TRY(h->wmeanb[b].ensure((size_t)W * sizeof(double)));
+        GP_TRY(h->ozBb[b].ensure((size_t)W * per_cand));
+    }
+    if (host) {
+        GP_TRY(h->cand[0].ensure((size_t)W * d * sizeof(double)));
+        GP_TRY(h->cand[1].ensure((size_t)W * d * sizeof(double)));
+    }
+    if (h->screen_built_S != S) {
+        GP_TRY(h->ozAs.ensure((size_t)h->Np * h->Np * S));
+        DISPATCH_SCREEN_S(S, launch_screen_slices, h, st);
+        GP_TRY(check_launch(h, "screen_slices"));
+        h->screen_built_S = S;
+    }
+    CU_TRY(cudaMemsetAsync(h->scr_state.p, 0, 4 * sizeof(unsigned long long), st));
+    // during the screening pass the persisting-L2 window of the product stream covers the low-digit tiles of L^-1
+    GP_TRY(set_l2_window(h, h->ozAs.p, (size_t)h->Np * h->Np * S));
+    cudaStream_t user_st = st;
+    cudaStream_t xs = overlap ? h->aux_stream : st;
+    cudaStream_t cs = h->copy_stream;
+    CU_TRY(cudaEventRecord(h->ev_start, st));
+    if (overlap && st != h->stream) {
+        st = h->stream;
+        CU_TRY(cudaStreamWaitEvent(st, h->ev_start, 0));
+    }
+    if (xs != st) CU_TRY(cudaStreamWaitEvent(xs, h->ev_start, 0));
+    if (host) CU_TRY(cudaStreamWaitEvent(cs, h->ev_start, 0));
+    bool cand_busy[2] = {false, false}, buf_busy[2] = {false, false};
+    const double beta = oz_beta(h);
+    const float bscale = (float)(ldexp(1.0, 8 * S - 2) / beta);
+    const double gscale = beta * ldexp(1.0, -2 * (8 * S - 2) + 8 * (S - 1));
+    for (long long w = 0; w < nwin; w++) {
+        const int cb = (int)(w & 1);
+        const int b = overlap ? cb : 0;
+        const long long off = w * W;
+        const long long Mw = std::min(W, M - off);
+        const long long Mw_pad = ((Mw + SCR_NT - 1) / SCR_NT) * SCR_NT;
+        const double* src;
+        if (host) {
+            if (cand_busy[cb]) CU_TRY(cudaStreamWaitEvent(cs, h->ev_used[cb], 0));
+            CU_TRY(cudaMemcpyAsync(h->cand[cb].p, Xc_host + off * d, (size_t)Mw * d * sizeof(double), cudaMemcpyHostToDevice, cs));
+            CU_TRY(cudaEventRecord(h->ev_copy[cb], cs));
+            CU_TRY(cudaStreamWaitEvent(xs, h->ev_copy[cb], 0));
+            src = h->cand[cb].as<double>();
+        } else {
+            src = Xc_dev + off * d;
+        }
+        if (overlap && buf_busy[b]) CU_TRY(cudaStreamWaitEvent(xs, h->ev_free[b], 0));
+        DISPATCH_SCREEN_S(S, launch_screen_crosscov_s, h, xs, src, Mw, Mw_pad / 64, bscale, h->ozBb[b].as<uint8_t>(), h->wmeanb[b].as<double>());
+        GP_TRY(check_launch(h, "crosscov_screen"));
+        if (host) {
+            CU_TRY(cudaEventRecord(h->ev_used[cb], xs));
+            cand_busy[cb] = true;
+        }
+        if (xs != st) {
+            CU_TRY(cudaEventRecord(h->ev_xcov[b], xs));
+            CU_TRY(cudaStreamWaitEvent(st, h->ev_xcov[b], 0));
+        }
+        GP_TRY(prod_mark(h, st));
+        DISPATCH_SCREEN_S(S, launch_screen_product, h, st, Mw_pad / SCR_NT, Mw_pad, gscale, h->ozBb[b].as<uint8_t>());
+        GP_TRY(check_launch(h, "ozaki_screen"));
+        GP_TRY(prod_mark(h, st));
+        screen_finalize_kernel<<<(unsigned)((Mw + 255) / 256), 256, 0, st>>>(h->part32.as<float>(), h->wmeanb[b].as<double>(), h->nb, Mw_pad, Mw,
+                                                                             off, h->variance, h->noise, varsigma, h->scr_ucb.as<double>(),
+                                                                             h->scr_state.as<unsigned long long>());
+        GP_TRY(check_launch(h, "screen_finalize"));
+        if (overlap) {
+            CU_TRY(cudaEventRecord(h->ev_free[b], st));
+            buf_busy[b] = true;
+        }
+        h->last_windows++;
+    }
+    h->scr_info[6] = (double)nwin;
+    *product_stream_out = st;
+    GP_TRY(set_l2_window(h, h->ozA.p, (size_t)h->Np * h->Np * h->oz_S));  // back on the full-precision tiles (refine pass)
+    if (st != user_st) {
+        CU_TRY(cudaEventRecord(h->ev_start, st));
+        CU_TRY(cudaStreamWaitEvent(user_st, h->ev_start, 0));
+    }
+    return 0;
+}
+
+static int fetch_best(gpso_handle* h, cudaStream_t st, double* result_host);
+
+// Fused predict_y + UCB + arg-max of M candidates (device- or host-resident): screened when it pays, else the plain window
+// pipeline.  The record returned is always produced by the full-precision engine.
+static int score_argmax(gpso_handle* h, cudaStream_t st, const double* Xc_dev, const double* Xc_host, long long M, double varsigma,
+                        double* result_host) {
+    for (int i = 0; i < 12; i++) h->scr_info[i] = 0.0;
+    h->scr_prod_marks = 0;
+    if (screen_applicable(h, M)) {
+        int S = h->screen_mode >= 2 ? std::min(std::max(h->screen_mode, SCREEN_S_MIN), SCREEN_S_MAX) : screen_pick_digits(h);
+        if (S >= h->oz_S) S = 0;  // nothing to gain
+        if (S != 0) {
+            double E = 0.0, e_var = 0.0, e_mean = 0.0;
+            screen_error_bound(h, S, varsigma, &E, &e_var, &e_mean);
+            cudaStream_t pst = st;
+            GP_TRY(run_screen_windows(h, st, Xc_dev, Xc_host, M, S, varsigma, &pst));
+            h->scr_prod_marks = h->prod_used;
+            const unsigned cap = (unsigned)std::min<long long>(SCREEN_LIST_CAP, std::max<long long>(M / 16, 1024));
+            GP_TRY(h->surv_list.ensure((size_t)cap * sizeof(long long)));
+            screen_select_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(h->scr_ucb.as<double>(), M, 2.0 * E,
+                                                                             h->scr_state.as<unsigned long long>(),
+                                                                             h->surv_list.as<long long>(), cap);
+            GP_TRY(check_launch(h, "screen_select"));
+            unsigned long long state[4] = {0, 0, 0, 0};
+            CU_TRY(cudaMemcpyAsync(state, h->scr_state.p, sizeof state, cudaMemcpyDeviceToHost, st));
+            CU_TRY(cudaStreamSynchronize(st));
+            const long long count = (long long)state[1];
+            h->scr_info[1] = S;
+            h->scr_info[2] = (double)count;
+            h->scr_info[3] = E;
+            h->scr_info[5] = scr_unkey(state[0]);
+            h->scr_info[9] = e_var;
+            h->scr_info[10] = e_mean;
+            // the digit count adapts to the survivor fraction (automatic mode): too many survivors -> one digit more next time
+            if (h->screen_mode == 1 && count * 64 > M && h->screen_S_cur < SCREEN_S_MAX) h->screen_S_cur++;
+            if (count >= 1 && count <= (long long)cap) {
+                const long long windows_before = h->last_windows;
+                std::vector<double> gathered;
+                const double* rdev = nullptr;
+                const double* rhost = nullptr;
+                if (Xc_host != nullptr) {
+                    std::vector<long long> list((size_t)count);
+                    CU_TRY(cudaMemcpyAsync(list.data(), h->surv_list.p, (size_t)count * sizeof(long long), cudaMemcpyDeviceToHost, st));
+                    CU_TRY(cudaStreamSynchronize(st));
+                    gathered.resize((size_t)count * h->d);
+                    for (long long i = 0; i < count; i++)
+                        memcpy(&gathered[(size_t)i * h->d], Xc_host + list[(size_t)i] * h->d, sizeof(double) * h->d);
+                    rhost = gathered.data();
+                } else {
+                    GP_TRY(h->surv_X.ensure((size_t)count * h->d * sizeof(double)));
+                    gather_rows_kernel<<<(unsigned)((count * h->d + 255) / 256), 256, 0, st>>>(Xc_dev, h->surv_list.as<long long>(), count, h->d,
+                                                                                            h->surv_X.as<double>());
+                    GP_TRY(check_launch(h, "gather_rows"));
+                    rdev = h->surv_X.as<double>();
+                }
+                h->rw_idx_map = h->surv_list.as<long long>();
+                h->rw_check = true;
+                int rc = run_windows(h, st, rdev, rhost, count, 1, varsigma, nullptr, nullptr);
+                h->rw_idx_map = nullptr;
+                h->rw_check = false;
+                GP_TRY(rc);
+                unsigned long long dbits = 0;
+                CU_TRY(cudaMemcpyAsync(&dbits, h->scr_state.as<unsigned long long>() + 2, sizeof dbits, cudaMemcpyDeviceToHost, st));
+                GP_TRY(fetch_best(h, st, result_host));  // synchronises st
+                double dmax;
+                memcpy(&dmax, &dbits, sizeof dmax);
+                h->scr_info[4] = dmax;
+                h->scr_info[8] = (double)(h->last_windows - windows_before);
+                if (dmax <= 0.25 * E) {
+                    h->scr_info[0] = 1.0;
+                    return 0;
+                }
+                h->scr_info[0] = 3.0;  // the bound did not hold with the required margin: do not trust the screen
+                if (h->screen_mode == 1 && h->screen_S_cur < SCREEN_S_MAX) h->screen_S_cur++;
+            } else {
+                h->scr_info[0] = 2.0;
+            }
+        }
+    }
+    GP_TRY(run_windows(h, st, Xc_dev, Xc_host, M, 1, varsigma, nullptr, nullptr));
+    return fetch_best(h, st, result_host);
+}
+
 extern "C" int gpso_predict_y_dev(gpso_handle* h, const double* Xc_dev, int64_t M, double* mean_dev, double* var_dev,
                                   void* stream) {
     GP_TRY(predict_common_checks(h, Xc_dev, M, "gpso_predict_y_dev"));
@@ -1382,9 +1750,9 @@ extern "C" int gpso_ucb_argmax_dev(gpso_handle* h, const double* Xc_dev, int64_t
     if (!result_host) return fail(GPSO_E_BADARG, "gpso_ucb_argmax_dev: null output");
     cudaStream_t st = (cudaStream_t)stream;
     CU_TRY(cudaEventRecord(h->ev_t0, st));
-    GP_TRY(run_windows(h, st, Xc_dev, nullptr, M, 1, varsigma, nullptr, nullptr));
+    GP_TRY(score_argmax(h, st, Xc_dev, nullptr, M, varsigma, result_host));
     CU_TRY(cudaEventRecord(h->ev_t1, st));
-    GP_TRY(fetch_best(h, st, result_host));
+    CU_TRY(cudaEventSynchronize(h->ev_t1));
     float ms = 0;
     cudaEventElapsedTime(&ms, h->ev_t0, h->ev_t1);
     h->last_ms[0] = ms;
@@ -1409,9 +1777,9 @@ extern "C" int gpso_ucb_argmax_host(gpso_handle* h, const double* Xc_host, int64
     GP_TRY(predict_common_checks(h, Xc_host, M, "gpso_ucb_argmax_host"));
     if (!result_host) return fail(GPSO_E_BADARG, "gpso_ucb_argmax_host: null output");
     CU_TRY(cudaEventRecord(h->ev_t0, h->stream));
-    GP_TRY(run_windows(h, h->stream, nullptr, Xc_host, M, 1, varsigma, nullptr, nullptr));
+    GP_TRY(score_argmax(h, h->stream, nullptr, Xc_host, M, varsigma, result_host));
     CU_TRY(cudaEventRecord(h->ev_t1, h->stream));
-    GP_TRY(fetch_best(h, h->stream, result_host));
+    CU_TRY(cudaEventSynchronize(h->ev_t1));
     float ms = 0;
     cudaEventElapsedTime(&ms, h->ev_t0, h->ev_t1);
     h->last_ms[0] = ms;
@@ -1548,9 +1916,9 @@ extern "C" int gpso_grow_ucb_argmax(gpso_handle* h, const double* bounds_host, i
     CU_TRY(cudaMemcpyAsync(bdev, bounds_host, sizeof(double) * 2 * d, cudaMemcpyHostToDevice, st));
     grow_leaves_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, st>>>(bdev, d, depth, rows, h->leaves.as<double>());
     GP_TRY(check_launch(h, "grow_leaves"));
-    GP_TRY(run_windows(h, st, h->leaves.as<double>(), nullptr, rows, 1, varsigma, nullptr, nullptr));
+    GP_TRY(score_argmax(h, st, h->leaves.as<double>(), nullptr, rows, varsigma, result_host));
     CU_TRY(cudaEventRecord(h->ev_t1, st));
-    GP_TRY(fetch_best(h, st, result_host));
+    CU_TRY(cudaEventSynchronize(h->ev_t1));
     float ms = 0;
     cudaEventElapsedTime(&ms, h->ev_t0, h->ev_t1);
     h->last_ms[0] = ms;
@@ -1765,6 +2133,73 @@ extern "C" int gpso_predict_info(gpso_handle* h, double* out3) {
     out3[0] = h->oz_S ? 2.0 : 1.0;
     out3[1] = (double)h->oz_S;
     out3[2] = h->oz_est;
+    return 0;
+}
+
+extern "C" int gpso_set_screen_mode(gpso_handle* h, int mode) {
+    if (!h || mode < 0 || mode > SCREEN_S_MAX) return fail(GPSO_E_BADARG, "gpso_set_screen_mode: mode must be 0 (off), 1 (automatic) or 2..4 (digits)");
+    h->screen_mode = mode;
+    h->screen_S_cur = SCREEN_S_MIN;
+    h->factorized = false;  // the fp32 copies are prepared by the next gpso_factorize
+    return 0;
+}
+
+extern "C" int gpso_screen_info(gpso_handle* h, double* out12) {
+    if (!h || !out12) return fail(GPSO_E_BADARG, "gpso_screen_info: null argument");
+    for (int i = 0; i < 12; i++) out12[i] = h->scr_info[i];
+    return 0;
+}
+
+// Pipe peaks of this GPU, measured now (best of 3 launches each, CUDA events on the default stream; ~0.2 s in total):
+// out[0] int8 tensor TOP/s (tcgen05 kind::i8, M=128 N=256, one issuing thread per SM), out[1] FP64 TFLOP/s (DMMA.8x8x4),
+// out[2] L2 -> shared-memory bulk-copy GB/s (24 KB chunks, 8 in flight per SM, 64 MB working set), out[3] number of SMs.
+extern "C" int gpso_probe_peaks(int device, double* out4) {
+    if (!out4) return fail(GPSO_E_BADARG, "gpso_probe_peaks: null argument");
+    CU_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU_TRY(cudaGetDeviceProperties(&prop, device));
+    const int nsm = prop.multiProcessorCount;
+    cudaEvent_t e0, e1;
+    CU_TRY(cudaEventCreate(&e0));
+    CU_TRY(cudaEventCreate(&e1));
+    DevBuf sink, dout, src;
+    GP_TRY(sink.ensure(64, true));
+    auto best_of = [&](auto launch, double* best_ms) -> int {
+        *best_ms = 1e30;
+        for (int r = 0; r < 4; r++) {  // the first launch warms up
+            CU_TRY(cudaEventRecord(e0, 0));
+            launch();
+            CU_TRY(cudaEventRecord(e1, 0));
+            CU_TRY(cudaEventSynchronize(e1));
+            if (cudaGetLastError() != cudaSuccess) return fail(GPSO_E_CUDA, "gpso_probe_peaks: probe launch failed");
+            float ms = 0;
+            cudaEventElapsedTime(&ms, e0, e1);
+            if (r > 0) *best_ms = std::min(*best_ms, (double)ms);
+        }
+        return 0;
+    };
+    double ms = 0.0;
+    // int8 tensor pipe
+    const int iters8 = 200000;
+    const int smem8 = 2 * (4096 + 256 * 32);
+    CU_TRY(cudaFuncSetAttribute(probe_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem8));
+    GP_TRY(best_of([&] { probe_i8_kernel<<<nsm, 128, smem8>>>(iters8, sink.as<int>()); }, &ms));
+    out4[0] = 2.0 * 128 * 256 * 32 * (double)(iters8 / 2 * 2) * nsm / (ms * 1e-3) / 1e12;
+    // FP64 pipe
+    const int iters64 = 20000, blocks = nsm * 4;
+    GP_TRY(dout.ensure((size_t)blocks * 256 * sizeof(double)));
+    GP_TRY(best_of([&] { probe_dmma_kernel<<<blocks, 256>>>(dout.as<double>(), iters64, 1.0000001, 0.9999999); }, &ms));
+    out4[1] = 2.0 * 8 * 8 * 4 * 16.0 * iters64 * (double)blocks * 8 / (ms * 1e-3) / 1e12;
+    // L2 -> SMEM bulk copies
+    const int chunk = 24576, per_cta = 4096;
+    const size_t bytes = (size_t)64 << 20;
+    GP_TRY(src.ensure(bytes, true));
+    CU_TRY(cudaFuncSetAttribute(probe_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * chunk));
+    GP_TRY(best_of([&] { probe_bulk_kernel<<<nsm, 128, 8 * chunk>>>(src.as<uint8_t>(), bytes / chunk, chunk, per_cta); }, &ms));
+    out4[2] = (double)per_cta * nsm * chunk / (ms * 1e-3) / 1e9;
+    out4[3] = nsm;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
     return 0;
 }
 

@@ -112,12 +112,15 @@ struct BestRec {
 };
 
 // mode 0: write mean/var for candidates [0, Mw) of the window to out_mean/out_var (already offset to the window)
-// mode 1: per-block best record -> blockbest[blockIdx.x]
+// mode 1: per-block best record -> blockbest[blockIdx.x] (mean/var are written too when out_mean is given)
+// idx_map (optional): global index of window candidate c is idx_map[idx0 + c] instead of idx0 + c (refine pass of the
+// screened arg-max: the window holds a gathered subset of the caller's candidates)
 __global__ void __launch_bounds__(256) predict_finalize_kernel(const double* __restrict__ part, const double* __restrict__ mean,
                                                                int nb, int ldp, long long Mw, long long idx0, double variance,
                                                                double noise, double varsigma, int mode,
                                                                double* __restrict__ out_mean, double* __restrict__ out_var,
-                                                               BestRec* __restrict__ blockbest) {
+                                                               BestRec* __restrict__ blockbest,
+                                                               const long long* __restrict__ idx_map) {
     long long c = (long long)blockIdx.x * 256 + threadIdx.x;
     double m = 0.0, v = 0.0, u = 0.0;
     bool valid = c < Mw;
@@ -128,15 +131,13 @@ __global__ void __launch_bounds__(256) predict_finalize_kernel(const double* __r
         v = __dadd_rn(__dsub_rn(variance, ss), noise);
         u = __dadd_rn(m, __dmul_rn(varsigma, v));
     }
-    if (mode == 0) {
-        if (valid) {
-            out_mean[c] = m;
-            out_var[c] = v;
-        }
-        return;
+    if (out_mean != nullptr && valid) {
+        out_mean[c] = m;
+        out_var[c] = v;
     }
+    if (mode == 0) return;
     // block arg-max, numpy semantics (first NaN wins; lowest index on ties)
-    long long gi = valid ? idx0 + c : 0x7fffffffffffffffLL;
+    long long gi = valid ? (idx_map != nullptr ? idx_map[idx0 + c] : idx0 + c) : 0x7fffffffffffffffLL;
     double bu = valid ? u : -INFINITY, bm = m, bv = v;
     long long bi = gi;
 #pragma unroll

@@ -161,32 +161,48 @@ def restart_points(u0, n_restarts, seed=20240517):
     return starts
 
 
+def _rank_world(group=None):
+    """(rank, world) of this process; (0, 1) when torch.distributed is not initialised (single-process use)."""
+    try:
+        dist = _dist()
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank(group), dist.get_world_size(group)
+    except ImportError:
+        pass
+    return 0, 1
+
+
 def sharded_multistart_fit(objective, u0, n_restarts, group=None, seed=20240517, maxiter=50, on_error=np.inf):
     """
     Multi-start L-BFGS-B with the restarts dealt round-robin over the ranks.  ``objective(u) -> (f, grad)`` is this
     rank's device closure (``model.neg_log_marginal_likelihood_and_grad``).  Returns (u_best, f_best, restart_id, table)
-    identically on every rank; ``table[i] = (f_i, restart i's optimum)``.
+    identically on every rank; ``table[i] = (f_i, restart i's optimum)``.  Restart 0 is the warm start ``u0`` itself, so
+    ``n_restarts=1`` with ``maxiter=None`` (SciPy's default budget) is the reference's single fit.  Works without an
+    initialised process group (all restarts run here).
     """
-    import torch
-
-    dist = _dist()
-    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    rank, world = _rank_world(group)
     starts = restart_points(u0, n_restarts, seed)
     p = len(u0)
+    options = {} if maxiter is None else {"maxiter": maxiter}
     mine = np.full((n_restarts, p + 1), np.nan)
     for i in range(rank, n_restarts, world):
         try:
-            res = scipy.optimize.minimize(objective, starts[i], jac=True, method="L-BFGS-B", options={"maxiter": maxiter})
+            res = scipy.optimize.minimize(objective, starts[i], jac=True, method="L-BFGS-B", options=options)
             mine[i, 0], mine[i, 1:] = res.fun, res.x
         except np.linalg.LinAlgError:
             mine[i, 0], mine[i, 1:] = on_error, starts[i]
-    dev = _comm_device(group)
-    local = torch.tensor(mine, dtype=torch.float64, device=dev)
-    parts = [torch.empty_like(local) for _ in range(world)]
-    dist.all_gather(parts, local, group=group)
-    # row i is taken verbatim from its owner (rank i mod W): a restart whose own optimum is NaN/inf stays non-finite here and
-    # is ranked last below, instead of turning into a spurious f = 0 under a SUM reduction
-    table = np.stack([parts[i % world][i].cpu().numpy() for i in range(n_restarts)])
+    if world > 1:
+        import torch
+
+        dist = _dist()
+        local = torch.tensor(mine, dtype=torch.float64, device=_comm_device(group))
+        parts = [torch.empty_like(local) for _ in range(world)]
+        dist.all_gather(parts, local, group=group)
+        # row i is taken verbatim from its owner (rank i mod W): a restart whose own optimum is NaN/inf stays non-finite here
+        # and is ranked last below, instead of turning into a spurious f = 0 under a SUM reduction
+        table = np.stack([parts[i % world][i].cpu().numpy() for i in range(n_restarts)])
+    else:
+        table = mine
     f = np.where(np.isfinite(table[:, 0]), table[:, 0], np.inf)
     best = int(np.argmin(f))  # first minimum = lowest restart id on ties
     return table[best, 1:].copy(), float(f[best]), best, table
