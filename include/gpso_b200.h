@@ -98,6 +98,10 @@ int gpso_grow_leaves_dev(int device, const double* bounds_host, int d, int depth
 /* child.grow(depth) fused with gp_eval_best_ucb: optimisation.py:379-381.  Leaves never leave the device. */
 int gpso_grow_ucb_argmax(gpso_handle* h, const double* bounds_host, int d, int depth, double varsigma,
                          double* result_host);
+/* The same for rows [row0, row1) of the batch only (a rank of a candidate-sharded run scores its own slice of the leaf batch,
+ * reference call site gpso/optimisation.py:379-381); result_host[0] is the row number inside the FULL batch. */
+int gpso_grow_ucb_argmax_range(gpso_handle* h, const double* bounds_host, int d, int depth, double varsigma, int64_t row0,
+                               int64_t row1, double* result_host);
 
 /* ---- multi-GPU: share one fit with the ranks that score candidate shards -------------------------------------- */
 /* The fitted state (theta, scaled training inputs, alpha, L^-1) is exposed as ONE contiguous device buffer so the host

@@ -90,6 +90,7 @@ def load_library():
         "gpso_grow_leaves_host": (i32, [i32, _c_double_p, i32, i32, _c_double_p]),
         "gpso_grow_leaves_dev": (i32, [i32, _c_double_p, i32, i32, ctypes.c_void_p, ctypes.c_void_p]),
         "gpso_grow_ucb_argmax": (i32, [H, _c_double_p, i32, i32, dbl, _c_double_p]),
+        "gpso_grow_ucb_argmax_range": (i32, [H, _c_double_p, i32, i32, dbl, i64, i64, _c_double_p]),
         "gpso_state_bytes": (i32, [H, i32, i32, ctypes.POINTER(i64)]),
         "gpso_export_state_dev": (i32, [H, ctypes.c_void_p, i64, ctypes.c_void_p]),
         "gpso_import_state_dev": (i32, [H, ctypes.c_void_p, i64, i32, i32, ctypes.c_void_p]),
@@ -132,7 +133,7 @@ EXPORTED_SYMBOLS = (
     "gpso_version gpso_last_error gpso_device_count gpso_create gpso_destroy gpso_set_data gpso_neg_lml_grad "
     "gpso_factorize gpso_factor_lml gpso_predict_y_host gpso_predict_y_dev gpso_ucb_argmax_host gpso_ucb_argmax_dev "
     "gpso_ucb_topk_host gpso_ucb_topk_dev "
-    "gpso_grow_count gpso_grow_leaves_host gpso_grow_leaves_dev gpso_grow_ucb_argmax gpso_state_bytes "
+    "gpso_grow_count gpso_grow_leaves_host gpso_grow_leaves_dev gpso_grow_ucb_argmax gpso_grow_ucb_argmax_range gpso_state_bytes "
     "gpso_export_state_dev gpso_import_state_dev gpso_launch_count gpso_debug_fetch gpso_last_timing gpso_set_window "
     "gpso_set_profile gpso_last_windows gpso_set_predict_mode gpso_predict_info gpso_set_overlap "
     "gpso_set_factor_mode gpso_debug_factor_tasks gpso_debug_trace gpso_set_kinv_mode gpso_set_inverse_mode gpso_set_l2_window gpso_debug_product_items "
@@ -239,11 +240,17 @@ class CudaSession:
                                                       stream), "gpso_ucb_topk_dev")
         return out[: found.value]
 
-    def grow_ucb_argmax(self, bounds, depth, varsigma):
+    def grow_ucb_argmax(self, bounds, depth, varsigma, rows=None):
+        """Arg-max over the ``grow(depth)`` leaf batch of the box, or over its rows ``[rows[0], rows[1])`` only (index = row
+        number in the full batch either way)."""
         bounds = np.ascontiguousarray(bounds, dtype=np.float64)
         out = np.empty(4)
-        _check(self._lib, self._lib.gpso_grow_ucb_argmax(self._h, _dptr(bounds), bounds.shape[0], int(depth), float(varsigma),
-                                                         _dptr(out)), "gpso_grow_ucb_argmax")
+        if rows is None:
+            _check(self._lib, self._lib.gpso_grow_ucb_argmax(self._h, _dptr(bounds), bounds.shape[0], int(depth), float(varsigma),
+                                                             _dptr(out)), "gpso_grow_ucb_argmax")
+        else:
+            _check(self._lib, self._lib.gpso_grow_ucb_argmax_range(self._h, _dptr(bounds), bounds.shape[0], int(depth), float(varsigma),
+                                                                   int(rows[0]), int(rows[1]), _dptr(out)), "gpso_grow_ucb_argmax_range")
         return int(out[0]), float(out[1]), float(out[2]), float(out[3])
 
     # -- device-pointer variants (benchmarks, multi-GPU sharding): pointers are ints (e.g. torch.Tensor.data_ptr()) -----

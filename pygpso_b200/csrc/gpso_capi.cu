@@ -275,7 +275,10 @@ static int screen_configure() {
     return 0;
 }
 
-static size_t screen_xcov_smem(int d) { return (size_t)(64 * d + 2 * d * OZ_XK + 2 * OZ_XK) * sizeof(float) + 8 * 64 * sizeof(double); }
+static size_t screen_xcov_smem(int d) {
+    static const int pad_env = getenv("GPSO_SCR_XCOV_PAD") ? atoi(getenv("GPSO_SCR_XCOV_PAD")) : 0;  // co-residency experiments
+    return (size_t)(64 * d + 2 * d * OZ_XK + 2 * OZ_XK) * sizeof(float) + 8 * 64 * sizeof(double) + pad_env;
+}
 
 template <int KID, int S>
 static void launch_screen_crosscov(gpso_handle* h, cudaStream_t st, const double* Xc, long long Mw, long long ngroups, float bscale,
@@ -308,9 +311,14 @@ static void launch_screen_product(gpso_handle* h, cudaStream_t st, long long nct
     P.nks = h->Np / 32;
     P.nct = (int)nct;
     P.ldp = ldp;
+    // ring depth: the whole budget unless GPSO_SCR_STAGES asks for less (co-residency experiments)
+    static const int stages_env = getenv("GPSO_SCR_STAGES") ? atoi(getenv("GPSO_SCR_STAGES")) : 0;
+    using Cfg = ScrCfg<S, SCR_NT>;
+    P.stages = (stages_env >= 2 && stages_env < Cfg::STAGES) ? stages_env : Cfg::STAGES;
+    const size_t smem = (size_t)P.stages * Cfg::STAGE_BYTES + (Cfg::SMEM_BYTES - Cfg::RING_BYTES);
     const long long units = nct * ((h->nb + 1) / 2);
     const int grid = (int)std::min<long long>(h->nsm, units);
-    ozaki_screen_kernel<S, SCR_NT><<<grid, OZ_THREADS, ScrCfg<S, SCR_NT>::SMEM_BYTES, st>>>(P);
+    ozaki_screen_kernel<S, SCR_NT><<<grid, OZ_THREADS, smem, st>>>(P);
 }
 
 template <int S>
@@ -1057,7 +1065,8 @@ extern "C" int gpso_create(int device, int kernel_id, int ard, int mean_id, gpso
     // the (default-priority) cross-covariance blocks of the next window when both become eligible at the same time
     int prio_least = 0, prio_greatest = 0;
     CU_TRY(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
-    CU_TRY(cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, prio_greatest));
+    static const int prio_env = getenv("GPSO_PRODUCT_PRIO") ? atoi(getenv("GPSO_PRODUCT_PRIO")) : 1;  // 0: default priority (experiments)
+    CU_TRY(cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, prio_env ? prio_greatest : prio_least));
     CU_TRY(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
     CU_TRY(cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
     CU_TRY(cudaEventCreateWithFlags(&h->ev_start, cudaEventDisableTiming));
@@ -1546,7 +1555,7 @@ extern "C" int gpso_debug_screen_bound(int N, double variance, double noise, dou
 }
 
 static bool screen_applicable(const gpso_handle* h, long long M) {
-    if (h->screen_mode == 0 || !h->screen_ready || h->oz_S == 0 || h->profile || h->trace) return false;
+    if (h->screen_mode == 0 || !h->screen_ready || h->oz_S == 0 || h->profile) return false;
     if (h->Np < SCREEN_MIN_NP || M < SCREEN_MIN_M) return false;
     // the fp32 path needs the kernel variance and the lengthscales well inside the float range
     if (!(h->variance > 1e-30 && h->variance < 1e30)) return false;
@@ -1620,8 +1629,10 @@ static int run_screen_windows(gpso_handle* h, cudaStream_t st, const double* Xc_
             src = Xc_dev + off * d;
         }
         if (overlap && buf_busy[b]) CU_TRY(cudaStreamWaitEvent(xs, h->ev_free[b], 0));
+        GP_TRY(trace_mark(h, xs, 1, w));
         DISPATCH_SCREEN_S(S, launch_screen_crosscov_s, h, xs, src, Mw, Mw_pad / 64, bscale, h->ozBb[b].as<uint8_t>(), h->wmeanb[b].as<double>());
         GP_TRY(check_launch(h, "crosscov_screen"));
+        GP_TRY(trace_mark(h, xs, 2, w));
         if (host) {
             CU_TRY(cudaEventRecord(h->ev_used[cb], xs));
             cand_busy[cb] = true;
@@ -1631,13 +1642,16 @@ static int run_screen_windows(gpso_handle* h, cudaStream_t st, const double* Xc_
             CU_TRY(cudaStreamWaitEvent(st, h->ev_xcov[b], 0));
         }
         GP_TRY(prod_mark(h, st));
+        GP_TRY(trace_mark(h, st, 3, w));
         DISPATCH_SCREEN_S(S, launch_screen_product, h, st, Mw_pad / SCR_NT, Mw_pad, gscale, h->ozBb[b].as<uint8_t>());
         GP_TRY(check_launch(h, "ozaki_screen"));
+        GP_TRY(trace_mark(h, st, 4, w));
         GP_TRY(prod_mark(h, st));
         screen_finalize_kernel<<<(unsigned)((Mw + 255) / 256), 256, 0, st>>>(h->part32.as<float>(), h->wmeanb[b].as<double>(), h->nb, Mw_pad, Mw,
                                                                              off, h->variance, h->noise, varsigma, h->scr_ucb.as<double>(),
                                                                              h->scr_state.as<unsigned long long>());
         GP_TRY(check_launch(h, "screen_finalize"));
+        GP_TRY(trace_mark(h, st, 5, w));
         if (overlap) {
             CU_TRY(cudaEventRecord(h->ev_free[b], st));
             buf_busy[b] = true;
@@ -1894,17 +1908,23 @@ extern "C" int gpso_grow_leaves_host(int device, const double* bounds_host, int 
     return rc;
 }
 
-extern "C" int gpso_grow_ucb_argmax(gpso_handle* h, const double* bounds_host, int d, int depth, double varsigma,
-                                    double* result_host) {
+// Rows [row0, row1) of the grow(depth) batch of the box: generated on the device, scored, reduced to their arg-max.  The index
+// returned is the row number inside the FULL batch, so the records of several ranks (each with its own row range) merge like
+// those of gpso_ucb_argmax_* with a global offset.
+extern "C" int gpso_grow_ucb_argmax_range(gpso_handle* h, const double* bounds_host, int d, int depth, double varsigma, int64_t row0,
+                                          int64_t row1, double* result_host) {
     if (!h || !bounds_host || !result_host) return fail(GPSO_E_BADARG, "gpso_grow_ucb_argmax: null argument");
     if (!h->factorized) return fail(GPSO_E_STATE, "gpso_grow_ucb_argmax: call gpso_factorize first");
     h->prof_used = 0;
     h->prod_used = 0;
+    h->trace_used = 0;
     h->last_windows = 0;
     if (d != h->d) return fail(GPSO_E_BADARG, "gpso_grow_ucb_argmax: dimension differs from the training data");
     GP_TRY(set_device(h));
-    long long rows = gpso_grow_count(depth);
-    if (rows <= 0) return fail(GPSO_E_BADARG, "gpso_grow_ucb_argmax: bad depth");
+    const long long total = gpso_grow_count(depth);
+    if (total <= 0) return fail(GPSO_E_BADARG, "gpso_grow_ucb_argmax: bad depth");
+    if (row0 < 0 || row1 > total || row0 >= row1) return fail(GPSO_E_BADARG, "gpso_grow_ucb_argmax: empty or out-of-range row range");
+    const long long rows = row1 - row0;
     GP_TRY(h->leaves.ensure((size_t)rows * d * sizeof(double) + sizeof(double) * 2 * LEAF_MAXD));
     // bounds live at the tail of the leaves buffer
     double* bdev = h->leaves.as<double>() + (size_t)rows * d;
@@ -1914,7 +1934,7 @@ extern "C" int gpso_grow_ucb_argmax(gpso_handle* h, const double* bounds_host, i
     if (depth < 1 || depth > 20) return fail(GPSO_E_BADARG, "gpso_grow_ucb_argmax: depth must be in 1..20");
     CU_TRY(cudaEventRecord(h->ev_t0, st));
     CU_TRY(cudaMemcpyAsync(bdev, bounds_host, sizeof(double) * 2 * d, cudaMemcpyHostToDevice, st));
-    grow_leaves_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, st>>>(bdev, d, depth, rows, h->leaves.as<double>());
+    grow_leaves_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, st>>>(bdev, d, depth, rows, h->leaves.as<double>(), row0);
     GP_TRY(check_launch(h, "grow_leaves"));
     GP_TRY(score_argmax(h, st, h->leaves.as<double>(), nullptr, rows, varsigma, result_host));
     CU_TRY(cudaEventRecord(h->ev_t1, st));
@@ -1922,7 +1942,13 @@ extern "C" int gpso_grow_ucb_argmax(gpso_handle* h, const double* bounds_host, i
     float ms = 0;
     cudaEventElapsedTime(&ms, h->ev_t0, h->ev_t1);
     h->last_ms[0] = ms;
+    result_host[0] += (double)row0;
     return 0;
+}
+
+extern "C" int gpso_grow_ucb_argmax(gpso_handle* h, const double* bounds_host, int d, int depth, double varsigma,
+                                    double* result_host) {
+    return gpso_grow_ucb_argmax_range(h, bounds_host, d, depth, varsigma, 0, gpso_grow_count(depth), result_host);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

@@ -15,10 +15,13 @@ namespace gpso {
 
 constexpr int LEAF_MAXD = 64;
 
+// Rows [row0, row0 + nrows) of the batch go to out[0 .. nrows) (a rank of a candidate-sharded run generates only its shard).
 __global__ void __launch_bounds__(128) grow_leaves_kernel(const double* __restrict__ bounds /* [d][2] */, int d, int depth,
-                                                          long long nrows, double* __restrict__ out /* [nrows][d] */) {
-    long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= nrows) return;
+                                                          long long nrows, double* __restrict__ out /* [nrows][d] */,
+                                                          long long row0 = 0) {
+    const long long local = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (local >= nrows) return;
+    const long long r = row0 + local;
     // level of row r: offsets (3^l - 1)/2
     int level = 0;
     long long off = 0, width = 1;  // width = 3^level
@@ -53,7 +56,7 @@ __global__ void __launch_bounds__(128) grow_leaves_kernel(const double* __restri
         lo[k] = c0;
         hi[k] = c1;
     }
-    for (int j = 0; j < d; j++) out[r * d + j] = __dmul_rn(__dadd_rn(lo[j], hi[j]), 0.5);
+    for (int j = 0; j < d; j++) out[local * d + j] = __dmul_rn(__dadd_rn(lo[j], hi[j]), 0.5);
 }
 
 }  // namespace gpso

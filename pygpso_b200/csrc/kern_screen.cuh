@@ -52,6 +52,7 @@ struct ScrParams {
     double gscale;
     int nb, nks, nct;
     long long ldp;
+    int stages;              // ring depth in use (<= ScrCfg::STAGES; the launch passes the matching dynamic shared memory)
 };
 
 // ---- FP32 covariance (screening only) -----------------------------------------------------------------------------------
@@ -219,13 +220,15 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_screen_kernel(ScrParams P
     constexpr int NBUF = Cfg::NBUF;
     extern __shared__ __align__(1024) uint8_t scr_smem_raw[];
     uint8_t* ring = scr_smem_raw;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(scr_smem_raw + Cfg::RING_BYTES);
+    const int nstages = P.stages;  // ring depth in use; barriers and scratch follow the ring
+    const size_t ring_bytes = (size_t)nstages * Cfg::STAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(scr_smem_raw + ring_bytes);
     uint64_t* full = bars;                      // [STAGES]
     uint64_t* empty = bars + STAGES;            // [STAGES]
     uint64_t* tmem_full = bars + 2 * STAGES;    // [2]
     uint64_t* tmem_empty = tmem_full + 2;       // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-    float* red = reinterpret_cast<float*>(scr_smem_raw + Cfg::RING_BYTES + 1024);  // [4][NT]
+    float* red = reinterpret_cast<float*>(scr_smem_raw + ring_bytes + 1024);  // [4][NT]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -271,7 +274,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_screen_kernel(ScrParams P
                     oz_mbar_expect_tx(&full[st], Cfg::STAGE_BYTES);
                     oz_bulk_g2s_hint(dst, a + (size_t)ks * Cfg::A_BYTES, Cfg::A_BYTES, &full[st], keep);
                     oz_bulk_g2s(dst + Cfg::A_BYTES, b + (size_t)ks * Cfg::B_BYTES, Cfg::B_BYTES, &full[st]);
-                    if (++st == STAGES) {
+                    if (++st == nstages) {
                         st = 0;
                         ph ^= 1;
                     }
@@ -307,7 +310,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_screen_kernel(ScrParams P
                         }
                     }
                     oz_commit(&empty[st]);
-                    if (++st == STAGES) {
+                    if (++st == nstages) {
                         st = 0;
                         ph ^= 1;
                     }

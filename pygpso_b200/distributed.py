@@ -111,16 +111,32 @@ class ShardedScorer:
 
     # -- one exchange per fit -----------------------------------------------------------------------------------------
     def broadcast_fit(self, n, d, src=0):
-        """Broadcast the fitted state of rank ``src`` to every rank's session (NCCL, one contiguous buffer)."""
+        """Broadcast the fitted state of rank ``src`` to every rank's session: one contiguous device buffer
+        (``gpso_export_state_dev`` -> broadcast -> ``gpso_import_state_dev``) over NCCL; with gloo the same buffer is staged
+        through host memory.  Sessions without device state (the checker backend of the CPU tests) exchange
+        ``get_state()`` / ``set_state()`` objects."""
         import torch
 
         dist = _dist()
+        if not hasattr(self.session, "export_state_dev"):
+            box = [self.session.get_state() if self.rank == src else None]
+            dist.broadcast_object_list(box, src=src, group=self.group)
+            if self.rank != src:
+                self.session.set_state(box[0])
+            return 0
         nbytes = self.session.state_bytes(n, d)
-        buf = torch.empty(nbytes, dtype=torch.uint8, device=_comm_device(self.group))
+        dev = torch.device("cuda", torch.cuda.current_device())
+        buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         stream = torch.cuda.current_stream().cuda_stream
         if self.rank == src:
             self.session.export_state_dev(buf.data_ptr(), nbytes, stream)
-        dist.broadcast(buf, src=src, group=self.group)
+        if _comm_device(self.group).type == "cuda":
+            dist.broadcast(buf, src=src, group=self.group)
+        else:
+            staged = buf.cpu()
+            dist.broadcast(staged, src=src, group=self.group)
+            if self.rank != src:
+                buf.copy_(staged)
         if self.rank != src:
             torch.cuda.current_stream().synchronize()
             self.session.import_state_dev(buf.data_ptr(), nbytes, n, d, stream)
@@ -145,6 +161,17 @@ class ShardedScorer:
             local = np.asarray(self.session.ucb_topk(x_local, varsigma, k), dtype=np.float64).reshape(-1, 4)
             mine[: len(local)] = np.column_stack([local[:, 3], local[:, 0] + global_offset, local[:, 1], local[:, 2]])
         return merge_topk(gather_records(mine, self.group), k)
+
+    def grow_ucb_argmax(self, bounds, depth, varsigma):
+        """``gp_eval_best_ucb(leaf.grow(depth))`` with the rows of the leaf batch sharded over the ranks: every rank generates
+        and scores its own contiguous slice on its GPU (no candidate ever crosses a link), one record per rank is gathered."""
+        total = (3 ** int(depth) - 1) // 2
+        start, stop = shard_bounds(total, self.world, self.rank)
+        record = [-np.inf, -1.0, 0.0, 0.0]
+        if stop > start:
+            idx, mean, var, ucb = self.session.grow_ucb_argmax(bounds, depth, varsigma, rows=(start, stop))
+            record = [ucb, float(idx), mean, var]
+        return pick_best(gather_records(record, self.group))
 
     def ucb_argmax_full(self, x_all, varsigma):
         """Convenience: every rank holds the full candidate matrix and scores only its own contiguous shard."""
@@ -206,3 +233,48 @@ def sharded_multistart_fit(objective, u0, n_restarts, group=None, seed=20240517,
     f = np.where(np.isfinite(table[:, 0]), table[:, 0], np.inf)
     best = int(np.argmin(f))  # first minimum = lowest restart id on ties
     return table[best, 1:].copy(), float(f[best]), best, table
+
+
+def multistart_fit(surrogate, model, n_restarts, group=None, seed=20240517, maxiter=50):
+    """
+    The hyper-parameter fit of ``GPRSurrogate._gp_train`` with ``n_restarts`` restarts dealt round-robin over the ranks of
+    ``group`` (SPMD: every rank calls it with a model holding the same data and hyper-parameters).
+
+    Restart 0 is the reference's own fit -- ``surrogate.optimiser.minimize(model.training_loss, ...)`` from the warm start,
+    whatever optimiser the surrogate was given, with its full budget (reference gp_surrogate.py:500-503) -- so
+    ``n_restarts=1`` is the reference trajectory.  Restart i > 0 runs SciPy L-BFGS-B (``maxiter`` iterations) from
+    ``u0 + N(0,1)`` in unconstrained space.  All ranks end with the winner's hyper-parameters installed.  Returns a dict with
+    the table of (-LML*, u*) per restart.
+    """
+    rank, world = _rank_world(group)
+    u0 = model._pack()
+    starts = restart_points(u0, n_restarts, seed)
+    p = len(u0)
+    mine = np.full((n_restarts, p + 1), np.nan)
+    for i in range(rank, n_restarts, world):
+        try:
+            if i == 0:
+                model._unpack(u0)
+                surrogate.optimiser.minimize(model.training_loss, model.trainable_variables)
+                x = model._pack()
+                mine[i, 0], mine[i, 1:] = model.neg_log_marginal_likelihood_and_grad(x)[0], x
+            else:
+                res = scipy.optimize.minimize(model.neg_log_marginal_likelihood_and_grad, starts[i], jac=True, method="L-BFGS-B",
+                                              options={} if maxiter is None else {"maxiter": maxiter})
+                mine[i, 0], mine[i, 1:] = res.fun, res.x
+        except (np.linalg.LinAlgError, ValueError):
+            mine[i, 0], mine[i, 1:] = np.inf, starts[i]
+    if world > 1:
+        import torch
+
+        dist = _dist()
+        local = torch.tensor(mine, dtype=torch.float64, device=_comm_device(group))
+        parts = [torch.empty_like(local) for _ in range(world)]
+        dist.all_gather(parts, local, group=group)
+        table = np.stack([parts[i % world][i].cpu().numpy() for i in range(n_restarts)])
+    else:
+        table = mine
+    f = np.where(np.isfinite(table[:, 0]), table[:, 0], np.inf)
+    best = int(np.argmin(f))  # restart 0 wins ties: the reference's optimum is kept unless a restart is strictly better
+    model._unpack(table[best, 1:])
+    return {"restart": best, "fun": float(f[best]), "x": table[best, 1:].copy(), "table": table}

@@ -367,17 +367,63 @@ class GPSurrogate:
             )
 
     def gp_eval_best_ucb(self, normed_coords):
-        """(mean, var, ucb) of the candidate with the highest ``mean + varsigma*var`` (first one on ties)."""
-        _, mean, var, ucb = self._require_model().ucb_argmax(normed_coords, self.gp_varsigma)
+        """(mean, var, ucb) of the candidate with the highest ``mean + varsigma*var`` (first one on ties).  With a process
+        group every rank passes the same candidates and scores its own contiguous shard of them."""
+        model = self._require_model()
+        scorer = self._sharded_scorer()
+        if scorer is not None:
+            _, mean, var, ucb = scorer.ucb_argmax_full(np.ascontiguousarray(normed_coords, dtype=np.float64), self.gp_varsigma)
+        else:
+            _, mean, var, ucb = model.ucb_argmax(normed_coords, self.gp_varsigma)
         return mean, var, ucb
 
     def gp_eval_best_ucb_in_leaf(self, leaf, depth):
         """
         ``gp_eval_best_ucb(leaf.grow(depth))`` without the round trip through the host: the leaf-centre batch is
-        generated on the device and scored in place (reference optimisation.py:379-381).
+        generated on the device and scored in place (reference optimisation.py:379-381).  With a process group every rank
+        generates and scores its own slice of the batch.
         """
-        _, mean, var, ucb = self._require_model().grow_ucb_argmax(leaf.bounds_array(), depth, self.gp_varsigma)
+        model = self._require_model()
+        scorer = self._sharded_scorer()
+        if scorer is not None:
+            _, mean, var, ucb = scorer.grow_ucb_argmax(leaf.bounds_array(), depth, self.gp_varsigma)
+        else:
+            _, mean, var, ucb = model.grow_ucb_argmax(leaf.bounds_array(), depth, self.gp_varsigma)
         return mean, var, ucb
+
+    # -- multi-GPU (SURVEY.md 8e): one process per GPU, every rank holds a replica of the surrogate ------------------------
+    group = None
+
+    def _world(self):
+        from .distributed import _rank_world
+
+        return _rank_world(None if self.group in (None, True) else self.group) if self.group is not None else (0, 1)
+
+    def _sharded_scorer(self):
+        """``ShardedScorer`` over this rank's session when the surrogate was given a process group of more than one rank."""
+        if self.group is None or self._world()[1] == 1:
+            return None
+        from .distributed import ShardedScorer
+
+        session = self._require_model()._session
+        scorer = getattr(self, "_scorer", None)
+        if scorer is None or scorer.session is not session:
+            scorer = self._scorer = ShardedScorer(session, None if self.group is True else self.group)
+        return scorer
+
+    def _broadcast_fit(self):
+        """After a fit: rank 0 factorises, its state (scaled inputs, alpha, L^-1, hyper-parameters) is broadcast once and
+        imported by the other ranks, so every rank scores with bit-identical factors."""
+        scorer = self._sharded_scorer()
+        if scorer is None:
+            return
+        model = self._require_model()
+        n, d = model.data[0].shape
+        if scorer.rank == 0:
+            model._ensure_factor()
+        scorer.broadcast_fit(n, d, src=0)
+        if scorer.rank != 0:
+            model._factor_key = model._theta().tobytes()  # the imported factor belongs to the hyper-parameters in force
 
     def gp_update(self):
         """Re-train on all evaluated points, then refresh every GP-based point with the new posterior."""
@@ -438,8 +484,20 @@ class GPRSurrogate(GPSurrogate):
         points=None,
         gpflow_model=None,
         backend=None,
+        n_restarts=1,
+        group=None,
+        restart_maxiter=50,
+        restart_seed=20240517,
     ):
-        """:param gauss_likelihood_sigma: initial noise *variance* of the Gaussian likelihood (normalised units)"""
+        """
+        :param gauss_likelihood_sigma: initial noise *variance* of the Gaussian likelihood (normalised units)
+        :param n_restarts: multi-start restarts of every hyper-parameter fit.  Restart 0 is the reference's own fit (warm
+            start, the optimiser's full budget), so 1 reproduces the reference trajectory; restarts i > 0 start at
+            ``u + N(0,1)`` in unconstrained space with ``restart_maxiter`` iterations; the smallest -LML wins
+        :param group: ``True`` (default process group) or a ``torch.distributed`` group: one process per GPU, every rank
+            builds the same surrogate and calls the same methods (SPMD).  Restarts are dealt round-robin over the ranks,
+            the fitted state is broadcast once per fit, candidates / leaf batches are sharded over the ranks
+        """
         super().__init__(
             gp_kernel=gp_kernel,
             gp_meanf=gp_meanf,
@@ -450,9 +508,14 @@ class GPRSurrogate(GPSurrogate):
             backend=backend,
         )
         self.gp_lik_sigma = gauss_likelihood_sigma
+        assert int(n_restarts) >= 1
+        self.n_restarts = int(n_restarts)
+        self.group = group
+        self.restart_maxiter = restart_maxiter
+        self.restart_seed = restart_seed
 
     @classmethod
-    def default(cls, backend=None):
+    def default(cls, backend=None, **kwargs):
         """Matern-5/2 with lengthscale 0.25, unit variance, constant mean 0, noise variance 1e-3, SciPy L-BFGS-B."""
         return cls(
             gp_kernel=gpmodel.Matern52(lengthscales=np.sum(NORM_PARAMS_BOUNDS) * 0.25, variance=1.0),
@@ -463,6 +526,7 @@ class GPRSurrogate(GPSurrogate):
             points=None,
             gpflow_model=None,
             backend=backend,
+            **kwargs,
         )
 
     def _gp_train(self, x, y):
@@ -478,7 +542,19 @@ class GPRSurrogate(GPSurrogate):
             )
         else:
             self.gpflow_model.data = (x, y)  # hyper-parameters warm-start from the previous optimum
-        return self.optimiser.minimize(self.gpflow_model.training_loss, self.gpflow_model.trainable_variables)
+        model = self.gpflow_model
+        rank, world = self._world()
+        if self.n_restarts == 1 and world == 1:
+            return self.optimiser.minimize(model.training_loss, model.trainable_variables)
+        # restart 0 = the reference's fit with the surrogate's own optimiser (on the rank that owns it), the other restarts
+        # through SciPy L-BFGS-B from perturbed starts; (-LML*, u*) of every restart is gathered and the winner installed on
+        # every rank -- identical hyper-parameters everywhere, bit for bit
+        from .distributed import multistart_fit
+
+        result = multistart_fit(self, model, self.n_restarts, None if self.group in (None, True) else self.group,
+                                seed=self.restart_seed, maxiter=self.restart_maxiter)
+        self._broadcast_fit()
+        return result
 
     # -- persistence: same file names and JSON keys as the reference (:505-533 / :436-482) -----------------------------
     def save(self, folder):
@@ -502,7 +578,7 @@ class GPRSurrogate(GPSurrogate):
             handle.write(json.dumps(save_info))
 
     @classmethod
-    def from_saved(cls, folder, backend=None):
+    def from_saved(cls, folder, backend=None, **kwargs):
         points = GPListOfPoints.from_file(os.path.join(folder, cls.POINTS_FILE))
         evaluated = [point for point in points if point.label == PointLabels.evaluated]
         x = np.array([point.normed_coord for point in evaluated])
@@ -531,4 +607,5 @@ class GPRSurrogate(GPSurrogate):
             points=points,
             gpflow_model=model,
             backend=backend,
+            **kwargs,
         )

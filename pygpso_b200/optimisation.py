@@ -112,6 +112,7 @@ class GPSOptimiser:
         for attr, value in opt_attrs.items():
             setattr(optimiser, attr, value)
         optimiser.gp_surr = gp_surr
+        optimiser.group = getattr(gp_surr, "group", None)
         assert callable(objective_function)
         optimiser.obj_func = objective_function
         assert callable(eval_repeats_function)
@@ -130,6 +131,7 @@ class GPSOptimiser:
         n_workers=1,
         callbacks=None,
         saver=None,
+        group=None,
     ):
         """
         :param parameter_space: `ParameterSpace` to optimise over
@@ -142,6 +144,9 @@ class GPSOptimiser:
         :param n_workers: processes used to evaluate the objective
         :param callbacks: list of `GPSOCallback`
         :param saver: object with ``save_runs(results, scores, params)``; then the objective returns (result, score)
+        :param group: ``True`` / a ``torch.distributed`` group for a multi-GPU run (one process per GPU, every rank runs this
+            same loop): rank 0 evaluates the objective and broadcasts the scores, fits and candidate scoring are sharded by
+            the surrogate (``GPRSurrogate(group=...)``, which is created with this group when none is passed)
         """
         assert isinstance(parameter_space, ParameterSpace)
         self.param_space = parameter_space
@@ -162,7 +167,8 @@ class GPSOptimiser:
         callbacks = [] if callbacks is None else callbacks
         assert all(isinstance(callback, GPSOCallback) for callback in callbacks)
         self.callbacks = callbacks
-        self.gp_surr = gp_surrogate or GPRSurrogate.default()
+        self.group = group if group is not None else getattr(gp_surrogate, "group", None)
+        self.gp_surr = gp_surrogate or GPRSurrogate.default(group=self.group)
         assert isinstance(self.gp_surr, GPSurrogate)
         self.saver = saver
         if saver is not None:
@@ -258,6 +264,18 @@ class GPSOptimiser:
         if self.method == "tree":
             return self.gp_surr.gp_eval_best_ucb_in_leaf(child, depth=self.max_depth)
         samples = child.sample_uniformly(n_points=self.max_depth, seed=kwargs.pop("seed", None))
+        rank, world = self._rank_world()
+        if world > 1:
+            # SPMD: unseeded draws differ between the ranks; every rank scores rank 0's samples
+            import torch
+            import torch.distributed as dist
+
+            from .distributed import _comm_device
+
+            group = None if self.group is True else self.group
+            box = torch.tensor(np.ascontiguousarray(samples, dtype=np.float64), dtype=torch.float64, device=_comm_device(group))
+            dist.broadcast(box, src=0, group=group)
+            samples = box.cpu().numpy()
         return self.gp_surr.gp_eval_best_ucb(samples)
 
     def _tree_explore(self, levels_to_explore, **kwargs):
@@ -335,6 +353,31 @@ class GPSOptimiser:
         """Scores of the objective at ``orig_coords[n, ndim]`` (original coordinates), aggregated over the repeats."""
         assert orig_coords.ndim == 2
         assert orig_coords.shape[1] == self.param_space.ndim
+        rank, world = self._rank_world()
+        if world > 1:
+            # SPMD: the objective runs once, on rank 0 (it may be expensive or stochastic); every rank gets the same scores
+            import torch
+            import torch.distributed as dist
+
+            from .distributed import _comm_device
+
+            group = None if self.group is True else self.group
+            scores = self._evaluate_local(orig_coords) if rank == 0 else np.zeros(orig_coords.shape[0])
+            box = torch.tensor(np.asarray(scores, dtype=np.float64).reshape(-1), dtype=torch.float64, device=_comm_device(group))
+            dist.broadcast(box, src=0, group=group)
+            if rank != 0:
+                self.n_eval_counter += orig_coords.shape[0]
+            return box.cpu().numpy()
+        return self._evaluate_local(orig_coords)
+
+    def _rank_world(self):
+        if self.group is None:
+            return 0, 1
+        from .distributed import _rank_world
+
+        return _rank_world(None if self.group is True else self.group)
+
+    def _evaluate_local(self, orig_coords):
         repeated = np.vstack(self.eval_repeats * [orig_coords])
         if self.n_workers > 1 and (self.eval_repeats * orig_coords.shape[0]) > 1:
             if getattr(self, "_pool", None) is None:
@@ -439,6 +482,8 @@ class GPSOptimiser:
 
     def save_state(self, folder):
         """Persist tree, surrogate and loop counters to ``folder`` (callbacks and saver are not saved)."""
+        if self._rank_world()[0] != 0:
+            return  # multi-GPU run: every rank holds the same state, rank 0 writes it
         make_dirs(folder)
         logging.warning("When saving, all callbacks and saver will be lost!")
         self.param_space.save(os.path.join(folder, self.PARAM_SPACE_FILE))
