@@ -186,3 +186,63 @@ def test_reference_v3_saver_and_repeats(cuda):
     np.testing.assert_almost_equal(np.array([0.23525377, 0.68518519]), best.normed_coord)
     assert np.around(best.score_mu, decimals=8) == 8.10560594
     assert len(saver.calls) == opt.n_eval_counter and all(len(c[0]) == 4 for c in saver.calls)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the sharding axes behind the kept API: two ranks (gloo for the collectives, both sessions on this
+# GPU) replay GPSOptimiser.run with GPRSurrogate(group=True); candidates / leaf batches are sharded over the ranks, the
+# fitted state is broadcast once per fit.  CUDA results do not depend on the shard a candidate arrives in, so the SPMD run
+# must equal the single-process run BIT FOR BIT.
+# ---------------------------------------------------------------------------------------------------------------------
+def _spmd_gpu_run(group, n_restarts):
+    def rastrigin(point):
+        x = np.asarray(point)
+        return -float(10 * x.size + np.sum(x * x - 10 * np.cos(2 * np.pi * x)))
+
+    space = ParameterSpace(parameter_names=[f"p{i}" for i in range(4)], parameter_bounds=[[-5.12, 5.12]] * 4)
+    surr = GPRSurrogate.default(group=group, n_restarts=n_restarts, restart_maxiter=15)
+    opt = GPSOptimiser(parameter_space=space, gp_surrogate=surr, exploration_method="tree", exploration_depth=8, budget=40,
+                       stopping_condition="evaluations", update_cycle=1, n_workers=1)
+    best = opt.run(rastrigin)
+    return {"coord": np.asarray(best.normed_coord), "score": best.score_mu, "iterations": opt.iterations, "evals": opt.n_eval_counter,
+            "theta": surr.gpflow_model._theta(), "ucbs": np.array([p.score_ucb for p in surr.points]),
+            "mus": np.array([p.score_mu for p in surr.points])}
+
+
+def _spmd_gpu_worker(rank, world, port, out_dir, n_restarts):
+    import os
+    import pickle
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["GPSO_DEVICE"] = "0"
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        out = _spmd_gpu_run(True, n_restarts)
+        with open(os.path.join(out_dir, f"spmd{rank}.pkl"), "wb") as fh:
+            pickle.dump(out, fh)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("n_restarts", [1, 3])
+def test_spmd_two_ranks_equal_single_process_bit_for_bit(cuda, tmp_path, n_restarts):
+    import pickle
+
+    import torch.multiprocessing as mp
+
+    from tests.test_spmd_gloo import _free_port
+
+    mp.spawn(_spmd_gpu_worker, args=(2, _free_port(), str(tmp_path), n_restarts), nprocs=2, join=True)
+    r0, r1 = (pickle.load(open(tmp_path / f"spmd{r}.pkl", "rb")) for r in range(2))
+    single = _spmd_gpu_run(None, n_restarts)
+    for other in (r1, single):
+        assert r0["iterations"] == other["iterations"] and r0["evals"] == other["evals"]
+        for key in ("coord", "theta", "ucbs", "mus"):
+            assert np.array_equal(r0[key], other[key]), key
+        assert r0["score"] == other["score"]
