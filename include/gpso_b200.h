@@ -174,13 +174,17 @@ int gpso_set_window(gpso_handle* h, int64_t candidates);
  * cross-covariance, the candidates whose screened UCB is within 2E of the best one (E = modelled error bound, checked on the
  * survivors) are re-scored by the full-precision engine, and the record of that engine is returned -- bit-identical to the
  * unscreened call.  mode 0 = off, 1 = automatic (default; from N >= 1024 and M >= 65536, digits adapt to the survivor
- * fraction), 2..4 = forced digit count.  Takes effect at the next gpso_factorize.  gpso_predict_y_* and gpso_ucb_topk_* never
- * screen. */
+ * fraction), 2..4 = forced digit count, 5 = bound-and-refine: a first level evaluates only the posterior MEAN of every
+ * candidate (the variance lies between the noise variance and prior + noise variance, so a candidate whose mean is more than
+ * |varsigma| * kernel variance below the best mean cannot win) and hands its survivors to the full-precision engine; when the
+ * means do not separate the candidates it continues with the automatic digit screen.  Takes effect at the next
+ * gpso_factorize.  gpso_predict_y_* and gpso_ucb_topk_* never screen. */
 int gpso_set_screen_mode(gpso_handle* h, int mode);
 /* last fused arg-max call: out[0] path (0 unscreened, 1 screened, 2 full pass: too many survivors, 3 full pass: bound check
- * failed), out[1] screening digits, out[2] survivors, out[3] error bound E, out[4] largest |refined - screened| UCB over
+ * failed, 4 mean-bound level + refine), out[1] screening digits (0 for path 4), out[2] survivors, out[3] error bound E, out[4] largest |refined - screened| UCB over
  * the survivors, out[5] best screened UCB, out[6] screening windows, out[7] summed duration (ms) of the screening product
- * launches, out[8] refine windows, out[9] E_var, out[10] E_mean, out[11] unused */
+ * launches, out[8] refine windows, out[9] E_var, out[10] E_mean, out[11] mode 5: admissible distance below the best mean (path 4) or the
+ * survivors of the mean-bound level when it gave up */
 int gpso_screen_info(gpso_handle* h, double* out12);
 /* Host-only (works without a GPU): the error bound E of the screening pass and its variance / mean parts,
  * out3 = {E, E_var, E_mean}, for N training points, kernel variance, noise variance, the largest power-of-two row scale of

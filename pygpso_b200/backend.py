@@ -334,14 +334,16 @@ class CudaSession:
         return {"engine": "int8-tcgen05" if out[0] == 2 else "fp64-dmma", "slices": int(out[1]), "error_estimate_over_tol": float(out[2])}
 
     def set_screen_mode(self, mode=1):
-        """Screen-and-refine arg-max: 0 off, 1 automatic (default), 2..4 forced screening digits; results are bit-identical."""
+        """Screen-and-refine arg-max: 0 off, 1 automatic (default), 2..4 forced screening digits, 5 mean-bound level first;
+        results are bit-identical."""
         self.factorized = False
         _check(self._lib, self._lib.gpso_set_screen_mode(self._h, int(mode)), "gpso_set_screen_mode")
 
     def screen_info(self):
         out = np.zeros(12)
         _check(self._lib, self._lib.gpso_screen_info(self._h, _dptr(out)), "gpso_screen_info")
-        path = {0: "unscreened", 1: "screened", 2: "full pass (too many survivors)", 3: "full pass (bound check failed)"}[int(out[0])]
+        path = {0: "unscreened", 1: "screened", 2: "full pass (too many survivors)", 3: "full pass (bound check failed)",
+                4: "mean-bound"}[int(out[0])]
         return {"path": path, "digits": int(out[1]), "survivors": int(out[2]), "error_bound": float(out[3]),
                 "max_observed_deviation": float(out[4]), "best_screened_ucb": float(out[5]), "screen_windows": int(out[6]),
                 "screen_product_ms": float(out[7]), "refine_windows": int(out[8]), "e_var": float(out[9]), "e_mean": float(out[10])}

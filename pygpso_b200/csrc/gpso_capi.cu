@@ -72,6 +72,7 @@ constexpr long long SCREEN_MIN_M = 65536;      // fewer candidates than this: no
 constexpr double SCREEN_SAFETY = 4.0;          // error bound E = SAFETY * (model estimate); the refine pass must observe <= E / 4
 constexpr unsigned SCREEN_LIST_CAP = 1u << 20; // survivor list capacity; more survivors than this or than M / 16 -> full pass
 constexpr int SCREEN_S_MIN = 2, SCREEN_S_MAX = 4;
+constexpr int SCREEN_MODE_BOUND = 5;           // gpso_set_screen_mode: mean-bound level first, then the automatic digit screen
 
 struct DevBuf {
     void* p = nullptr;
@@ -171,6 +172,7 @@ struct gpso_handle {
     double scr_info[12] = {0};
     const long long* rw_idx_map = nullptr;  // run_windows: global indices of the (gathered) candidates
     bool rw_check = false;                  // run_windows: compare refined and screened UCB of every candidate
+    bool rw_check_mean = false;             // ... the stored value is the screened mean (bound-and-refine level 0)
     size_t scr_prod_marks = 0;
     // host copies of the hyper-parameters in force
     double ls_host[MAX_LS] = {0}, variance = 1.0, noise = 1.0, c0 = 0.0;
@@ -426,6 +428,10 @@ static int configure_kernels() {
     CU_TRY(cudaFuncSetAttribute(factor_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM_BYTES));
     CU_TRY(cudaFuncSetAttribute(ozaki_kernel<OZ_KINV_S, OZ_LAUUM>, cudaFuncAttributeMaxDynamicSharedMemorySize, OzCfg<OZ_KINV_S>::SMEM_BYTES));
     CU_TRY(cudaFuncSetAttribute(ozaki_kernel<OZ_INV_S, OZ_GEMM>, cudaFuncAttributeMaxDynamicSharedMemorySize, OzCfg<OZ_INV_S>::SMEM_BYTES));
+    CU_TRY(cudaFuncSetAttribute(crosscov_screen_kernel<KERNEL_MATERN12, 0, SCR_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_XCOV_SMEM_MAX));
+    CU_TRY(cudaFuncSetAttribute(crosscov_screen_kernel<KERNEL_MATERN32, 0, SCR_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_XCOV_SMEM_MAX));
+    CU_TRY(cudaFuncSetAttribute(crosscov_screen_kernel<KERNEL_MATERN52, 0, SCR_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_XCOV_SMEM_MAX));
+    CU_TRY(cudaFuncSetAttribute(crosscov_screen_kernel<KERNEL_SE, 0, SCR_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_XCOV_SMEM_MAX));
     GP_TRY(screen_configure<2>());
     GP_TRY(screen_configure<3>());
     GP_TRY(screen_configure<4>());
@@ -1453,7 +1459,7 @@ static int run_windows(gpso_handle* h, cudaStream_t st, const double* Xc_dev, co
         GP_TRY(check_launch(h, "predict_finalize"));
         if (check) {
             screen_check_kernel<<<fb, 256, 0, st>>>(om, ov, Mw, h->rw_idx_map + off, varsigma, h->scr_ucb.as<double>(),
-                                                    h->scr_state.as<unsigned long long>());
+                                                    h->scr_state.as<unsigned long long>(), h->rw_check_mean ? 1 : 0);
             GP_TRY(check_launch(h, "screen_check"));
         }
         if (mode == 2) {
@@ -1670,6 +1676,127 @@ static int run_screen_windows(gpso_handle* h, cudaStream_t st, const double* Xc_
 
 static int fetch_best(gpso_handle* h, cudaStream_t st, double* result_host);
 
+// ---- bound-and-refine, level 0 (screen mode 5) ---------------------------------------------------------------------------
+// UCB = mean + varsigma * var with sigma_n^2 <= var <= sigma_f^2 + sigma_n^2 for EVERY candidate (the posterior variance of
+// the latent function lies between 0 and the prior variance), so a candidate whose posterior mean is more than
+// |varsigma| sigma_f^2 below the best mean cannot be the arg-max whatever its variance.  Only the mean is evaluated for all
+// candidates (fp32 cross-covariance, error bound E_mean of screen_error_model); the survivors go straight to the
+// full-precision engine.  Exact like the digit screen, and much cheaper when the means spread wider than |varsigma| sigma_f^2;
+// when they do not (too many survivors) the caller continues with the digit screen over all candidates.
+static int run_bound_windows(gpso_handle* h, cudaStream_t st, const double* Xc_dev, const double* Xc_host, long long M) {
+    const bool host = Xc_host != nullptr;
+    const int d = h->d;
+    long long W = 1LL << 19;
+    if (h->window_override > 0) W = std::max<long long>(1024, h->window_override / 1024 * 1024);
+    W = std::min(W, ((M + SCR_NT - 1) / SCR_NT) * SCR_NT);
+    const long long nwin = (M + W - 1) / W;
+    GP_TRY(h->scr_ucb.ensure((size_t)M * sizeof(double)));
+    GP_TRY(h->scr_state.ensure(4 * sizeof(unsigned long long)));
+    GP_TRY(h->wmeanb[0].ensure((size_t)W * sizeof(double)));
+    if (host) {
+        GP_TRY(h->cand[0].ensure((size_t)W * d * sizeof(double)));
+        GP_TRY(h->cand[1].ensure((size_t)W * d * sizeof(double)));
+    }
+    CU_TRY(cudaMemsetAsync(h->scr_state.p, 0, 4 * sizeof(unsigned long long), st));
+    cudaStream_t cs = h->copy_stream;
+    CU_TRY(cudaEventRecord(h->ev_start, st));
+    if (host) CU_TRY(cudaStreamWaitEvent(cs, h->ev_start, 0));
+    bool cand_busy[2] = {false, false};
+    for (long long w = 0; w < nwin; w++) {
+        const int cb = (int)(w & 1);
+        const long long off = w * W;
+        const long long Mw = std::min(W, M - off);
+        const long long Mw_pad = ((Mw + SCR_NT - 1) / SCR_NT) * SCR_NT;
+        const double* src;
+        if (host) {
+            if (cand_busy[cb]) CU_TRY(cudaStreamWaitEvent(cs, h->ev_used[cb], 0));
+            CU_TRY(cudaMemcpyAsync(h->cand[cb].p, Xc_host + off * d, (size_t)Mw * d * sizeof(double), cudaMemcpyHostToDevice, cs));
+            CU_TRY(cudaEventRecord(h->ev_copy[cb], cs));
+            CU_TRY(cudaStreamWaitEvent(st, h->ev_copy[cb], 0));
+            src = h->cand[cb].as<double>();
+        } else {
+            src = Xc_dev + off * d;
+        }
+        GP_TRY(trace_mark(h, st, 1, w));
+        launch_screen_crosscov_s<0>(h, st, src, Mw, Mw_pad / 64, 0.0f, nullptr, h->wmeanb[0].as<double>());
+        GP_TRY(check_launch(h, "crosscov_mean"));
+        GP_TRY(trace_mark(h, st, 2, w));
+        if (host) {
+            CU_TRY(cudaEventRecord(h->ev_used[cb], st));
+            cand_busy[cb] = true;
+        }
+        bound_finalize_kernel<<<(unsigned)((Mw + 255) / 256), 256, 0, st>>>(h->wmeanb[0].as<double>(), Mw, off, h->scr_ucb.as<double>(),
+                                                                            h->scr_state.as<unsigned long long>());
+        GP_TRY(check_launch(h, "bound_finalize"));
+        h->last_windows++;
+    }
+    h->scr_info[6] = (double)nwin;
+    return 0;
+}
+
+// survivors of a screening level (scr_ucb / scr_state on the device, slack = admissible distance below the best value) ->
+// gathered, re-scored by the full-precision engine with the per-survivor check.  Returns 0 with *ok = true when the record in
+// result_host can be trusted, *ok = false when the caller has to fall back (too many survivors, or the check failed).
+static int refine_survivors(gpso_handle* h, cudaStream_t st, const double* Xc_dev, const double* Xc_host, long long M, double varsigma,
+                            double slack, double check_bound, bool mean_only, long long cap_in, double* result_host, bool* ok) {
+    *ok = false;
+    const unsigned cap = (unsigned)std::min<long long>(SCREEN_LIST_CAP, std::max<long long>(cap_in, 1024));
+    GP_TRY(h->surv_list.ensure((size_t)cap * sizeof(long long)));
+    screen_select_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(h->scr_ucb.as<double>(), M, slack, h->scr_state.as<unsigned long long>(),
+                                                                     h->surv_list.as<long long>(), cap);
+    GP_TRY(check_launch(h, "screen_select"));
+    unsigned long long state[4] = {0, 0, 0, 0};
+    CU_TRY(cudaMemcpyAsync(state, h->scr_state.p, sizeof state, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    const long long count = (long long)state[1];
+    h->scr_info[2] = (double)count;
+    h->scr_info[5] = scr_unkey(state[0]);
+    if (count < 1 || count > (long long)cap) {
+        h->scr_info[0] = 2.0;
+        return 0;
+    }
+    const long long windows_before = h->last_windows;
+    std::vector<double> gathered;
+    const double* rdev = nullptr;
+    const double* rhost = nullptr;
+    if (Xc_host != nullptr) {
+        std::vector<long long> list((size_t)count);
+        CU_TRY(cudaMemcpyAsync(list.data(), h->surv_list.p, (size_t)count * sizeof(long long), cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaStreamSynchronize(st));
+        gathered.resize((size_t)count * h->d);
+        for (long long i = 0; i < count; i++)
+            memcpy(&gathered[(size_t)i * h->d], Xc_host + list[(size_t)i] * h->d, sizeof(double) * h->d);
+        rhost = gathered.data();
+    } else {
+        GP_TRY(h->surv_X.ensure((size_t)count * h->d * sizeof(double)));
+        gather_rows_kernel<<<(unsigned)((count * h->d + 255) / 256), 256, 0, st>>>(Xc_dev, h->surv_list.as<long long>(), count, h->d,
+                                                                                h->surv_X.as<double>());
+        GP_TRY(check_launch(h, "gather_rows"));
+        rdev = h->surv_X.as<double>();
+    }
+    h->rw_idx_map = h->surv_list.as<long long>();
+    h->rw_check = true;
+    h->rw_check_mean = mean_only;
+    int rc = run_windows(h, st, rdev, rhost, count, 1, varsigma, nullptr, nullptr);
+    h->rw_idx_map = nullptr;
+    h->rw_check = false;
+    h->rw_check_mean = false;
+    GP_TRY(rc);
+    unsigned long long dbits = 0;
+    CU_TRY(cudaMemcpyAsync(&dbits, h->scr_state.as<unsigned long long>() + 2, sizeof dbits, cudaMemcpyDeviceToHost, st));
+    GP_TRY(fetch_best(h, st, result_host));  // synchronises st
+    double dmax;
+    memcpy(&dmax, &dbits, sizeof dmax);
+    h->scr_info[4] = dmax;
+    h->scr_info[8] = (double)(h->last_windows - windows_before);
+    if (dmax <= 0.25 * check_bound) {
+        *ok = true;
+        return 0;
+    }
+    h->scr_info[0] = 3.0;  // the bound did not hold with the required margin: do not trust the screen
+    return 0;
+}
+
 // Fused predict_y + UCB + arg-max of M candidates (device- or host-resident): screened when it pays, else the plain window
 // pipeline.  The record returned is always produced by the full-precision engine.
 static int score_argmax(gpso_handle* h, cudaStream_t st, const double* Xc_dev, const double* Xc_host, long long M, double varsigma,
@@ -1677,73 +1804,45 @@ static int score_argmax(gpso_handle* h, cudaStream_t st, const double* Xc_dev, c
     for (int i = 0; i < 12; i++) h->scr_info[i] = 0.0;
     h->scr_prod_marks = 0;
     if (screen_applicable(h, M)) {
-        int S = h->screen_mode >= 2 ? std::min(std::max(h->screen_mode, SCREEN_S_MIN), SCREEN_S_MAX) : screen_pick_digits(h);
+        double E = 0.0, e_var = 0.0, e_mean = 0.0;
+        bool ok = false;
+        if (h->screen_mode == SCREEN_MODE_BOUND) {
+            // level 0: posterior mean of every candidate, variance bounded by the prior
+            screen_error_bound(h, SCREEN_S_MAX, varsigma, &E, &e_var, &e_mean);
+            GP_TRY(run_bound_windows(h, st, Xc_dev, Xc_host, M));
+            const double width = fabs(varsigma) * h->variance * (1.0 + 2.0e-6);  // |varsigma| (v_max - v_min) with rounding slack
+            h->scr_info[1] = 0.0;
+            h->scr_info[3] = e_mean;
+            h->scr_info[10] = e_mean;
+            h->scr_info[11] = width;
+            GP_TRY(refine_survivors(h, st, Xc_dev, Xc_host, M, varsigma, 2.0 * e_mean + width, e_mean, true, M / 64, result_host, &ok));
+            if (ok) {
+                h->scr_info[0] = 4.0;
+                return 0;
+            }
+            // too many survivors (the means do not separate the candidates) or check failed: digit screen over all candidates
+            h->scr_info[11] = h->scr_info[2];  // survivors of the bound level, kept for the record
+        }
+        int S = (h->screen_mode >= 2 && h->screen_mode <= SCREEN_S_MAX) ? std::max(h->screen_mode, SCREEN_S_MIN) : screen_pick_digits(h);
         if (S >= h->oz_S) S = 0;  // nothing to gain
         if (S != 0) {
-            double E = 0.0, e_var = 0.0, e_mean = 0.0;
             screen_error_bound(h, S, varsigma, &E, &e_var, &e_mean);
             cudaStream_t pst = st;
+            h->prod_used = 0;
             GP_TRY(run_screen_windows(h, st, Xc_dev, Xc_host, M, S, varsigma, &pst));
             h->scr_prod_marks = h->prod_used;
-            const unsigned cap = (unsigned)std::min<long long>(SCREEN_LIST_CAP, std::max<long long>(M / 16, 1024));
-            GP_TRY(h->surv_list.ensure((size_t)cap * sizeof(long long)));
-            screen_select_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(h->scr_ucb.as<double>(), M, 2.0 * E,
-                                                                             h->scr_state.as<unsigned long long>(),
-                                                                             h->surv_list.as<long long>(), cap);
-            GP_TRY(check_launch(h, "screen_select"));
-            unsigned long long state[4] = {0, 0, 0, 0};
-            CU_TRY(cudaMemcpyAsync(state, h->scr_state.p, sizeof state, cudaMemcpyDeviceToHost, st));
-            CU_TRY(cudaStreamSynchronize(st));
-            const long long count = (long long)state[1];
             h->scr_info[1] = S;
-            h->scr_info[2] = (double)count;
             h->scr_info[3] = E;
-            h->scr_info[5] = scr_unkey(state[0]);
             h->scr_info[9] = e_var;
             h->scr_info[10] = e_mean;
-            // the digit count adapts to the survivor fraction (automatic mode): too many survivors -> one digit more next time
-            if (h->screen_mode == 1 && count * 64 > M && h->screen_S_cur < SCREEN_S_MAX) h->screen_S_cur++;
-            if (count >= 1 && count <= (long long)cap) {
-                const long long windows_before = h->last_windows;
-                std::vector<double> gathered;
-                const double* rdev = nullptr;
-                const double* rhost = nullptr;
-                if (Xc_host != nullptr) {
-                    std::vector<long long> list((size_t)count);
-                    CU_TRY(cudaMemcpyAsync(list.data(), h->surv_list.p, (size_t)count * sizeof(long long), cudaMemcpyDeviceToHost, st));
-                    CU_TRY(cudaStreamSynchronize(st));
-                    gathered.resize((size_t)count * h->d);
-                    for (long long i = 0; i < count; i++)
-                        memcpy(&gathered[(size_t)i * h->d], Xc_host + list[(size_t)i] * h->d, sizeof(double) * h->d);
-                    rhost = gathered.data();
-                } else {
-                    GP_TRY(h->surv_X.ensure((size_t)count * h->d * sizeof(double)));
-                    gather_rows_kernel<<<(unsigned)((count * h->d + 255) / 256), 256, 0, st>>>(Xc_dev, h->surv_list.as<long long>(), count, h->d,
-                                                                                            h->surv_X.as<double>());
-                    GP_TRY(check_launch(h, "gather_rows"));
-                    rdev = h->surv_X.as<double>();
-                }
-                h->rw_idx_map = h->surv_list.as<long long>();
-                h->rw_check = true;
-                int rc = run_windows(h, st, rdev, rhost, count, 1, varsigma, nullptr, nullptr);
-                h->rw_idx_map = nullptr;
-                h->rw_check = false;
-                GP_TRY(rc);
-                unsigned long long dbits = 0;
-                CU_TRY(cudaMemcpyAsync(&dbits, h->scr_state.as<unsigned long long>() + 2, sizeof dbits, cudaMemcpyDeviceToHost, st));
-                GP_TRY(fetch_best(h, st, result_host));  // synchronises st
-                double dmax;
-                memcpy(&dmax, &dbits, sizeof dmax);
-                h->scr_info[4] = dmax;
-                h->scr_info[8] = (double)(h->last_windows - windows_before);
-                if (dmax <= 0.25 * E) {
-                    h->scr_info[0] = 1.0;
-                    return 0;
-                }
-                h->scr_info[0] = 3.0;  // the bound did not hold with the required margin: do not trust the screen
-                if (h->screen_mode == 1 && h->screen_S_cur < SCREEN_S_MAX) h->screen_S_cur++;
-            } else {
-                h->scr_info[0] = 2.0;
+            GP_TRY(refine_survivors(h, st, Xc_dev, Xc_host, M, varsigma, 2.0 * E, E, false, M / 16, result_host, &ok));
+            // the digit count adapts to the survivor fraction (automatic mode): too many survivors or a failed check -> one
+            // digit more next time
+            const long long count = (long long)h->scr_info[2];
+            if (h->screen_mode == 1 && (count * 64 > M || h->scr_info[0] == 3.0) && h->screen_S_cur < SCREEN_S_MAX) h->screen_S_cur++;
+            if (ok) {
+                h->scr_info[0] = 1.0;
+                return 0;
             }
         }
     }
@@ -2163,7 +2262,8 @@ extern "C" int gpso_predict_info(gpso_handle* h, double* out3) {
 }
 
 extern "C" int gpso_set_screen_mode(gpso_handle* h, int mode) {
-    if (!h || mode < 0 || mode > SCREEN_S_MAX) return fail(GPSO_E_BADARG, "gpso_set_screen_mode: mode must be 0 (off), 1 (automatic) or 2..4 (digits)");
+    if (!h || mode < 0 || mode > SCREEN_MODE_BOUND)
+        return fail(GPSO_E_BADARG, "gpso_set_screen_mode: mode must be 0 (off), 1 (automatic), 2..4 (digits) or 5 (mean bound first)");
     h->screen_mode = mode;
     h->screen_S_cur = SCREEN_S_MIN;
     h->factorized = false;  // the fp32 copies are prepared by the next gpso_factorize

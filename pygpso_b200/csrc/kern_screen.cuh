@@ -93,6 +93,8 @@ __global__ void __launch_bounds__(256) screen_convert_kernel(const double* __res
     if (i < Np) alpha32[i] = (float)alpha[i];
 }
 
+// S = 0: posterior mean only (no digit tiles are formed or written): the first level of the bound-and-refine arg-max, which
+// needs nothing but the mean of every candidate (gpso_capi.cu: bound_argmax).
 // One block = 64 candidates x all training points (super-steps of 128 training points), the register tiling of
 // crosscov_slices_kernel in FP32: thread = 2 candidates (lane, lane + 32) x 16 consecutive training points (warp w owns
 // points 16 w .. 16 w + 15 of the super-step).  The digit tiles are written in the NT-candidate layout of the screening
@@ -175,29 +177,34 @@ __global__ void __launch_bounds__(256, 2) crosscov_screen_kernel(const double* _
         const float* al = sAl + b * OZ_XK + kg * 16;
 #pragma unroll
         for (int a = 0; a < 2; a++) {
-            uint32_t out[S][4];
+            constexpr int SD = S > 0 ? S : 1;
+            uint32_t out[SD][4];
 #pragma unroll
-            for (int p = 0; p < S; p++) out[p][0] = out[p][1] = out[p][2] = out[p][3] = 0u;
+            for (int p = 0; p < SD; p++) out[p][0] = out[p][1] = out[p][2] = out[p][3] = 0u;
             float msum = 0.0f;
 #pragma unroll
             for (int g = 0; g < 16; g++) {
                 float k = cov32_from_r2<KID>(r2[a][g], var);
                 k = (cvalid[a] && j0 + g < N) ? k : 0.0f;
                 msum = fmaf(k, al[g], msum);
-                const uint32_t z = scr_digits<S>(k, bscale);
+                if (S > 0) {
+                    const uint32_t z = scr_digits<SD>(k, bscale);
 #pragma unroll
-                for (int p = 0; p < S; p++) {
-                    // digit p (0 = most significant) = byte S-1-p of z -> byte (g & 3) of word g >> 2
-                    const uint32_t sel = (0x3210u & ~(0xFu << (4 * (g & 3)))) | ((uint32_t)(4 + (S - 1 - p)) << (4 * (g & 3)));
-                    out[p][g >> 2] = __byte_perm(out[p][g >> 2], z, sel);
+                    for (int p = 0; p < SD; p++) {
+                        // digit p (0 = most significant) = byte S-1-p of z -> byte (g & 3) of word g >> 2
+                        const uint32_t sel = (0x3210u & ~(0xFu << (4 * (g & 3)))) | ((uint32_t)(4 + (SD - 1 - p)) << (4 * (g & 3)));
+                        out[p][g >> 2] = __byte_perm(out[p][g >> 2], z, sel);
+                    }
                 }
             }
             macc[a] += (double)msum;
-            const int r = rbase + cl + 32 * a;
-            uint8_t* dst = B + ((size_t)ct * nks + ks) * S * (NT * 32) + (r >> 3) * 256 + half * 128 + (r & 7) * 16;
+            if (S > 0) {
+                const int r = rbase + cl + 32 * a;
+                uint8_t* dst = B + ((size_t)ct * nks + ks) * SD * (NT * 32) + (r >> 3) * 256 + half * 128 + (r & 7) * 16;
 #pragma unroll
-            for (int p = 0; p < S; p++)
-                *reinterpret_cast<uint4*>(dst + (size_t)p * (NT * 32)) = make_uint4(out[p][0], out[p][1], out[p][2], out[p][3]);
+                for (int p = 0; p < SD; p++)
+                    *reinterpret_cast<uint4*>(dst + (size_t)p * (NT * 32)) = make_uint4(out[p][0], out[p][1], out[p][2], out[p][3]);
+            }
         }
     }
     sR[kg * 64 + cl] = macc[0];
@@ -442,6 +449,30 @@ __global__ void __launch_bounds__(256) screen_finalize_kernel(const float* __res
     }
 }
 
+// first level of the bound-and-refine arg-max: store the (fp32-evaluated) posterior mean per candidate, running maximum
+__global__ void __launch_bounds__(256) bound_finalize_kernel(const double* __restrict__ mean, long long Mw, long long idx0,
+                                                             double* __restrict__ scr_ucb, unsigned long long* __restrict__ state) {
+    const long long c = (long long)blockIdx.x * 256 + threadIdx.x;
+    double m = -INFINITY;
+    if (c < Mw) {
+        m = mean[c];
+        scr_ucb[idx0 + c] = m;
+    }
+    unsigned long long key = (m == m) ? scr_key(m) : 0ULL;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+        key = other > key ? other : key;
+    }
+    __shared__ unsigned long long sk[8];
+    if ((threadIdx.x & 31) == 0) sk[threadIdx.x >> 5] = key;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < 8; i++) key = sk[i] > key ? sk[i] : key;
+        atomicMax(state, key);
+    }
+}
+
 __global__ void __launch_bounds__(256) screen_select_kernel(const double* __restrict__ scr_ucb, long long M, double two_e,
                                                             unsigned long long* __restrict__ state, long long* __restrict__ list,
                                                             unsigned int cap) {
@@ -463,13 +494,15 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const double* __restri
     out[e] = Xc[list[r] * d + (e - r * d)];
 }
 
-// refined (full-precision) UCB of the survivors of one refine window against their screened value
+// refined (full-precision) UCB of the survivors of one refine window against their screened value (mean_only: the stored
+// value is the screened MEAN, first level of the bound-and-refine arg-max)
 __global__ void __launch_bounds__(256) screen_check_kernel(const double* __restrict__ mean, const double* __restrict__ var, long long Mw,
                                                            const long long* __restrict__ list, double varsigma,
-                                                           const double* __restrict__ scr_ucb, unsigned long long* __restrict__ state) {
+                                                           const double* __restrict__ scr_ucb, unsigned long long* __restrict__ state,
+                                                           int mean_only) {
     const long long c = (long long)blockIdx.x * 256 + threadIdx.x;
     if (c >= Mw) return;
-    const double u = __dadd_rn(mean[c], __dmul_rn(varsigma, var[c]));
+    const double u = mean_only ? mean[c] : __dadd_rn(mean[c], __dmul_rn(varsigma, var[c]));
     const double us = scr_ucb[list[c]];
     const double diff = fabs(u - us);
     // NaN on either side: nothing to compare (a NaN screened value is refined unconditionally).  An infinite difference

@@ -38,7 +38,7 @@ def same_record(a, b):
 
 @pytest.mark.parametrize("kernel", ["Matern52", "SquaredExponential", "Matern32", "Matern12"])
 @pytest.mark.parametrize("N,d,M", [(1100, 4, 70_000), (2100, 6, 150_000)])
-@pytest.mark.parametrize("mode", [1, 2, 3, 4])
+@pytest.mark.parametrize("mode", [1, 2, 3, 4, 5])
 def test_screened_argmax_is_bit_identical(cuda, kernel, N, d, M, mode):
     X, y = synthetic(N, d, seed=N)
     h = go.Hyper(0.25 * np.sqrt(d), 1.0, 1e-3, 0.05)
@@ -48,7 +48,7 @@ def test_screened_argmax_is_bit_identical(cuda, kernel, N, d, M, mode):
     s.close()
     assert same_record(ref, got), (ref, got, info)
     assert info["path"] != "unscreened", info
-    if info["path"] == "screened":
+    if info["path"] in ("screened", "mean-bound"):
         assert info["max_observed_deviation"] <= 0.25 * info["error_bound"]
         assert 1 <= info["survivors"] <= M // 16
     if mode in (1, 3, 4):  # the model-chosen and the 3/4-digit screens must not need the fall-back on these problems
@@ -71,7 +71,7 @@ def test_screened_matches_oracle_winner(cuda):
     assert got[0] == go.ucb_argmax(mean, var, VARSIGMA)[0]
 
 
-@pytest.mark.parametrize("mode", [1, 2, 3])
+@pytest.mark.parametrize("mode", [1, 2, 3, 5])
 def test_ties_near_ties_and_nan(cuda, mode):
     N, d, M = 1100, 4, 80_000
     X, y = synthetic(N, d, seed=12)
@@ -120,10 +120,11 @@ def test_plateau_falls_back_to_full_pass(cuda):
     rng = np.random.default_rng(5)
     Xc = 50.0 + rng.random((M, d))  # all far outside the unit cube of the training data
     s = open_session(cuda, "Matern52", X, y)
-    ref, got, info = both(s, Xc, theta_of(h), 1)
+    for mode in (1, 5):
+        ref, got, info = both(s, Xc, theta_of(h), mode)
+        assert same_record(ref, got), (ref, got, info)
+        assert info["path"].startswith("full pass"), info
     s.close()
-    assert same_record(ref, got), (ref, got, info)
-    assert info["path"].startswith("full pass"), info
 
 
 @pytest.mark.parametrize("host", [True, False])
@@ -185,6 +186,9 @@ def test_c3_shape_screened_vs_full(cuda):
     ref, got, info = both(s, Xc, theta, 1)
     assert same_record(ref, got), (ref, got, info)
     assert info["path"] == "screened" and info["survivors"] < 2000, info
+    ref5, got5, info5 = both(s, Xc, theta, 5)
+    assert same_record(ref, got5), (ref, got5, info5)
+    assert info5["path"] == "mean-bound" and info5["survivors"] < 20000, info5
     s.set_screen_mode(0)
     s.set_predict_mode(1, 0)
     s.factorize(theta)
