@@ -1,7 +1,8 @@
 """
 Callbacks that read the surrogate model (reference ``gpso/callbacks.py``): the logging, save-before-finalise and
-checkpoint callbacks.  ``PostIterationPlotting`` (``callbacks.py:19-87``) draws with matplotlib and is out of scope
-(DESIGN.md section 9).
+checkpoint callbacks, and ``PostIterationPlotting`` (``callbacks.py:19-87``) with its model-reading part -- the conditional
+surrogate distributions, one batched ``predict_y`` -- computed and saved as arrays; figures are drawn only when matplotlib is
+importable (it is not a dependency).
 
 Same class names, constructor arguments and callback types as the reference, so a callback list written for pyGPSO runs
 unchanged.  ``GPFlowCheckpoints`` kept its name; instead of a TensorFlow checkpoint manager it writes the model's parameter
@@ -17,6 +18,48 @@ import numpy as np
 from . import gpmodel
 from .optimisation import CallbackTypes, GPSOCallback
 from .utils import PKL_EXT, make_dirs
+
+
+class PostIterationPlotting(GPSOCallback):
+    """
+    After every iteration: conditional surrogate distributions (posterior mean / variance on 2-D slices through the best
+    point, reference ``plotting.py:257-494``) and the evaluated scores per parameter.  Constructor arguments as in the
+    reference (``callbacks.py:27-64``).  Writes ``<pattern>_iter<k>_surrogate_dist.npz`` with one ``mean_i_j`` / ``var_i_j``
+    array per parameter pair, and ``<pattern>_iter<k>_surrogate_dist<plot_ext>`` when matplotlib is available.
+    """
+
+    callback_type = CallbackTypes.post_iteration
+
+    def __init__(self, filename_pattern, plot_ext=".png", gp_mean_limits=[-10, 10], gp_var_limits=[0, 5], marginal_plot_type="kde",
+                 marginal_percentile=0.9, from_iteration=1, granularity=None):
+        super().__init__()
+        self.filename_pattern = filename_pattern
+        self.plot_ext = plot_ext
+        self.gp_mean_limits = gp_mean_limits
+        self.gp_var_limits = gp_var_limits
+        self.marginal_plot_type = marginal_plot_type
+        self.marginal_percentile = marginal_percentile
+        self.from_iteration = from_iteration
+        self.granularity = granularity
+
+    def run(self, optimiser):
+        super().run(optimiser)
+        if optimiser.iterations < self.from_iteration:
+            return
+        from . import plotting
+
+        stem = self.filename_pattern + f"_iter{optimiser.iterations}"
+        make_dirs(os.path.dirname(os.path.abspath(stem)))
+        kwargs = {} if self.granularity is None else {"granularity": self.granularity}
+        slices = plotting.conditional_surrogate_slices(optimiser, **kwargs)
+        coords, scores = plotting.evaluated_scores_by_parameter(optimiser)
+        arrays = {"evaluated_coords": coords, "evaluated_scores": scores}
+        for (i, j), (mean, var) in slices.items():
+            arrays[f"mean_{i}_{j}"] = mean
+            arrays[f"var_{i}_{j}"] = var
+        np.savez(stem + "_surrogate_dist.npz", **arrays)
+        plotting.render_conditional_surrogate(optimiser, slices, self.gp_mean_limits, self.gp_var_limits,
+                                              fname=stem + f"_surrogate_dist{self.plot_ext}")
 
 
 class PostUpdateLogging(GPSOCallback):

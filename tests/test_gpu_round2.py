@@ -246,3 +246,34 @@ def test_spmd_two_ranks_equal_single_process_bit_for_bit(cuda, tmp_path, n_resta
         for key in ("coord", "theta", "ucbs", "mus"):
             assert np.array_equal(r0[key], other[key]), key
         assert r0["score"] == other["score"]
+
+
+def test_post_iteration_plotting_on_gpu(cuda, tmp_path):
+    """N4: the model-reading part of ``PostIterationPlotting`` (conditional surrogate slices, one batched predict_y) on the GPU
+    against the oracle at the final hyper-parameters."""
+    import os
+
+    from pygpso_b200.callbacks import PostIterationPlotting
+
+    space = ParameterSpace(parameter_names=["a", "b", "c"], parameter_bounds=[[-1, 1], [0, 2], [-3, 3]])
+    pattern = str(tmp_path / "plots" / "run")
+    opt = GPSOptimiser(parameter_space=space, exploration_depth=4, budget=20,
+                       callbacks=[PostIterationPlotting(pattern, from_iteration=1, granularity=9)])
+    opt.run(lambda p: -float(np.sum((np.asarray(p) - 0.3) ** 2)))
+    files = sorted(f for f in os.listdir(tmp_path / "plots") if f.endswith(".npz"))
+    data = np.load(tmp_path / "plots" / files[-1])
+    model = opt.gp_surr.gpflow_model
+    X, y = model.data
+    theta = model._theta()
+    h = go.Hyper(theta[0], theta[1], theta[2], theta[3])
+    g = 9
+    best = np.vstack([opt.gp_surr.highest_score.normed_coord] * g ** 2)
+    gx, gy = np.meshgrid(np.linspace(0, 1, g), np.linspace(0, 1, g))
+    for (i, j) in ((0, 1), (0, 2), (1, 2)):
+        at = best.copy()
+        at[:, i], at[:, j] = gx.flatten(), gy.flatten()
+        mean, var = go.predict_y("Matern52", X, y, h, at)
+        mtol = 1e-8 * np.maximum(np.abs(mean[:, 0]), np.abs(y).max())
+        vtol = 1e-8 * np.maximum(np.abs(var[:, 0]), h.variance)
+        assert np.all(np.abs(data[f"mean_{i}_{j}"].reshape(-1) - mean[:, 0]) <= mtol)
+        assert np.all(np.abs(data[f"var_{i}_{j}"].reshape(-1) - var[:, 0]) <= vtol)
