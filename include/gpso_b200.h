@@ -186,6 +186,11 @@ int gpso_set_screen_mode(gpso_handle* h, int mode);
  * launches, out[8] refine windows, out[9] E_var, out[10] E_mean, out[11] mode 5: admissible distance below the best mean (path 4) or the
  * survivors of the mean-bound level when it gave up */
 int gpso_screen_info(gpso_handle* h, double* out12);
+/* 3-digit screening product as CTA pairs (tcgen05.mma.cta_group::2, the B digits of a k-step split between the two shared
+ * memories of a TPC; needs an even number of 128-row blocks) or as single CTAs (default: the pair form moves 17 % fewer
+ * bytes into shared memory and reads 30 % fewer from it, but measured 5.48 vs 5.37 ms per window at N = 4096 -- the kernel is
+ * bound by the accumulator hand-over, not by operand traffic); bit-identical results */
+int gpso_set_screen_pair(gpso_handle* h, int enabled);
 /* Host-only (works without a GPU): the error bound E of the screening pass and its variance / mean parts,
  * out3 = {E, E_var, E_mean}, for N training points, kernel variance, noise variance, the largest power-of-two row scale of
  * L^-1, the sum of the squared row scales, |alpha|_2, the screening digit count (2..4) and the UCB multiplier. */

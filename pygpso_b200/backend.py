@@ -111,6 +111,7 @@ def load_library():
         "gpso_set_l2_window": (i32, [H, i32]),
         "gpso_set_screen_mode": (i32, [H, i32]),
         "gpso_screen_info": (i32, [H, _c_double_p]),
+        "gpso_set_screen_pair": (i32, [H, i32]),
         "gpso_probe_peaks": (i32, [i32, _c_double_p]),
         "gpso_debug_screen_bound": (i32, [i32, dbl, dbl, dbl, dbl, dbl, i32, dbl, _c_double_p]),
         "gpso_debug_product_items": (i64, [i32, i32, i32, ctypes.POINTER(ctypes.c_int), i64, ctypes.POINTER(ctypes.c_int), i32,
@@ -137,7 +138,7 @@ EXPORTED_SYMBOLS = (
     "gpso_export_state_dev gpso_import_state_dev gpso_launch_count gpso_debug_fetch gpso_last_timing gpso_set_window "
     "gpso_set_profile gpso_last_windows gpso_set_predict_mode gpso_predict_info gpso_set_overlap "
     "gpso_set_factor_mode gpso_debug_factor_tasks gpso_debug_trace gpso_set_kinv_mode gpso_set_inverse_mode gpso_set_l2_window gpso_debug_product_items "
-    "gpso_set_screen_mode gpso_screen_info gpso_debug_screen_bound gpso_probe_peaks"
+    "gpso_set_screen_mode gpso_screen_info gpso_debug_screen_bound gpso_probe_peaks gpso_set_screen_pair"
 ).split()
 
 
@@ -338,6 +339,16 @@ class CudaSession:
         results are bit-identical."""
         self.factorized = False
         _check(self._lib, self._lib.gpso_set_screen_mode(self._h, int(mode)), "gpso_set_screen_mode")
+
+    def set_screen_pair(self, enabled=True):
+        """3-digit screening product as CTA pairs (cta_group::2, default) or single CTAs; identical results."""
+        _check(self._lib, self._lib.gpso_set_screen_pair(self._h, int(bool(enabled))), "gpso_set_screen_pair")
+
+    def screened_values(self, count):
+        """Screened UCB (or mean, bound level) of the first ``count`` candidates of the last screened call (tests)."""
+        out = np.empty(int(count))
+        _check(self._lib, self._lib.gpso_debug_fetch(self._h, 5, _dptr(out), out.size), "gpso_debug_fetch")
+        return out
 
     def screen_info(self):
         out = np.zeros(12)

@@ -164,6 +164,8 @@ struct gpso_handle {
     int screen_mode = 1;        // 0 off, 1 automatic (digits adapt to the survivor fraction), 2..4 forced digits
     int screen_S_cur = SCREEN_S_MIN;
     int screen_built_S = 0;     // digits of the tiles in ozAs (0: stale)
+    int screen_pair = 0;        // CTA-pair (cta_group::2) form of the 3-digit screening product (gpso_set_screen_pair); measured no
+                                // faster than single CTAs (5.48 vs 5.37 ms per 174 080-candidate window at N = 4096): off by default
     bool screen_ready = false;  // fp32 copies and norms valid for the factor in force
     double alpha_l2 = 0.0, rho_max = 0.0, rho_l2sq = 0.0;
     // last call: [0] path (0 unscreened, 1 screened, 2 fallback: too many survivors, 3 fallback: check failed), [1] digits,
@@ -301,6 +303,10 @@ static void launch_screen_crosscov_s(gpso_handle* h, cudaStream_t st, const doub
     }
 }
 
+static bool screen_pair_enabled(const gpso_handle* h, int S) {
+    return h->screen_pair && S == ScrPairCfg::S && (h->nb % 2) == 0 && h->nsm >= 2;
+}
+
 template <int S>
 static void launch_screen_product(gpso_handle* h, cudaStream_t st, long long nct, long long ldp, double gscale, const uint8_t* B) {
     ScrParams P;
@@ -317,6 +323,15 @@ static void launch_screen_product(gpso_handle* h, cudaStream_t st, long long nct
     static const int stages_env = getenv("GPSO_SCR_STAGES") ? atoi(getenv("GPSO_SCR_STAGES")) : 0;
     using Cfg = ScrCfg<S, SCR_NT>;
     P.stages = (stages_env >= 2 && stages_env < Cfg::STAGES) ? stages_env : Cfg::STAGES;
+    if (screen_pair_enabled(h, S)) {
+        // CTA pairs (cta_group::2): one cluster per TPC, each pair works on two adjacent row blocks of one candidate tile
+        P.stages = ScrPairCfg::STAGES;
+        const int nbp = h->nb / 2;
+        const long long punits = nct * ((nbp + 1) / 2);
+        const int clusters = (int)std::min<long long>(h->nsm / 2, punits);
+        ozaki_screen_pair_kernel<<<2 * clusters, OZ_THREADS, ScrPairCfg::SMEM_BYTES, st>>>(P);
+        return;
+    }
     const size_t smem = (size_t)P.stages * Cfg::STAGE_BYTES + (Cfg::SMEM_BYTES - Cfg::RING_BYTES);
     const long long units = nct * ((h->nb + 1) / 2);
     const int grid = (int)std::min<long long>(h->nsm, units);
@@ -432,6 +447,8 @@ static int configure_kernels() {
     CU_TRY(cudaFuncSetAttribute(crosscov_screen_kernel<KERNEL_MATERN32, 0, SCR_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_XCOV_SMEM_MAX));
     CU_TRY(cudaFuncSetAttribute(crosscov_screen_kernel<KERNEL_MATERN52, 0, SCR_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_XCOV_SMEM_MAX));
     CU_TRY(cudaFuncSetAttribute(crosscov_screen_kernel<KERNEL_SE, 0, SCR_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_XCOV_SMEM_MAX));
+    CU_TRY(cudaFuncSetAttribute(ozaki_screen_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ScrPairCfg::SMEM_BYTES));
+    CU_TRY(cudaFuncSetAttribute(ozaki_screen_pair_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     GP_TRY(screen_configure<2>());
     GP_TRY(screen_configure<3>());
     GP_TRY(screen_configure<4>());
@@ -1582,7 +1599,11 @@ static int run_screen_windows(gpso_handle* h, cudaStream_t st, const double* Xc_
     if (h->window_override > 0) W = std::max<long long>(1024, h->window_override / 1024 * 1024);
     W = std::min(W, ((M + SCR_NT - 1) / SCR_NT) * SCR_NT);
     const long long nwin = (M + W - 1) / W;
-    const bool overlap = h->overlap && nwin > 1;
+    // Side-stream overlap of the next window's cross-covariance: both kernels are power-bound, so running them side by side
+    // gains nothing measurable (profiles/r02c_screen_trace.json: 86.1 vs 88.4 ms per 2.1e6 candidates), and the CTA-pair
+    // product must not share its SMs with other blocks while its clusters are being placed (a co-resident cross-covariance
+    // kernel stalled it): with the pair kernel the windows run in order on one stream.
+    const bool overlap = h->overlap && nwin > 1 && !screen_pair_enabled(h, S);
     const int nbuf = overlap ? 2 : 1;
     GP_TRY(h->part32.ensure((size_t)W * h->nb * sizeof(float)));
     GP_TRY(h->scr_ucb.ensure((size_t)M * sizeof(double)));
@@ -1597,6 +1618,9 @@ static int run_screen_windows(gpso_handle* h, cudaStream_t st, const double* Xc_
     }
     if (h->screen_built_S != S) {
         GP_TRY(h->ozAs.ensure((size_t)h->Np * h->Np * S));
+        // tiles above the block diagonal stay zero: the CTA-pair kernel runs the shorter row block of a pair over the k-range
+        // of the longer one
+        CU_TRY(cudaMemsetAsync(h->ozAs.p, 0, (size_t)h->Np * h->Np * S, st));
         DISPATCH_SCREEN_S(S, launch_screen_slices, h, st);
         GP_TRY(check_launch(h, "screen_slices"));
         h->screen_built_S = S;
@@ -2135,6 +2159,11 @@ extern "C" int gpso_debug_fetch(gpso_handle* h, int which, double* out_host, int
     GP_TRY(set_device(h));
     CU_TRY(cudaStreamSynchronize(h->stream));
     const int N = h->N, Np = h->Np;
+    if (which == 5) {  // screened value (UCB, or mean for the bound level) of the first `count` candidates of the last screened call
+        if (!h->scr_ucb.p || (size_t)count * sizeof(double) > h->scr_ucb.cap) return fail(GPSO_E_BADARG, "gpso_debug_fetch: no screened values");
+        CU_TRY(cudaMemcpy(out_host, h->scr_ucb.p, sizeof(double) * (size_t)count, cudaMemcpyDeviceToHost));
+        return 0;
+    }
     if (which == 3) {
         if (count < N) return fail(GPSO_E_BADARG, "gpso_debug_fetch: buffer too small");
         CU_TRY(cudaMemcpy(out_host, h->alpha.p, sizeof(double) * N, cudaMemcpyDeviceToHost));
@@ -2267,6 +2296,12 @@ extern "C" int gpso_set_screen_mode(gpso_handle* h, int mode) {
     h->screen_mode = mode;
     h->screen_S_cur = SCREEN_S_MIN;
     h->factorized = false;  // the fp32 copies are prepared by the next gpso_factorize
+    return 0;
+}
+
+extern "C" int gpso_set_screen_pair(gpso_handle* h, int enabled) {
+    if (!h) return fail(GPSO_E_BADARG, "gpso_set_screen_pair: null handle");
+    h->screen_pair = enabled != 0;
     return 0;
 }
 
