@@ -77,6 +77,85 @@ __device__ __forceinline__ float cov32_from_r2(float r2, float var) {
     }
 }
 
+// ---- packed FP32 pairs (sm_100: add / mul / fma .f32x2 -> FADD2 / FMUL2 / FFMA2, one issue slot for two lanes of work) ---------
+// The cross-covariance kernel is issue-bound (83 % of the issue slots busy, FMA pipe 50 %, profiles/r02_ncu_screen_kernels.csv):
+// its two candidates per thread ride in the two halves of one 64-bit register.
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t f2_pack(float lo, float hi) {
+    f32x2_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void f2_unpack(f32x2_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2_t f2_sub(f32x2_t a, f32x2_t b) {
+    f32x2_t r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2_t f2_add(f32x2_t a, f32x2_t b) {
+    f32x2_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2_t f2_mul(f32x2_t a, f32x2_t b) {
+    f32x2_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2_t f2_fma(f32x2_t a, f32x2_t b, f32x2_t c) {
+    f32x2_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ float scr_ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float scr_rsqrt(float x) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// cov32_from_r2 for the two halves of a packed pair (same formulas; exp(-s) = 2^(-s log2 e))
+template <int KID>
+__device__ __forceinline__ f32x2_t cov32x2_from_r2(f32x2_t r2, float var) {
+    const float L2E = 1.4426950408889634f;
+    const f32x2_t var2 = f2_pack(var, var);
+    float a, b;
+    if (KID == KERNEL_SE) {
+        const f32x2_t t = f2_mul(r2, f2_pack(-0.5f * L2E, -0.5f * L2E));
+        f2_unpack(t, a, b);
+        return f2_mul(var2, f2_pack(scr_ex2(a), scr_ex2(b)));
+    } else {
+        f2_unpack(r2, a, b);
+        a = (a < 1e-36f) ? 1e-36f : a;  // NaN propagates (a select, not fmaxf)
+        b = (b < 1e-36f) ? 1e-36f : b;
+        const f32x2_t c = f2_pack(a, b);
+        const f32x2_t r = f2_mul(c, f2_pack(scr_rsqrt(a), scr_rsqrt(b)));
+        if (KID == KERNEL_MATERN52) {
+            const f32x2_t s = f2_mul(r, f2_pack(2.2360679775f, 2.2360679775f));
+            const f32x2_t t = f2_mul(s, f2_pack(-L2E, -L2E));
+            f2_unpack(t, a, b);
+            const f32x2_t e = f2_pack(scr_ex2(a), scr_ex2(b));
+            // 1 + s + 5/3 r^2
+            const f32x2_t poly = f2_add(f2_fma(f2_mul(r, r), f2_pack(1.6666666667f, 1.6666666667f), s), f2_pack(1.0f, 1.0f));
+            return f2_mul(f2_mul(var2, poly), e);
+        } else if (KID == KERNEL_MATERN32) {
+            const f32x2_t s = f2_mul(r, f2_pack(1.7320508076f, 1.7320508076f));
+            const f32x2_t t = f2_mul(s, f2_pack(-L2E, -L2E));
+            f2_unpack(t, a, b);
+            const f32x2_t e = f2_pack(scr_ex2(a), scr_ex2(b));
+            return f2_mul(f2_mul(var2, f2_add(s, f2_pack(1.0f, 1.0f))), e);
+        } else {
+            const f32x2_t t = f2_mul(r, f2_pack(-L2E, -L2E));
+            f2_unpack(t, a, b);
+            return f2_mul(var2, f2_pack(scr_ex2(a), scr_ex2(b)));
+        }
+    }
+}
+
 // balanced base-256 digits of an integer |X| < 2^(8S-2), S <= 4 (32-bit form of oz_digits)
 template <int S>
 __device__ __forceinline__ uint32_t scr_digits(float k, float scale) {
@@ -151,59 +230,75 @@ __global__ void __launch_bounds__(256, 2) crosscov_screen_kernel(const double* _
             cp_async_commit();
         }
         const float* x = sX + b * d * OZ_XK + kg * 16;
-        float r2[2][16];
+        // squared distances of this thread's two candidates (low / high half) to its 16 training points
+        f32x2_t r2[16];
 #pragma unroll
-        for (int i = 0; i < 16; i++) r2[0][i] = r2[1][i] = 0.0f;
+        for (int i = 0; i < 16; i++) r2[i] = 0ULL;
         for (int dim = 0; dim < d; dim++) {
-            const float xa = sC[dim * 64 + cl];
-            const float xb = sC[dim * 64 + cl + 32];
+            const f32x2_t xc = f2_pack(sC[dim * 64 + cl], sC[dim * 64 + cl + 32]);
             const float4* xr = reinterpret_cast<const float4*>(x + dim * OZ_XK);
 #pragma unroll
             for (int i = 0; i < 4; i++) {
                 const float4 xv = xr[i];
-                float df;
-                df = xv.x - xa; r2[0][4 * i] = fmaf(df, df, r2[0][4 * i]);
-                df = xv.y - xa; r2[0][4 * i + 1] = fmaf(df, df, r2[0][4 * i + 1]);
-                df = xv.z - xa; r2[0][4 * i + 2] = fmaf(df, df, r2[0][4 * i + 2]);
-                df = xv.w - xa; r2[0][4 * i + 3] = fmaf(df, df, r2[0][4 * i + 3]);
-                df = xv.x - xb; r2[1][4 * i] = fmaf(df, df, r2[1][4 * i]);
-                df = xv.y - xb; r2[1][4 * i + 1] = fmaf(df, df, r2[1][4 * i + 1]);
-                df = xv.z - xb; r2[1][4 * i + 2] = fmaf(df, df, r2[1][4 * i + 2]);
-                df = xv.w - xb; r2[1][4 * i + 3] = fmaf(df, df, r2[1][4 * i + 3]);
+                f32x2_t df;
+                df = f2_sub(f2_pack(xv.x, xv.x), xc); r2[4 * i] = f2_fma(df, df, r2[4 * i]);
+                df = f2_sub(f2_pack(xv.y, xv.y), xc); r2[4 * i + 1] = f2_fma(df, df, r2[4 * i + 1]);
+                df = f2_sub(f2_pack(xv.z, xv.z), xc); r2[4 * i + 2] = f2_fma(df, df, r2[4 * i + 2]);
+                df = f2_sub(f2_pack(xv.w, xv.w), xc); r2[4 * i + 3] = f2_fma(df, df, r2[4 * i + 3]);
             }
         }
         const int j0 = ss * OZ_XK + kg * 16;
         const int ks = ss * 4 + (kg >> 1), half = kg & 1;
         const float* al = sAl + b * OZ_XK + kg * 16;
+        constexpr int SD = S > 0 ? S : 1;
+        uint32_t out[2][SD][4];
 #pragma unroll
-        for (int a = 0; a < 2; a++) {
-            constexpr int SD = S > 0 ? S : 1;
-            uint32_t out[SD][4];
+        for (int a = 0; a < 2; a++)
 #pragma unroll
-            for (int p = 0; p < SD; p++) out[p][0] = out[p][1] = out[p][2] = out[p][3] = 0u;
-            float msum = 0.0f;
+            for (int p = 0; p < SD; p++) out[a][p][0] = out[a][p][1] = out[a][p][2] = out[a][p][3] = 0u;
+        f32x2_t msum = 0ULL;
+        const f32x2_t bs2 = f2_pack(bscale, bscale);
+        // training points beyond N exist only in the last super-step (padding of the last 128-row block)
+        const bool tail = j0 + 16 > N;
 #pragma unroll
-            for (int g = 0; g < 16; g++) {
-                float k = cov32_from_r2<KID>(r2[a][g], var);
-                k = (cvalid[a] && j0 + g < N) ? k : 0.0f;
-                msum = fmaf(k, al[g], msum);
-                if (S > 0) {
-                    const uint32_t z = scr_digits<SD>(k, bscale);
+        for (int g = 0; g < 16; g++) {
+            f32x2_t k2 = cov32x2_from_r2<KID>(r2[g], var);
+            float k0, k1;
+            f2_unpack(k2, k0, k1);
+            k0 = cvalid[0] ? k0 : 0.0f;
+            k1 = cvalid[1] ? k1 : 0.0f;
+            if (tail && j0 + g >= N) k0 = k1 = 0.0f;
+            k2 = f2_pack(k0, k1);
+            msum = f2_fma(k2, f2_pack(al[g], al[g]), msum);
+            if (S > 0) {
+                float q0, q1;
+                f2_unpack(f2_mul(k2, bs2), q0, q1);
+                constexpr uint32_t C = (SD >= 4) ? 0x00808080u : (SD == 3) ? 0x00008080u : 0x00000080u;
+                const uint32_t z[2] = {((uint32_t)__float2int_rn(q0) + C) ^ C, ((uint32_t)__float2int_rn(q1) + C) ^ C};
+#pragma unroll
+                for (int a = 0; a < 2; a++)
 #pragma unroll
                     for (int p = 0; p < SD; p++) {
                         // digit p (0 = most significant) = byte S-1-p of z -> byte (g & 3) of word g >> 2
                         const uint32_t sel = (0x3210u & ~(0xFu << (4 * (g & 3)))) | ((uint32_t)(4 + (SD - 1 - p)) << (4 * (g & 3)));
-                        out[p][g >> 2] = __byte_perm(out[p][g >> 2], z, sel);
+                        out[a][p][g >> 2] = __byte_perm(out[a][p][g >> 2], z[a], sel);
                     }
-                }
             }
-            macc[a] += (double)msum;
-            if (S > 0) {
+        }
+        {
+            float m0, m1;
+            f2_unpack(msum, m0, m1);
+            macc[0] += (double)m0;
+            macc[1] += (double)m1;
+        }
+        if (S > 0) {
+#pragma unroll
+            for (int a = 0; a < 2; a++) {
                 const int r = rbase + cl + 32 * a;
                 uint8_t* dst = B + ((size_t)ct * nks + ks) * SD * (NT * 32) + (r >> 3) * 256 + half * 128 + (r & 7) * 16;
 #pragma unroll
                 for (int p = 0; p < SD; p++)
-                    *reinterpret_cast<uint4*>(dst + (size_t)p * (NT * 32)) = make_uint4(out[p][0], out[p][1], out[p][2], out[p][3]);
+                    *reinterpret_cast<uint4*>(dst + (size_t)p * (NT * 32)) = make_uint4(out[a][p][0], out[a][p][1], out[a][p][2], out[a][p][3]);
             }
         }
     }
