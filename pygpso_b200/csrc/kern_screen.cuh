@@ -441,13 +441,19 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_screen_kernel(ScrParams P
             acc_ph[buf] ^= 1;
             const uint32_t tacc = tbase + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * Cfg::ACC_COLS + hsel * (NT / 2));
             float tot[NCH];
+            // software-pipelined drain: the TMEM loads of chunk cc+1 are in flight while chunk cc is reduced, so the issuer
+            // (which waits for the hand-over when there is only one accumulator buffer) gets the columns back after the read
+            // time of the tile, not after read + arithmetic
+            uint32_t r[2][S][8];
+#pragma unroll
+            for (int t = 0; t < S; t++) oz_tmem_ld8(tacc + (uint32_t)(t * NT), r[0][t]);
 #pragma unroll
             for (int cc = 0; cc < NCH; cc++) {
-                uint32_t r[S][8];
-#pragma unroll
-                for (int t = 0; t < S; t++) oz_tmem_ld8(tacc + (uint32_t)(t * NT + cc * 8), r[t]);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (cc == NCH - 1) {
+                if (cc + 1 < NCH) {
+#pragma unroll
+                    for (int t = 0; t < S; t++) oz_tmem_ld8(tacc + (uint32_t)(t * NT + (cc + 1) * 8), r[(cc + 1) & 1][t]);
+                } else {
                     oz_fence_before();
                     __syncwarp();
                     if (lane == 0) oz_mbar_arrive(&tmem_empty[buf]);
@@ -455,9 +461,9 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_screen_kernel(ScrParams P
                 float v[8];
 #pragma unroll
                 for (int i = 0; i < 8; i++) {
-                    float w = (float)(int32_t)r[0][i];
+                    float w = (float)(int32_t)r[cc & 1][0][i];
 #pragma unroll
-                    for (int t = 1; t < S; t++) w = fmaf(w, 256.0f, (float)(int32_t)r[t][i]);
+                    for (int t = 1; t < S; t++) w = fmaf(w, 256.0f, (float)(int32_t)r[cc & 1][t][i]);
                     w *= rs;
                     v[i] = w * w;
                 }
