@@ -32,7 +32,9 @@ def _dptr(a):
 
 
 def library_path():
-    return os.path.join(os.path.dirname(os.path.abspath(__file__)), _LIB_NAME)
+    """The in-tree library; ``GPSO_LIBRARY`` points at another build of the same sources (A/B experiments of compile-time
+    kernel parameters)."""
+    return os.environ.get("GPSO_LIBRARY") or os.path.join(os.path.dirname(os.path.abspath(__file__)), _LIB_NAME)
 
 
 _lib = None

@@ -249,7 +249,7 @@ static void launch_crosscov(gpso_handle* h, cudaStream_t st, const double* Xc, l
 
 template <int S>
 static int oz_configure() {
-    CU_TRY(cudaFuncSetAttribute(ozaki_kernel<S, OZ_TRMM>, cudaFuncAttributeMaxDynamicSharedMemorySize, OzCfg<S>::SMEM_BYTES));
+    CU_TRY(cudaFuncSetAttribute(ozaki_kernel<S, OZ_TRMM>, cudaFuncAttributeMaxDynamicSharedMemorySize, OzCfg<S>::SMEM_BYTES_TRMM));
     // full shared-memory carve-out for both kernels: the persistent product CTA (one per SM) must leave room for a
     // cross-covariance block of the next window on the same SM (they use different pipes and overlap)
     CU_TRY(cudaFuncSetAttribute(ozaki_kernel<S, OZ_TRMM>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -323,6 +323,8 @@ static void launch_screen_product(gpso_handle* h, cudaStream_t st, long long nct
     static const int stages_env = getenv("GPSO_SCR_STAGES") ? atoi(getenv("GPSO_SCR_STAGES")) : 0;
     using Cfg = ScrCfg<S, SCR_NT>;
     P.stages = (stages_env >= 2 && stages_env < Cfg::STAGES) ? stages_env : Cfg::STAGES;
+    static const int epi_env = getenv("GPSO_SCR_DEBUG_EPI") ? atoi(getenv("GPSO_SCR_DEBUG_EPI")) : 0;  // timing experiments only
+    P.debug_epi = epi_env;
     if (screen_pair_enabled(h, S)) {
         // CTA pairs (cta_group::2): one cluster per TPC, each pair works on two adjacent row blocks of one candidate tile
         P.stages = ScrPairCfg::STAGES;
@@ -390,7 +392,7 @@ static void launch_oz_trmm(gpso_handle* h, cudaStream_t st, long long nct, long 
     P.Np = h->Np;
     long long units = nct * ((h->nb + 1) / 2);
     int grid = (int)std::min<long long>(h->nsm, units);
-    ozaki_kernel<S, OZ_TRMM><<<grid, OZ_THREADS, OzCfg<S>::SMEM_BYTES, st>>>(P);
+    ozaki_kernel<S, OZ_TRMM><<<grid, OZ_THREADS, OzCfg<S>::SMEM_BYTES_TRMM, st>>>(P);
 }
 
 template <int S>
@@ -1030,7 +1032,8 @@ static int prepare_ozaki(gpso_handle* h, cudaStream_t st) {
     h->rho_max = rho_max;
     h->rho_l2sq = 0.0;
     for (int i = 0; i < h->N; i++) h->rho_l2sq += rs[i] * rs[i];
-    if (h->screen_mode != 0 && Np >= SCREEN_MIN_NP) {
+    static const int scr_min_np = getenv("GPSO_SCREEN_MIN_NP") ? atoi(getenv("GPSO_SCREEN_MIN_NP")) : SCREEN_MIN_NP;
+    if (h->screen_mode != 0 && Np >= scr_min_np) {
         GP_TRY(h->Xs32.ensure((size_t)h->d * Np * sizeof(float)));
         GP_TRY(h->alpha32.ensure((size_t)Np * sizeof(float)));
         screen_convert_kernel<<<(h->d * Np + 255) / 256, 256, 0, st>>>(h->Xs.as<double>(), h->alpha.as<double>(), h->d, Np,
@@ -1059,29 +1062,13 @@ extern "C" int gpso_device_count(void) {
     return n;
 }
 
-extern "C" int gpso_create(int device, int kernel_id, int ard, int mean_id, gpso_handle** out) {
-    if (!out) return fail(GPSO_E_BADARG, "gpso_create: out is null");
-    *out = nullptr;
-    if (kernel_id < 0 || kernel_id > 3) return fail(GPSO_E_BADARG, "gpso_create: unknown kernel id");
-    if (mean_id != GPSO_MEAN_ZERO && mean_id != GPSO_MEAN_CONSTANT) return fail(GPSO_E_BADARG, "gpso_create: unknown mean id");
-    int n = 0;
-    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) return fail(GPSO_E_NOGPU, "gpso_create: no CUDA device available");
-    if (device < 0 || device >= n) return fail(GPSO_E_BADARG, "gpso_create: device index out of range");
-    cudaDeviceProp prop;
-    CU_TRY(cudaGetDeviceProperties(&prop, device));
-    if (prop.major < 10) {
-        char b[256];
-        snprintf(b, sizeof b, "gpso_create: device %d (%s, sm_%d%d) is not a Blackwell sm_100 GPU", device, prop.name, prop.major,
-                 prop.minor);
-        return fail(GPSO_E_NOGPU, b);
-    }
-    CU_TRY(cudaSetDevice(device));
-    gpso_handle* h = new gpso_handle();
+static int init_handle(gpso_handle* h, int device, int kernel_id, int ard, int mean_id, const cudaDeviceProp& prop) {
     h->device = device;
     h->kernel_id = kernel_id;
     h->ard = ard ? 1 : 0;
     h->mean_id = mean_id;
     h->nsm = prop.multiProcessorCount;
+    if (getenv("GPSO_SCREEN_MODE")) h->screen_mode = std::min(std::max(atoi(getenv("GPSO_SCREEN_MODE")), 0), SCREEN_MODE_BOUND);  // tuning experiments
     h->l2_persist_max = (size_t)std::max(0, prop.persistingL2CacheMaxSize);
     h->l2_window_max = (size_t)std::max(0, prop.accessPolicyMaxWindowSize);
     // h->stream carries the tensor-core product kernels: highest priority, so that its persistent CTAs are placed before
@@ -1102,32 +1089,64 @@ extern "C" int gpso_create(int device, int kernel_id, int ard, int mean_id, gpso
     CU_TRY(cudaEventCreate(&h->ev_t0));
     CU_TRY(cudaEventCreate(&h->ev_t1));
     GP_TRY(configure_kernels());
+    return 0;
+}
+
+extern "C" int gpso_destroy(gpso_handle* h);
+
+extern "C" int gpso_create(int device, int kernel_id, int ard, int mean_id, gpso_handle** out) {
+    if (!out) return fail(GPSO_E_BADARG, "gpso_create: out is null");
+    *out = nullptr;
+    if (kernel_id < 0 || kernel_id > 3) return fail(GPSO_E_BADARG, "gpso_create: unknown kernel id");
+    if (mean_id != GPSO_MEAN_ZERO && mean_id != GPSO_MEAN_CONSTANT) return fail(GPSO_E_BADARG, "gpso_create: unknown mean id");
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) return fail(GPSO_E_NOGPU, "gpso_create: no CUDA device available");
+    if (device < 0 || device >= n) return fail(GPSO_E_BADARG, "gpso_create: device index out of range");
+    cudaDeviceProp prop;
+    CU_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        char b[256];
+        snprintf(b, sizeof b, "gpso_create: device %d (%s, sm_%d%d) is not a Blackwell sm_100 GPU", device, prop.name, prop.major,
+                 prop.minor);
+        return fail(GPSO_E_NOGPU, b);
+    }
+    CU_TRY(cudaSetDevice(device));
+    gpso_handle* h = new gpso_handle();
+    int rc = init_handle(h, device, kernel_id, ard, mean_id, prop);
+    if (rc != 0) {
+        gpso_destroy(h);  // releases whatever was created before the failure (null streams / events are skipped)
+        return rc;
+    }
     *out = h;
     return 0;
 }
 
+
 extern "C" int gpso_destroy(gpso_handle* h) {
     if (!h) return 0;
     cudaSetDevice(h->device);
-    cudaStreamSynchronize(h->stream);
-    cudaStreamSynchronize(h->copy_stream);
-    cudaStreamSynchronize(h->aux_stream);
+    // a handle whose creation failed half-way arrives here too: every stream / event may still be null
+    for (cudaStream_t st : {h->stream, h->copy_stream, h->aux_stream})
+        if (st) cudaStreamSynchronize(st);
+    auto drop = [](cudaEvent_t e) {
+        if (e) cudaEventDestroy(e);
+    };
     for (int i = 0; i < 2; i++) {
-        cudaEventDestroy(h->ev_copy[i]);
-        cudaEventDestroy(h->ev_used[i]);
-        cudaEventDestroy(h->ev_xcov[i]);
-        cudaEventDestroy(h->ev_free[i]);
+        drop(h->ev_copy[i]);
+        drop(h->ev_used[i]);
+        drop(h->ev_xcov[i]);
+        drop(h->ev_free[i]);
     }
-    cudaEventDestroy(h->ev_start);
-    cudaStreamDestroy(h->aux_stream);
-    cudaEventDestroy(h->ev_t0);
-    cudaEventDestroy(h->ev_t1);
-    for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
-    for (cudaEvent_t e : h->prod_events) cudaEventDestroy(e);
-    for (cudaEvent_t e : h->trace_events) cudaEventDestroy(e);
-    cudaStreamDestroy(h->stream);
-    cudaStreamDestroy(h->copy_stream);
+    drop(h->ev_start);
+    drop(h->ev_t0);
+    drop(h->ev_t1);
+    for (cudaEvent_t e : h->prof_events) drop(e);
+    for (cudaEvent_t e : h->prod_events) drop(e);
+    for (cudaEvent_t e : h->trace_events) drop(e);
+    for (cudaStream_t st : {h->aux_stream, h->stream, h->copy_stream})
+        if (st) cudaStreamDestroy(st);
     delete h;  // ~DevBuf releases every device buffer of the handle
+    cudaGetLastError();
     return 0;
 }
 
@@ -1579,7 +1598,8 @@ extern "C" int gpso_debug_screen_bound(int N, double variance, double noise, dou
 
 static bool screen_applicable(const gpso_handle* h, long long M) {
     if (h->screen_mode == 0 || !h->screen_ready || h->oz_S == 0 || h->profile) return false;
-    if (h->Np < SCREEN_MIN_NP || M < SCREEN_MIN_M) return false;
+    static const int min_np = getenv("GPSO_SCREEN_MIN_NP") ? atoi(getenv("GPSO_SCREEN_MIN_NP")) : SCREEN_MIN_NP;  // tuning experiments
+    if (h->Np < min_np || M < SCREEN_MIN_M) return false;
     // the fp32 path needs the kernel variance and the lengthscales well inside the float range
     if (!(h->variance > 1e-30 && h->variance < 1e30)) return false;
     for (int i = 0; i < h->n_ls(); i++)

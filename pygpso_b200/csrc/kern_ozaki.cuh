@@ -49,6 +49,14 @@ struct OzCfg {
     static constexpr int STAGES = (S <= 5) ? 6 : (S == 6) ? 5 : 4;
     static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
     static constexpr int SMEM_BYTES = RING_BYTES + 1024 /* barriers + tmem slot */ + 4 * OZ_NT * (int)sizeof(double);
+    // OZ_TRMM: two k-steps per ring stage (consecutive k-steps are contiguous in both digit buffers: one bulk copy of A and one of
+    // B per stage) and ONE tcgen05.commit per stage -- a commit per 32-wide k-step cost ~40 clocks of tensor pipe each (8 % of the
+    // screening product, profiles/README.md round 2).  Every row block has a multiple of 4 k-steps.
+    static constexpr int KPS_TRMM = (S <= 6) ? 2 : 1;
+    static constexpr int STAGE_BYTES_TRMM = KPS_TRMM * STAGE_BYTES;
+    static constexpr int STAGES_TRMM = (S <= 6) ? 3 : STAGES;
+    static constexpr int RING_BYTES_TRMM = STAGES_TRMM * STAGE_BYTES_TRMM;
+    static constexpr int SMEM_BYTES_TRMM = RING_BYTES_TRMM + 1024 + 4 * OZ_NT * (int)sizeof(double);
 };
 
 struct OzParams {
@@ -449,16 +457,19 @@ __global__ void __launch_bounds__(256, 2) crosscov_slices_kernel(const double* _
 template <int S, int MODE>
 __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_kernel(OzParams P) {
     using Cfg = OzCfg<S>;
-    constexpr int STAGES = Cfg::STAGES;
+    constexpr int KPS = (MODE == OZ_TRMM) ? Cfg::KPS_TRMM : 1;                           // k-steps per ring stage
+    constexpr int STAGES = (MODE == OZ_TRMM) ? Cfg::STAGES_TRMM : Cfg::STAGES;
+    constexpr int STAGE_BYTES = KPS * Cfg::STAGE_BYTES;
+    constexpr int RING_BYTES = STAGES * STAGE_BYTES;
     extern __shared__ __align__(1024) uint8_t oz_smem_raw[];
     uint8_t* ring = oz_smem_raw;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(oz_smem_raw + Cfg::RING_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(oz_smem_raw + RING_BYTES);
     uint64_t* full = bars;                  // [STAGES] producer -> issuer (tx bytes)
     uint64_t* empty = bars + STAGES;        // [STAGES] issuer (tcgen05.commit) -> producer
     uint64_t* tmem_full = bars + 2 * STAGES;   // issuer -> epilogue
     uint64_t* tmem_empty = tmem_full + 1;      // epilogue (8 warps) -> issuer
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 1);
-    double* red = reinterpret_cast<double*>(oz_smem_raw + Cfg::RING_BYTES + 1024);  // [4][64]
+    double* red = reinterpret_cast<double*>(oz_smem_raw + RING_BYTES + 1024);  // [4][64]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -495,13 +506,14 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_kernel(OzParams P) {
                 // (OZ_GEMM: the same with another digit buffer)
                 const uint8_t* b = MODE == OZ_TRMM ? P.B + ((size_t)ct * nks + ks0) * S * OZ_B_SLICE
                                                    : P.B + ((size_t)(ct >> 1) * nks + ks0) * S * OZ_A_SLICE + (ct & 1) * OZ_B_SLICE;
-                for (int ks = 0; ks < n; ks++) {
+                for (int ks = 0; ks < n; ks += KPS) {
                     oz_mbar_wait(&empty[st], ph ^ 1);
-                    uint8_t* dst = ring + (size_t)st * Cfg::STAGE_BYTES;
-                    oz_mbar_expect_tx(&full[st], Cfg::STAGE_BYTES);
+                    uint8_t* dst = ring + (size_t)st * STAGE_BYTES;
+                    oz_mbar_expect_tx(&full[st], STAGE_BYTES);
                     if (MODE == OZ_TRMM) {
-                        oz_bulk_g2s_hint(dst, a + (size_t)ks * S * OZ_A_SLICE, S * OZ_A_SLICE, &full[st], keep);
-                        oz_bulk_g2s(dst + S * OZ_A_SLICE, b + (size_t)ks * S * OZ_B_SLICE, S * OZ_B_SLICE, &full[st]);
+                        // stage = [A of KPS k-steps][B of KPS k-steps]
+                        oz_bulk_g2s_hint(dst, a + (size_t)ks * S * OZ_A_SLICE, KPS * S * OZ_A_SLICE, &full[st], keep);
+                        oz_bulk_g2s(dst + KPS * S * OZ_A_SLICE, b + (size_t)ks * S * OZ_B_SLICE, KPS * S * OZ_B_SLICE, &full[st]);
                     } else {
                         oz_bulk_g2s(dst, a + (size_t)ks * S * OZ_A_SLICE, S * OZ_A_SLICE, &full[st]);
 #pragma unroll
@@ -527,23 +539,26 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_kernel(OzParams P) {
             while (items.next(I, ct, ks0, n)) {
                 oz_mbar_wait(tmem_empty, acc_ph ^ 1);  // epilogue has drained the accumulators of the previous item
                 oz_fence_after();
-                for (int ks = 0; ks < n; ks++) {
+                for (int ks = 0; ks < n; ks += KPS) {
                     oz_mbar_wait(&full[st], ph);
                     oz_fence_after();
-                    const uint32_t sa = ring_addr + (uint32_t)st * Cfg::STAGE_BYTES;
-                    const uint32_t sb = sa + S * OZ_A_SLICE;
 #pragma unroll
-                    for (int p = 0; p < S; p++) {
-                        // digit p of A against digits 0..S-1-p of B (stacked along N), level t = p+q -> columns 64 t
-                        const uint64_t ad = oz_desc(sa + p * OZ_A_SLICE);
-                        const int rem = S - p;
-                        const int nch = (rem + 3) / 4;
-                        const int take = (rem + nch - 1) / nch;
+                    for (int kk = 0; kk < KPS; kk++) {
+                        const uint32_t sa = ring_addr + (uint32_t)st * STAGE_BYTES + kk * S * OZ_A_SLICE;
+                        const uint32_t sb = ring_addr + (uint32_t)st * STAGE_BYTES + KPS * S * OZ_A_SLICE + kk * S * OZ_B_SLICE;
 #pragma unroll
-                        for (int q0 = 0; q0 < rem; q0 += take) {
-                            const int nq = (rem - q0 < take) ? rem - q0 : take;
-                            oz_mma(tbase + (uint32_t)((p + q0) * OZ_NT), ad, oz_desc(sb + q0 * OZ_B_SLICE), oz_idesc(nq * OZ_NT),
-                                   (ks > 0 || p > 0) ? 1u : 0u);
+                        for (int p = 0; p < S; p++) {
+                            // digit p of A against digits 0..S-1-p of B (stacked along N), level t = p+q -> columns 64 t
+                            const uint64_t ad = oz_desc(sa + p * OZ_A_SLICE);
+                            const int rem = S - p;
+                            const int nch = (rem + 3) / 4;
+                            const int take = (rem + nch - 1) / nch;
+#pragma unroll
+                            for (int q0 = 0; q0 < rem; q0 += take) {
+                                const int nq = (rem - q0 < take) ? rem - q0 : take;
+                                oz_mma(tbase + (uint32_t)((p + q0) * OZ_NT), ad, oz_desc(sb + q0 * OZ_B_SLICE), oz_idesc(nq * OZ_NT),
+                                       (ks + kk > 0 || p > 0) ? 1u : 0u);
+                            }
                         }
                     }
                     oz_commit(&empty[st]);  // frees the stage once these MMAs have read it

@@ -25,13 +25,19 @@
 namespace gpso {
 
 constexpr int SCR_NT = 128;  // candidates per tile of the screening product
+#ifndef SCR_KPS
+#define SCR_KPS 2
+#endif
 
 template <int S, int NT>
 struct ScrCfg {
     static constexpr int A_BYTES = S * OZ_A_SLICE;
     static constexpr int B_SLICE = NT * 32;
     static constexpr int B_BYTES = S * B_SLICE;
-    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    // k-steps (of 32) per ring stage: one bulk copy of A and one of B per stage (consecutive k-steps are contiguous in both
+    // digit buffers) and ONE tcgen05.commit per stage -- every row block has a multiple of 4 k-steps
+    static constexpr int KPS = SCR_KPS;
+    static constexpr int STAGE_BYTES = KPS * (A_BYTES + B_BYTES);
     // the ring is what hides the L2 latency: bytes in flight / latency is the operand bandwidth this CTA can draw (24 KB
     // chunks, 8 in flight reach 20 TB/s chip-wide, profiles/r01_i8_tcgen05_probe.txt).  192 KB leave room for one
     // cross-covariance block of the next window on the same SM.
@@ -53,6 +59,7 @@ struct ScrParams {
     int nb, nks, nct;
     long long ldp;
     int stages;              // ring depth in use (<= ScrCfg::STAGES; the launch passes the matching dynamic shared memory)
+    int debug_epi;           // timing experiments only: 1 = hand the accumulators back without reading them (results are garbage)
 };
 
 // ---- FP32 covariance (screening only) -----------------------------------------------------------------------------------
@@ -370,12 +377,12 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_screen_kernel(ScrParams P
             while (items.next(I, ct, ks0, n)) {
                 const uint8_t* a = P.A + ((size_t)I * nks) * Cfg::A_BYTES;
                 const uint8_t* b = P.B + ((size_t)ct * nks) * Cfg::B_BYTES;
-                for (int ks = 0; ks < n; ks++) {
+                for (int ks = 0; ks < n; ks += Cfg::KPS) {
                     oz_mbar_wait(&empty[st], ph ^ 1);
                     uint8_t* dst = ring + (size_t)st * Cfg::STAGE_BYTES;
                     oz_mbar_expect_tx(&full[st], Cfg::STAGE_BYTES);
-                    oz_bulk_g2s_hint(dst, a + (size_t)ks * Cfg::A_BYTES, Cfg::A_BYTES, &full[st], keep);
-                    oz_bulk_g2s(dst + Cfg::A_BYTES, b + (size_t)ks * Cfg::B_BYTES, Cfg::B_BYTES, &full[st]);
+                    oz_bulk_g2s_hint(dst, a + (size_t)ks * Cfg::A_BYTES, Cfg::KPS * Cfg::A_BYTES, &full[st], keep);
+                    oz_bulk_g2s(dst + Cfg::KPS * Cfg::A_BYTES, b + (size_t)ks * Cfg::B_BYTES, Cfg::KPS * Cfg::B_BYTES, &full[st]);
                     if (++st == nstages) {
                         st = 0;
                         ph ^= 1;
@@ -396,19 +403,22 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_screen_kernel(ScrParams P
                 oz_mbar_wait(&tmem_empty[buf], acc_ph[buf] ^ 1);  // the epilogue has drained this accumulator buffer
                 oz_fence_after();
                 const uint32_t tacc = tbase + (uint32_t)(buf * Cfg::ACC_COLS);
-                for (int ks = 0; ks < n; ks++) {
+                for (int ks = 0; ks < n; ks += Cfg::KPS) {
                     oz_mbar_wait(&full[st], ph);
                     oz_fence_after();
-                    const uint32_t sa = ring_addr + (uint32_t)st * Cfg::STAGE_BYTES;
-                    const uint32_t sb = sa + Cfg::A_BYTES;
 #pragma unroll
-                    for (int p = 0; p < S; p++) {
-                        const uint64_t ad = oz_desc(sa + p * OZ_A_SLICE);
+                    for (int kk = 0; kk < Cfg::KPS; kk++) {
+                        const uint32_t sa = ring_addr + (uint32_t)st * Cfg::STAGE_BYTES + kk * Cfg::A_BYTES;
+                        const uint32_t sb = ring_addr + (uint32_t)st * Cfg::STAGE_BYTES + Cfg::KPS * Cfg::A_BYTES + kk * Cfg::B_BYTES;
 #pragma unroll
-                        for (int q0 = 0; q0 < S - p; q0 += DPM) {
-                            const int nq = (S - p - q0 < DPM) ? S - p - q0 : DPM;
-                            oz_mma(tacc + (uint32_t)((p + q0) * NT), ad, oz_desc(sb + q0 * Cfg::B_SLICE), oz_idesc(nq * NT),
-                                   (ks > 0 || p > 0) ? 1u : 0u);
+                        for (int p = 0; p < S; p++) {
+                            const uint64_t ad = oz_desc(sa + p * OZ_A_SLICE);
+#pragma unroll
+                            for (int q0 = 0; q0 < S - p; q0 += DPM) {
+                                const int nq = (S - p - q0 < DPM) ? S - p - q0 : DPM;
+                                oz_mma(tacc + (uint32_t)((p + q0) * NT), ad, oz_desc(sb + q0 * Cfg::B_SLICE), oz_idesc(nq * NT),
+                                       (ks + kk > 0 || p > 0) ? 1u : 0u);
+                            }
                         }
                     }
                     oz_commit(&empty[st]);
@@ -440,6 +450,13 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_screen_kernel(ScrParams P
             oz_fence_after();
             acc_ph[buf] ^= 1;
             const uint32_t tacc = tbase + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * Cfg::ACC_COLS + hsel * (NT / 2));
+            if (P.debug_epi == 1) {
+                oz_fence_before();
+                __syncwarp();
+                if (lane == 0) oz_mbar_arrive(&tmem_empty[buf]);
+                buf = (buf + 1 == NBUF) ? 0 : buf + 1;
+                continue;
+            }
             float tot[NCH];
             // software-pipelined drain: the TMEM loads of chunk cc+1 are in flight while chunk cc is reduced, so the issuer
             // (which waits for the hand-over when there is only one accumulator buffer) gets the columns back after the read
