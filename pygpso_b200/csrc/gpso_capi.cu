@@ -1847,7 +1847,9 @@ static int score_argmax(gpso_handle* h, cudaStream_t st, const double* Xc_dev, c
                         double* result_host) {
     for (int i = 0; i < 12; i++) h->scr_info[i] = 0.0;
     h->scr_prod_marks = 0;
-    if (screen_applicable(h, M)) {
+    // the screen keeps one double per candidate: when that does not fit beside the caller's data the call runs unscreened
+    const bool room = screen_applicable(h, M) && h->scr_ucb.ensure((size_t)M * sizeof(double)) == 0;
+    if (room) {
         double E = 0.0, e_var = 0.0, e_mean = 0.0;
         bool ok = false;
         if (h->screen_mode == SCREEN_MODE_BOUND) {

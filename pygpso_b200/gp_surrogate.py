@@ -89,6 +89,7 @@ class GPListOfPoints(list):
         self._key_idx = []    # list positions, parallel to _keys
         self.epoch = 0
         self.uid = next(GPListOfPoints._uids)  # identity of this list for position caches (never pickled)
+        self._labels = None   # positions of the evaluated / GP-based points, ascending (rebuilt lazily after generic edits)
 
     def __reduce__(self):
         # pickle as the plain list of points (the reference class is a bare list subclass); the index is rebuilt lazily
@@ -118,7 +119,31 @@ class GPListOfPoints(list):
 
     def _invalidate(self):
         self._coords, self._count = None, 0
+        self._labels = None
         self.epoch = getattr(self, "epoch", 0) + 1
+
+    # -- positions by label (the optimiser asks for them after every update; a scan of the list per question was a
+    # visible share of a 500-evaluation run) ------------------------------------------------------------------------------
+    def _label_index(self):
+        if getattr(self, "_labels", None) is None:
+            self._labels = {PointLabels.evaluated: [i for i, p in enumerate(self) if p.label == PointLabels.evaluated],
+                            PointLabels.gp_based: [i for i, p in enumerate(self) if p.label == PointLabels.gp_based]}
+        return self._labels
+
+    def positions_with_label(self, label):
+        """Ascending list positions of the points carrying ``label`` (evaluated or gp_based)."""
+        return self._label_index().get(label, [])
+
+    def _label_moved(self, position, old_label, new_label):
+        if getattr(self, "_labels", None) is None or old_label == new_label:
+            return
+        if old_label in self._labels:
+            lst = self._labels[old_label]
+            at = bisect.bisect_left(lst, position)
+            if at < len(lst) and lst[at] == position:
+                del lst[at]
+        if new_label in self._labels:
+            bisect.insort(self._labels[new_label], position)
 
     def _window(self, coords):
         """(projection, lo, hi): the slice of the sorted projections that can hold points within the tolerance."""
@@ -159,6 +184,7 @@ class GPListOfPoints(list):
 
     def _store(self, position, point):
         """Replace the point at ``position`` in place (coordinates may move within the tolerance)."""
+        self._label_moved(position, self[position].label, point.label)
         list.__setitem__(self, position, point)
         new = np.asarray(point.normed_coord, dtype=np.float64).reshape(-1)
         if self._coords is not None and not np.array_equal(self._coords[position], new):
@@ -174,6 +200,8 @@ class GPListOfPoints(list):
         if len(hits) == 0:
             n = len(self)
             super().append(object)
+            if getattr(self, "_labels", None) is not None and object.label in self._labels:
+                self._labels[object.label].append(n)  # positions only grow: the list stays ascending
             if self._coords is not None and self._count == n and n < self._coords.shape[0]:
                 self._coords[n] = object.normed_coord
                 self._count = n + 1
@@ -195,6 +223,7 @@ class GPListOfPoints(list):
         for position, point in zip(positions, new_points):
             assert self[position].label != PointLabels.evaluated
             if coords_unchanged:
+                self._label_moved(position, self[position].label, point.label)
                 list.__setitem__(self, position, point)
             else:
                 self._store(int(position), point)
@@ -280,13 +309,19 @@ class GPSurrogate:
     def _with_label(self, label):
         return [point for point in self.points if point.label == label]
 
+    def _positions(self, label):
+        points = self.points
+        if hasattr(points, "positions_with_label"):
+            return points.positions_with_label(label)
+        return [i for i, point in enumerate(points) if point.label == label]
+
     @property
     def num_evaluated(self):
-        return sum(1 for point in self.points if point.label == PointLabels.evaluated)
+        return len(self._positions(PointLabels.evaluated))
 
     @property
     def num_gp_based(self):
-        return sum(1 for point in self.points if point.label == PointLabels.gp_based)
+        return len(self._positions(PointLabels.gp_based))
 
     @property
     def highest_score(self):
@@ -433,7 +468,7 @@ class GPSurrogate:
         self._gp_train(x=x_train, y=y_train[:, np.newaxis])
         # gp_predict(gp_based_coords) of the reference (gp_surrogate.py:341-342) with the positions carried along: one
         # batched predict_y, then every GP-based point is replaced in place without the per-row duplicate search
-        positions = [i for i, point in enumerate(self.points) if point.label == PointLabels.gp_based]
+        positions = list(self._positions(PointLabels.gp_based))
         if positions:
             coords = np.array([self.points[i].normed_coord for i in positions])
             mean, var = self._require_model().predict_y(coords)

@@ -243,7 +243,10 @@ class GPSOptimiser:
             self.gp_surr.gp_update()
             points = self.gp_surr.points
             epoch, uid = getattr(points, "epoch", None), getattr(points, "uid", None)
-            for leaf in PreOrderIter(self.param_space):
+            # every node once, order irrelevant here: the root's per-depth index instead of a generator walk of the tree
+            by_depth = self.param_space._depth_index() if hasattr(self.param_space, "_depth_index") else None
+            nodes = (leaf for level in by_depth.values() for leaf in level) if by_depth is not None else PreOrderIter(self.param_space)
+            for leaf in nodes:
                 # the position of a node's point does not change while points are only appended / replaced in place; the
                 # cache names the list by its uid (not by reference: a pickled tree must not drag the point list along)
                 cached = getattr(leaf, "_point_ref", None)
