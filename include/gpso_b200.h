@@ -173,7 +173,7 @@ int gpso_set_window(gpso_handle* h, int64_t candidates);
  * sites, gpso/gp_surrogate.py:313-328): all candidates are first scored with `digits` 8-bit digits per operand and an fp32
  * cross-covariance, the candidates whose screened UCB is within 2E of the best one (E = modelled error bound, checked on the
  * survivors) are re-scored by the full-precision engine, and the record of that engine is returned -- bit-identical to the
- * unscreened call.  mode 0 = off, 1 = automatic (default; from N >= 1024 and M >= 65536, digits adapt to the survivor
+ * unscreened call.  mode 0 = off, 1 = automatic (default; from N >= 512 and M >= 65536, digits adapt to the survivor
  * fraction), 2..4 = forced digit count, 5 = bound-and-refine: a first level evaluates only the posterior MEAN of every
  * candidate (the variance lies between the noise variance and prior + noise variance, so a candidate whose mean is more than
  * |varsigma| * kernel variance below the best mean cannot win) and hands its survivors to the full-precision engine; when the

@@ -67,7 +67,8 @@ constexpr int OZ_INV_S = 8;                    // digits per operand of the int8
 constexpr int OZ_INV_MIN_NP = 512;             // automatic mode; measured down to N = 512 (0.498 -> 0.474 ms there, 2.05 -> 1.75 ms at 2048)
 constexpr double OZ_TARGET = 0.02;             // accepted (estimated error) / (parity tolerance 1e-8 * variance)
 // screen-and-refine arg-max (kern_screen.cuh)
-constexpr int SCREEN_MIN_NP = 1024;            // below this the full-precision product is cheap: no screening
+constexpr int SCREEN_MIN_NP = 512;             // below this the full-precision pass is cheap: no screening (config C2, N = 512, 1e5
+                                               // candidates: 1.92e8 -> 2.55e8 candidates/s with the screen, 323 survivors)
 constexpr long long SCREEN_MIN_M = 65536;      // fewer candidates than this: no screening
 constexpr double SCREEN_SAFETY = 4.0;          // error bound E = SAFETY * (model estimate); the refine pass must observe <= E / 4
 constexpr unsigned SCREEN_LIST_CAP = 1u << 20; // survivor list capacity; more survivors than this or than M / 16 -> full pass
@@ -434,6 +435,11 @@ static void launch_grad(gpso_handle* h, cudaStream_t st, int nblk, int stride) {
         default: fn<KERNEL_SE>(__VA_ARGS__); break;                        \
     }
 
+// Function attributes (dynamic shared-memory limits, carve-out preferences) belong to the device's primary context: set once per
+// device and process, not per handle (the ~90 cudaFuncSetAttribute calls cost 0.3 s per gpso_create).
+static bool g_configured[64] = {false};
+static int configure_kernels_once(int device);
+
 static int configure_kernels() {
     CU_TRY(cudaFuncSetAttribute(dense_gemm_kernel<MODE_CHOL_PANEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     CU_TRY(cudaFuncSetAttribute(dense_gemm_kernel<MODE_CHOL_TRAIL>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
@@ -458,6 +464,14 @@ static int configure_kernels() {
     GP_TRY(oz_configure<6>());
     GP_TRY(oz_configure<7>());
     GP_TRY(oz_configure<8>());
+    return 0;
+}
+
+static int configure_kernels_once(int device) {
+    const int slot = device & 63;
+    if (g_configured[slot]) return 0;
+    GP_TRY(configure_kernels());
+    g_configured[slot] = true;
     return 0;
 }
 
@@ -1088,7 +1102,7 @@ static int init_handle(gpso_handle* h, int device, int kernel_id, int ard, int m
     }
     CU_TRY(cudaEventCreate(&h->ev_t0));
     CU_TRY(cudaEventCreate(&h->ev_t1));
-    GP_TRY(configure_kernels());
+    GP_TRY(configure_kernels_once(device));
     return 0;
 }
 
