@@ -637,7 +637,15 @@ def main():
                     roofline["traffic_source"] = entry.get("source")
             except Exception:
                 pass
+        hbm_peak = None
+        try:
+            hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs")
+        except Exception:
+            pass
+        hbm_alg = (80.0 * M * args.steps / (dev_ms * 1e-3)) / 1e9
         roofline.update({
+            "hbm_peak_gbs": hbm_peak, "hbm_peak_source": "MEASURED_PEAKS.json (driver-written)" if hbm_peak else None,
+            "hbm_frac_algorithmic": (hbm_alg / hbm_peak) if hbm_peak else None,
             "hbm_algorithmic_gbs": (80.0 * M * args.steps / (dev_ms * 1e-3)) / 1e9,
             "hbm_note": "algorithmic HBM traffic is 80 B per candidate (coordinates in, fused arg-max out): the pass is compute-bound by "
                         "five orders of magnitude, the 70 %-of-HBM target of north_star cannot apply to a variance pass (SURVEY 7.2)",

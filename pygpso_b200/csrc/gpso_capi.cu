@@ -181,6 +181,7 @@ struct gpso_handle {
     double ls_host[MAX_LS] = {0}, variance = 1.0, noise = 1.0, c0 = 0.0;
     bool have_data = false, factorized = false;
     double factor_nlml = 0.0;
+    double* host_rec = nullptr;  // pinned: results of an evaluation come back in one record without staging copies
     long long launches = 0;
     double last_ms[4] = {0, 0, 0, 0};
     // optional per-stage profiling: 4 events per window on the launch stream
@@ -1102,6 +1103,7 @@ static int init_handle(gpso_handle* h, int device, int kernel_id, int ard, int m
     }
     CU_TRY(cudaEventCreate(&h->ev_t0));
     CU_TRY(cudaEventCreate(&h->ev_t1));
+    CU_TRY(cudaHostAlloc((void**)&h->host_rec, (MAX_LS + 16) * sizeof(double), cudaHostAllocDefault));
     GP_TRY(configure_kernels_once(device));
     return 0;
 }
@@ -1159,6 +1161,7 @@ extern "C" int gpso_destroy(gpso_handle* h) {
     for (cudaEvent_t e : h->trace_events) drop(e);
     for (cudaStream_t st : {h->aux_stream, h->stream, h->copy_stream})
         if (st) cudaStreamDestroy(st);
+    if (h->host_rec) cudaFreeHost(h->host_rec);
     delete h;  // ~DevBuf releases every device buffer of the handle
     cudaGetLastError();
     return 0;
@@ -1228,13 +1231,16 @@ extern "C" int gpso_neg_lml_grad(gpso_handle* h, const double* u, int p, double*
     reduce_partials_kernel<<<stride, 256, 0, st>>>(h->gpart.as<double>(), nblk, stride, h->gout.as<double>());
     GP_TRY(check_launch(h, "reduce_partials"));
     CU_TRY(cudaEventRecord(h->ev_t1, st));
-    double sc[3];
-    std::vector<double> g(stride);
-    int info = 0;
-    CU_TRY(cudaMemcpyAsync(sc, h->scalars.p, sizeof sc, cudaMemcpyDeviceToHost, st));
-    CU_TRY(cudaMemcpyAsync(g.data(), h->gout.p, sizeof(double) * stride, cudaMemcpyDeviceToHost, st));
-    CU_TRY(cudaMemcpyAsync(&info, h->info.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    // one pinned record [scalars(3) | info | gradient partial sums(stride)]: three truly asynchronous copies, one wait
+    double* rec = h->host_rec;
+    CU_TRY(cudaMemcpyAsync(rec, h->scalars.p, 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(rec + 3, h->info.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(rec + 4, h->gout.p, sizeof(double) * stride, cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaStreamSynchronize(st));
+    const double* sc = rec;
+    const double* g = rec + 4;
+    int info = 0;
+    memcpy(&info, rec + 3, sizeof(int));
     float ms = 0;
     cudaEventElapsedTime(&ms, h->ev_t0, h->ev_t1);
     h->last_ms[0] = ms;
@@ -1551,8 +1557,9 @@ static int predict_common_checks(gpso_handle* h, const void* a, long long M, con
 
 static int fetch_best(gpso_handle* h, cudaStream_t st, double* result_host) {
     BestRec r;
-    CU_TRY(cudaMemcpyAsync(&r, h->running.p, sizeof r, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(h->host_rec, h->running.p, sizeof r, cudaMemcpyDeviceToHost, st));  // pinned: no staging copy
     CU_TRY(cudaStreamSynchronize(st));
+    memcpy(&r, h->host_rec, sizeof r);
     prof_collect(h);
     result_host[0] = (double)r.idx;
     result_host[1] = r.mean;
