@@ -315,6 +315,14 @@ def verify_result(session, cuda, X, y, theta, xc_dev, m_local, varsigma, stream,
     return out
 
 
+def side_leg(fn, *a, **kw):
+    """Run a side measurement; a failure there must not cost the headline line (the error text is reported instead)."""
+    try:
+        return fn(*a, **kw)
+    except Exception as err:  # noqa: BLE001
+        return {"error": f"{type(err).__name__}: {err}"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -542,7 +550,7 @@ def main():
     # ---- second half of the BASELINE metric at every GPU count: bounded config-C4 restart leg ---------------------------
     restarts = None
     if not args.no_lml:
-        restarts = bench_restarts(cuda, world, rank)
+        restarts = side_leg(bench_restarts, cuda, world, rank)
 
     if rank == 0:
         assert result_e2e[0] == result[0], "end-to-end and device-resident passes selected different candidates"
@@ -681,10 +689,10 @@ def main():
         }
         # ---- independent confirmation of the selected candidate (single-GPU runs) ----------------------------------------
         if world == 1 and not args.no_verify:
-            line["result"]["verified"] = verify_result(session, cuda, X, y, theta, xc_dev, m_local, varsigma, stream, result, args.screen)
+            line["result"]["verified"] = side_leg(verify_result, session, cuda, X, y, theta, xc_dev, m_local, varsigma, stream, result, args.screen)
         # ---- second half of the BASELINE metric: LML + gradient evaluations per second (the L-BFGS-B closure) ---------
         if world == 1 and not args.no_lml:
-            line["lml_grad"] = bench_lml_grad(cuda, peaks, cpu=not args.no_cpu_baseline)
+            line["lml_grad"] = side_leg(bench_lml_grad, cuda, peaks, cpu=not args.no_cpu_baseline)
         # ---- CPU baseline beside it (bounded sample, rank 0, single GPU runs only) -----------------------------------
         if world == 1 and not args.no_cpu_baseline:
             use_all_host_cores()

@@ -115,3 +115,39 @@ def test_epoch_and_replace_at():
     assert pts.index_by_coords(np.array([0.9, 0.9, 0.9 - 4e-13])) == 5   # still within the tolerance of the moved point
     pts.insert(0, point([0.55, 0.55, 0.55]))       # positions move: cached indices are invalid from here on
     assert pts.epoch != epoch and pts.index_by_coords(np.array([0.9, 0.9, 0.9 + 4e-13])) == 6
+
+
+def test_label_positions_follow_every_kind_of_edit():
+    """The incrementally maintained positions of evaluated / GP-based points equal a literal scan after appends, in-place
+    replacements (GP -> GP, GP -> evaluated), bulk re-predictions and generic list edits, whenever they are asked for."""
+    rng = np.random.default_rng(7)
+    base = rng.random((60, 2))
+    pts = GPListOfPoints()
+
+    def check():
+        for label in (PointLabels.evaluated, PointLabels.gp_based):
+            assert pts.positions_with_label(label) == [i for i, p in enumerate(pts) if p.label == label]
+
+    check()
+    for step in range(600):
+        action = rng.random()
+        if action < 0.70 or len(pts) < 5:
+            label = PointLabels.evaluated if rng.random() < 0.35 else PointLabels.gp_based
+            pts.append(point(base[rng.integers(60)], mu=float(step), label=label))
+        elif action < 0.85:
+            positions = pts.positions_with_label(PointLabels.gp_based)[::2]
+            pts.replace_at(positions, (point(pts[i].normed_coord, mu=-1.0 - step, label=PointLabels.gp_based) for i in positions),
+                           coords_unchanged=True)
+        elif action < 0.92:
+            del pts[int(rng.integers(len(pts)))]          # generic edit: index rebuilt lazily
+        elif action < 0.96:
+            pts.insert(0, point(rng.random(2) + 5.0, label=PointLabels.evaluated))
+        else:
+            pts.extend([point(rng.random(2) + 9.0, label=PointLabels.gp_based)])
+        if step % 7 == 0:
+            check()
+    check()
+    import pickle
+
+    clone = pickle.loads(pickle.dumps(pts))
+    assert clone.positions_with_label(PointLabels.evaluated) == pts.positions_with_label(PointLabels.evaluated)
