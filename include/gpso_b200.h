@@ -177,28 +177,30 @@ int gpso_set_window(gpso_handle* h, int64_t candidates);
  * fraction), 2..4 = forced digit count, 5 = bound-and-refine: a first level evaluates only the posterior MEAN of every
  * candidate (the variance lies between the noise variance and prior + noise variance, so a candidate whose mean is more than
  * |varsigma| * kernel variance below the best mean cannot win) and hands its survivors to the full-precision engine; when the
- * means do not separate the candidates it continues with the automatic digit screen.  Takes effect at the next
- * gpso_factorize.  gpso_predict_y_* and gpso_ucb_topk_* never screen. */
+ * means do not separate the candidates it continues with the automatic digit screen; 6 = forced 2-digit screen with all four
+ * digit pairs (the first rung of the automatic ladder: 2 digits / all pairs, then 3 and 4 digits / triangular).  Takes effect
+ * at the next gpso_factorize.  gpso_predict_y_* and gpso_ucb_topk_* never screen. */
 int gpso_set_screen_mode(gpso_handle* h, int mode);
 /* last fused arg-max call: out[0] path (0 unscreened, 1 screened, 2 full pass: too many survivors, 3 full pass: bound check
  * failed, 4 mean-bound level + refine), out[1] screening digits (0 for path 4), out[2] survivors, out[3] error bound E, out[4] largest |refined - screened| UCB over
  * the survivors, out[5] best screened UCB, out[6] screening windows, out[7] summed duration (ms) of the screening product
- * launches, out[8] refine windows, out[9] E_var, out[10] E_mean, out[11] mode 5: admissible distance below the best mean (path 4) or the
- * survivors of the mean-bound level when it gave up */
+ * launches, out[8] refine windows, out[9] E_var, out[10] E_mean, out[11] 1 when the screening product kept all digit pairs (path 1); mode
+ * 5: admissible distance below the best mean (path 4) */
 int gpso_screen_info(gpso_handle* h, double* out12);
 /* 3-digit screening product as CTA pairs (tcgen05.mma.cta_group::2, the B digits of a k-step split between the two shared
  * memories of a TPC; needs an even number of 128-row blocks) or as single CTAs (default: the pair form moves 17 % fewer
  * bytes into shared memory and reads 30 % fewer from it, but measured 5.48 vs 5.37 ms per window at N = 4096 -- the kernel is
  * bound by the accumulator hand-over, not by operand traffic); bit-identical results */
 int gpso_set_screen_pair(gpso_handle* h, int enabled);
-/* Host-only (works without a GPU): the error bound E of the screening pass and its variance / mean parts,
- * out3 = {E, E_var, E_mean}, for N training points, kernel variance, noise variance, the largest power-of-two row scale of
- * L^-1, the sum of the squared row scales, |alpha|_2, the screening digit count (2..4) and the UCB multiplier. */
 /* Pipe peaks of GPU `device`, measured now (~0.2 s): out4 = {int8 tensor TOP/s (tcgen05 kind::i8 issue rate), FP64 TFLOP/s
  * (DMMA.8x8x4 issue rate), L2 -> shared-memory bulk-copy GB/s, number of SMs}.  bench.py divides by these. */
 int gpso_probe_peaks(int device, double* out4);
-int gpso_debug_screen_bound(int N, double variance, double noise, double rho_max, double rho_l2sq, double alpha_l2, int digits,
-                            double varsigma, double* out3);
+/* Host-only (works without a GPU): the error bound E of the screening pass and its variance / mean parts,
+ * out3 = {E, E_var, E_mean}, for N training points, kernel variance, noise variance and fit5 = {largest power-of-two row scale of
+ * L^-1, sum of the squared row scales, largest row norm of L^-1, |L^-1|_F^2, |alpha|_2}, the screening digit count (2..4), whether
+ * all digit pairs are kept (full product) and the UCB multiplier. */
+int gpso_debug_screen_bound(int N, double variance, double noise, const double* fit5, int digits, int full, double varsigma,
+                            double* out3);
 
 #ifdef __cplusplus
 }

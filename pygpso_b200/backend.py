@@ -115,7 +115,7 @@ def load_library():
         "gpso_screen_info": (i32, [H, _c_double_p]),
         "gpso_set_screen_pair": (i32, [H, i32]),
         "gpso_probe_peaks": (i32, [i32, _c_double_p]),
-        "gpso_debug_screen_bound": (i32, [i32, dbl, dbl, dbl, dbl, dbl, i32, dbl, _c_double_p]),
+        "gpso_debug_screen_bound": (i32, [i32, dbl, dbl, _c_double_p, i32, i32, dbl, _c_double_p]),
         "gpso_debug_product_items": (i64, [i32, i32, i32, ctypes.POINTER(ctypes.c_int), i64, ctypes.POINTER(ctypes.c_int), i32,
                                            ctypes.POINTER(ctypes.c_int)]),
     }
@@ -337,8 +337,8 @@ class CudaSession:
         return {"engine": "int8-tcgen05" if out[0] == 2 else "fp64-dmma", "slices": int(out[1]), "error_estimate_over_tol": float(out[2])}
 
     def set_screen_mode(self, mode=1):
-        """Screen-and-refine arg-max: 0 off, 1 automatic (default), 2..4 forced screening digits, 5 mean-bound level first;
-        results are bit-identical."""
+        """Screen-and-refine arg-max: 0 off, 1 automatic (default), 2..4 forced screening digits (triangular product), 5 mean-bound
+        level first, 6 forced 2 digits with all digit pairs; results are bit-identical."""
         self.factorized = False
         _check(self._lib, self._lib.gpso_set_screen_mode(self._h, int(mode)), "gpso_set_screen_mode")
 
@@ -359,7 +359,8 @@ class CudaSession:
                 4: "mean-bound"}[int(out[0])]
         return {"path": path, "digits": int(out[1]), "survivors": int(out[2]), "error_bound": float(out[3]),
                 "max_observed_deviation": float(out[4]), "best_screened_ucb": float(out[5]), "screen_windows": int(out[6]),
-                "screen_product_ms": float(out[7]), "refine_windows": int(out[8]), "e_var": float(out[9]), "e_mean": float(out[10])}
+                "screen_product_ms": float(out[7]), "refine_windows": int(out[8]), "e_var": float(out[9]), "e_mean": float(out[10]),
+                "all_pairs": bool(out[11] == 1.0 and int(out[0]) != 4)}
 
     def set_window(self, candidates):
         _check(self._lib, self._lib.gpso_set_window(self._h, int(candidates)), "gpso_set_window")

@@ -74,6 +74,7 @@ constexpr double SCREEN_SAFETY = 4.0;          // error bound E = SAFETY * (mode
 constexpr unsigned SCREEN_LIST_CAP = 1u << 20; // survivor list capacity; more survivors than this or than M / 16 -> full pass
 constexpr int SCREEN_S_MIN = 2, SCREEN_S_MAX = 4;
 constexpr int SCREEN_MODE_BOUND = 5;           // gpso_set_screen_mode: mean-bound level first, then the automatic digit screen
+constexpr int SCREEN_MODE_FULL2 = 6;           // gpso_set_screen_mode: forced 2-digit full product
 
 struct DevBuf {
     void* p = nullptr;
@@ -138,7 +139,7 @@ struct gpso_handle {
     DevBuf KsT, part, blockbest, running, cand[2], leaves, omean, ovar, topk;
     int topk_k = 0;         // records per window of the top-k pass in flight
     // int8 tensor-core (tcgen05) variance product: digit tiles of L^-1 and of the cross-covariance window
-    DevBuf ozA, ozBb[2], wmeanb[2], rowscale, rowmax;
+    DevBuf ozA, ozBb[2], wmeanb[2], rowscale, rowmax, rowl2;
     // int8 tensor-core K_y^-1 = L^-T L^-1 (fit path): digit tiles of L^-T, its row scales, the tile -> CTA table
     DevBuf ozT, colscale, colmax, lauum_items;
     int lauum_items_nb = 0, lauum_rounds = 0;
@@ -163,12 +164,13 @@ struct gpso_handle {
     // {max key, survivor count, max |refined - screened|}, survivor index list and gathered survivor coordinates
     DevBuf Xs32, alpha32, ozAs, part32, scr_ucb, scr_state, surv_list, surv_X;
     int screen_mode = 1;        // 0 off, 1 automatic (digits adapt to the survivor fraction), 2..4 forced digits
-    int screen_S_cur = SCREEN_S_MIN;
+    int screen_S_cur = 0;       // rung of SCREEN_LADDER the automatic mode starts from
     int screen_built_S = 0;     // digits of the tiles in ozAs (0: stale)
     int screen_pair = 0;        // CTA-pair (cta_group::2) form of the 3-digit screening product (gpso_set_screen_pair); measured no
                                 // faster than single CTAs (5.48 vs 5.37 ms per 174 080-candidate window at N = 4096): off by default
     bool screen_ready = false;  // fp32 copies and norms valid for the factor in force
     double alpha_l2 = 0.0, rho_max = 0.0, rho_l2sq = 0.0;
+    double linv_frob2 = 0.0, linv_rowl2_max = 0.0;  // |L^-1|_F^2 (= tr K_y^-1) and the largest row norm of L^-1
     // last call: [0] path (0 unscreened, 1 screened, 2 fallback: too many survivors, 3 fallback: check failed), [1] digits,
     // [2] survivors, [3] E, [4] max |refined - screened| over the survivors, [5] best screened UCB, [6] screen windows,
     // [7] screening product ms, [8] refine windows, [9] E_var, [10] E_mean
@@ -268,8 +270,12 @@ static int oz_configure() {
 
 template <int S>
 static int screen_configure() {
-    CU_TRY(cudaFuncSetAttribute(ozaki_screen_kernel<S, SCR_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, ScrCfg<S, SCR_NT>::SMEM_BYTES));
-    CU_TRY(cudaFuncSetAttribute(ozaki_screen_kernel<S, SCR_NT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CU_TRY(cudaFuncSetAttribute(ozaki_screen_kernel<S, SCR_NT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ScrCfg<S, SCR_NT, false>::SMEM_BYTES));
+    CU_TRY(cudaFuncSetAttribute(ozaki_screen_kernel<S, SCR_NT, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    if (S == 2) {
+        CU_TRY(cudaFuncSetAttribute(ozaki_screen_kernel<2, SCR_NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ScrCfg<2, SCR_NT, true>::SMEM_BYTES));
+        CU_TRY(cudaFuncSetAttribute(ozaki_screen_kernel<2, SCR_NT, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    }
     CU_TRY(cudaFuncSetAttribute(crosscov_screen_kernel<KERNEL_MATERN12, S, SCR_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_XCOV_SMEM_MAX));
     CU_TRY(cudaFuncSetAttribute(crosscov_screen_kernel<KERNEL_MATERN32, S, SCR_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_XCOV_SMEM_MAX));
     CU_TRY(cudaFuncSetAttribute(crosscov_screen_kernel<KERNEL_MATERN52, S, SCR_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_XCOV_SMEM_MAX));
@@ -309,8 +315,8 @@ static bool screen_pair_enabled(const gpso_handle* h, int S) {
     return h->screen_pair && S == ScrPairCfg::S && (h->nb % 2) == 0 && h->nsm >= 2;
 }
 
-template <int S>
-static void launch_screen_product(gpso_handle* h, cudaStream_t st, long long nct, long long ldp, double gscale, const uint8_t* B) {
+template <int S, bool FULL>
+static void launch_screen_product_v(gpso_handle* h, cudaStream_t st, long long nct, long long ldp, double gscale, const uint8_t* B) {
     ScrParams P;
     P.A = h->ozAs.as<uint8_t>();
     P.B = B;
@@ -323,11 +329,11 @@ static void launch_screen_product(gpso_handle* h, cudaStream_t st, long long nct
     P.ldp = ldp;
     // ring depth: the whole budget unless GPSO_SCR_STAGES asks for less (co-residency experiments)
     static const int stages_env = getenv("GPSO_SCR_STAGES") ? atoi(getenv("GPSO_SCR_STAGES")) : 0;
-    using Cfg = ScrCfg<S, SCR_NT>;
+    using Cfg = ScrCfg<S, SCR_NT, FULL>;
     P.stages = (stages_env >= 2 && stages_env < Cfg::STAGES) ? stages_env : Cfg::STAGES;
     static const int epi_env = getenv("GPSO_SCR_DEBUG_EPI") ? atoi(getenv("GPSO_SCR_DEBUG_EPI")) : 0;  // timing experiments only
     P.debug_epi = epi_env;
-    if (screen_pair_enabled(h, S)) {
+    if (!FULL && screen_pair_enabled(h, S)) {
         // CTA pairs (cta_group::2): one cluster per TPC, each pair works on two adjacent row blocks of one candidate tile
         P.stages = ScrPairCfg::STAGES;
         const int nbp = h->nb / 2;
@@ -339,7 +345,12 @@ static void launch_screen_product(gpso_handle* h, cudaStream_t st, long long nct
     const size_t smem = (size_t)P.stages * Cfg::STAGE_BYTES + (Cfg::SMEM_BYTES - Cfg::RING_BYTES);
     const long long units = nct * ((h->nb + 1) / 2);
     const int grid = (int)std::min<long long>(h->nsm, units);
-    ozaki_screen_kernel<S, SCR_NT><<<grid, OZ_THREADS, smem, st>>>(P);
+    ozaki_screen_kernel<S, SCR_NT, FULL><<<grid, OZ_THREADS, smem, st>>>(P);
+}
+
+template <int S>
+static void launch_screen_product(gpso_handle* h, cudaStream_t st, long long nct, long long ldp, double gscale, const uint8_t* B) {
+    launch_screen_product_v<S, false>(h, st, nct, ldp, gscale, B);
 }
 
 template <int S>
@@ -1021,10 +1032,13 @@ static int prepare_ozaki(gpso_handle* h, cudaStream_t st) {
     const int Np = h->Np;
     GP_TRY(h->rowscale.ensure((size_t)Np * sizeof(double)));
     GP_TRY(h->rowmax.ensure((size_t)Np * sizeof(double)));
-    linv_rowscale_kernel<false><<<(Np + 7) / 8, 256, 0, st>>>(h->Linv.as<double>(), Np, h->rowscale.as<double>(), h->rowmax.as<double>());
+    GP_TRY(h->rowl2.ensure((size_t)Np * sizeof(double)));
+    linv_rowscale_kernel<false><<<(Np + 7) / 8, 256, 0, st>>>(h->Linv.as<double>(), Np, h->rowscale.as<double>(), h->rowmax.as<double>(),
+                                                              h->rowl2.as<double>());
     GP_TRY(check_launch(h, "linv_rowscale"));
-    std::vector<double> rs(Np);
+    std::vector<double> rs(Np), rl2(Np);
     CU_TRY(cudaMemcpyAsync(rs.data(), h->rowscale.p, sizeof(double) * Np, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(rl2.data(), h->rowl2.p, sizeof(double) * Np, cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaStreamSynchronize(st));
     double rho_max = 0.0;
     for (int i = 0; i < h->N; i++) rho_max = std::max(rho_max, rs[i]);
@@ -1046,7 +1060,13 @@ static int prepare_ozaki(gpso_handle* h, cudaStream_t st) {
     // (both enter the error bound); the low-digit tiles of L^-1 are built by the first screened call (their digit count adapts)
     h->rho_max = rho_max;
     h->rho_l2sq = 0.0;
-    for (int i = 0; i < h->N; i++) h->rho_l2sq += rs[i] * rs[i];
+    h->linv_frob2 = 0.0;
+    h->linv_rowl2_max = 0.0;
+    for (int i = 0; i < h->N; i++) {
+        h->rho_l2sq += rs[i] * rs[i];
+        h->linv_frob2 += rl2[i];
+        h->linv_rowl2_max = std::max(h->linv_rowl2_max, sqrt(rl2[i]));
+    }
     static const int scr_min_np = getenv("GPSO_SCREEN_MIN_NP") ? atoi(getenv("GPSO_SCREEN_MIN_NP")) : SCREEN_MIN_NP;
     if (h->screen_mode != 0 && Np >= scr_min_np) {
         GP_TRY(h->Xs32.ensure((size_t)h->d * Np * sizeof(float)));
@@ -1083,7 +1103,7 @@ static int init_handle(gpso_handle* h, int device, int kernel_id, int ard, int m
     h->ard = ard ? 1 : 0;
     h->mean_id = mean_id;
     h->nsm = prop.multiProcessorCount;
-    if (getenv("GPSO_SCREEN_MODE")) h->screen_mode = std::min(std::max(atoi(getenv("GPSO_SCREEN_MODE")), 0), SCREEN_MODE_BOUND);  // tuning experiments
+    if (getenv("GPSO_SCREEN_MODE")) h->screen_mode = std::min(std::max(atoi(getenv("GPSO_SCREEN_MODE")), 0), SCREEN_MODE_FULL2);  // tuning experiments
     h->l2_persist_max = (size_t)std::max(0, prop.persistingL2CacheMaxSize);
     h->l2_window_max = (size_t)std::max(0, prop.accessPolicyMaxWindowSize);
     // h->stream carries the tensor-core product kernels: highest priority, so that its persistent CTAs are placed before
@@ -1575,45 +1595,81 @@ static int fetch_best(gpso_handle* h, cudaStream_t st, double* result_host) {
 // d var = 2 dk^T K_y^-1 k*  with  |K_y^-1 k*|_2 <= sigma_f / sigma_n, plus the fp32 epilogue.  Mean: dk^T alpha with independent
 // fp32 errors of the covariance values and of the 16-term fp32 partial sums.  Everything times SCREEN_SAFETY; the refine pass
 // checks the bound on every survivor with another factor 4 of margin.
-static void screen_error_model(int N, double variance, double noise, double rho_max, double rho_l2sq, double alpha_l2, int S,
-                               double varsigma, double* e_total, double* e_var_out, double* e_mean_out) {
-    const double sigma_f = sqrt(variance), beta = ldexp(1.0, ilogb(variance) + 1);
-    // per-row standard deviation of the product error: 3 rho_i beta 2^-8S sqrt(N) (operand rounding + neglected levels)
-    const double unit = 3.0 * beta * ldexp(1.0, -8 * S) * sqrt((double)N);
-    const double est_var1 = 2.0 * sigma_f * unit * rho_max;   // first order:  2 sum_i v_i dv_i,  |v|_2 <= sigma_f
-    const double est_var2 = unit * unit * rho_l2sq;           // second order: sum_i dv_i^2 (a bias; matters at 2 digits only)
-    const double eps_k32 = 2.0e-6 * variance;
-    const double var_b = 2.0 * eps_k32 * sigma_f / sqrt(noise);
-    const double var_epi = 1.0e-6 * variance;
+struct ScreenFit {  // what the error model needs to know about a fit
+    int N;
+    double variance, noise;
+    double rho_max, rho_l2sq;        // largest power-of-two row scale of L^-1, sum of their squares
+    double rowl2_max, frob2;         // largest row norm of L^-1, |L^-1|_F^2
+    double alpha_l2;
+};
+
+static void screen_error_model(const ScreenFit& f, int S, int full, double varsigma, double* e_total, double* e_var_out,
+                               double* e_mean_out) {
+    const double sigma_f = sqrt(f.variance), beta = ldexp(1.0, ilogb(f.variance) + 1);
+    const double sqrtN = sqrt((double)f.N);
+    double est_var1, est_var2;
+    if (full) {
+        // all S^2 digit pairs: the product of the rounded operands is exact, what is left is the rounding itself,
+        //   dv_i = sum_k dA_ik b_k + A_ik db_k,  dA_ik ~ U(+-u rho_i), db_k ~ U(+-u beta), u = 2^-(8S-1),  0 <= b_k <= variance:
+        //   Var dv_i = u^2/3 (rho_i^2 |b|^2 + beta^2 |A_i|^2),  |b|^2 <= N variance^2
+        const double u2_3 = ldexp(1.0, -2 * (8 * S - 1)) / 3.0;
+        const double b2 = (double)f.N * f.variance * f.variance;
+        est_var1 = 2.0 * sigma_f * sqrt(u2_3 * (f.rho_max * f.rho_max * b2 + beta * beta * f.rowl2_max * f.rowl2_max));  // 2 sum v_i dv_i
+        est_var2 = u2_3 * (f.rho_l2sq * b2 + beta * beta * f.frob2);                                                      // sum dv_i^2
+    } else {
+        // triangular product (pairs p + q < S): per-row standard deviation c rho_i beta 2^-8S sqrt(N); operand rounding of A and
+        // of B contribute 1.15 each (against the other operand at its bound), the neglected levels 1.3 sqrt(S-1): c = 3 for S <= 4
+        const double unit = 3.0 * beta * ldexp(1.0, -8 * S) * sqrtN;
+        est_var1 = 2.0 * sigma_f * unit * f.rho_max;   // first order:  2 sum_i v_i dv_i,  |v|_2 <= sigma_f
+        est_var2 = unit * unit * f.rho_l2sq;           // second order: sum_i dv_i^2 (a bias; matters at 2 digits only)
+    }
+    const double eps_k32 = 2.0e-6 * f.variance;
+    const double var_b = 2.0 * eps_k32 * sigma_f / sqrt(f.noise);
+    const double var_epi = 1.0e-6 * f.variance;
     const double e_var = SCREEN_SAFETY * (est_var1 + est_var2 + var_b + var_epi);
-    const double e_mean = SCREEN_SAFETY * (eps_k32 + 1.0e-6 * variance) * alpha_l2;
+    const double e_mean = SCREEN_SAFETY * (eps_k32 + 1.0e-6 * f.variance) * f.alpha_l2;
     *e_var_out = e_var;
     *e_mean_out = e_mean;
     *e_total = e_mean + fabs(varsigma) * e_var;
 }
 
-static void screen_error_bound(const gpso_handle* h, int S, double varsigma, double* e_total, double* e_var_out, double* e_mean_out) {
-    screen_error_model(h->N, h->variance, h->noise, h->rho_max, h->rho_l2sq, h->alpha_l2, S, varsigma, e_total, e_var_out, e_mean_out);
+static void screen_error_bound(const gpso_handle* h, int S, bool full, double varsigma, double* e_total, double* e_var_out,
+                               double* e_mean_out) {
+    const ScreenFit f = {h->N, h->variance, h->noise, h->rho_max, h->rho_l2sq, h->linv_rowl2_max, h->linv_frob2, h->alpha_l2};
+    screen_error_model(f, S, full ? 1 : 0, varsigma, e_total, e_var_out, e_mean_out);
 }
 
 // automatic mode: the fewest digits whose variance bound is a screening-grade 5 % of the kernel variance, never below the
 // count the survivor feedback of earlier calls asked for
-static int screen_pick_digits(const gpso_handle* h) {
-    for (int S = std::max(SCREEN_S_MIN, h->screen_S_cur); S <= SCREEN_S_MAX; S++) {
+// The ladder of screening variants, cheapest first: 2 digits with all four digit pairs (16 KB of operands per k-step, exact
+// product of 14-bit operands), then the triangular products of 3 and 4 digits.  screen_S_cur is the rung the survivor
+// feedback of earlier calls asked for.  A rung is tried when its variance bound is below the kernel variance (a screen with
+// a looser bound cannot separate anything); how well it separates THESE candidates only the survivor count can tell.
+struct ScreenVariant { int S; bool full; };
+static const ScreenVariant SCREEN_LADDER[] = {{2, true}, {3, false}, {4, false}};
+constexpr int SCREEN_RUNGS = 3;
+
+[[maybe_unused]] static bool screen_pick_variant(const gpso_handle* h, ScreenVariant* out) {
+    for (int r = std::max(0, h->screen_S_cur); r < SCREEN_RUNGS; r++) {
         double e = 0.0, ev = 0.0, em = 0.0;
-        screen_error_bound(h, S, 0.0, &e, &ev, &em);
-        if (ev <= 0.05 * h->variance) return S;
+        screen_error_bound(h, SCREEN_LADDER[r].S, SCREEN_LADDER[r].full, 0.0, &e, &ev, &em);
+        if (ev <= 1.0 * h->variance) {
+            *out = SCREEN_LADDER[r];
+            return true;
+        }
     }
-    return 0;
+    return false;
 }
 
 // Host-only (no GPU needed): the error bound of the screening pass for a fit with N training points, the given kernel / noise
 // variance, largest power-of-two row scale of L^-1, sum of the squared row scales and |alpha|_2.  out3 = {E, E_var, E_mean}.
 // tests/test_screen_model.py checks it against a numpy emulation of the screening arithmetic.
-extern "C" int gpso_debug_screen_bound(int N, double variance, double noise, double rho_max, double rho_l2sq, double alpha_l2, int digits,
-                                       double varsigma, double* out3) {
-    if (!out3 || N <= 0 || digits < SCREEN_S_MIN || digits > SCREEN_S_MAX) return fail(GPSO_E_BADARG, "gpso_debug_screen_bound: bad argument");
-    screen_error_model(N, variance, noise, rho_max, rho_l2sq, alpha_l2, digits, varsigma, &out3[0], &out3[1], &out3[2]);
+extern "C" int gpso_debug_screen_bound(int N, double variance, double noise, const double* fit5, int digits, int full, double varsigma,
+                                       double* out3) {
+    if (!out3 || !fit5 || N <= 0 || digits < SCREEN_S_MIN || digits > SCREEN_S_MAX)
+        return fail(GPSO_E_BADARG, "gpso_debug_screen_bound: bad argument");
+    const ScreenFit f = {N, variance, noise, fit5[0], fit5[1], fit5[2], fit5[3], fit5[4]};
+    screen_error_model(f, digits, full, varsigma, &out3[0], &out3[1], &out3[2]);
     return 0;
 }
 
@@ -1631,8 +1687,9 @@ static bool screen_applicable(const gpso_handle* h, long long M) {
 // The screening pass over all candidates: per window [H2D] -> fp32 cross-covariance digits (+ mean) on the side stream ->
 // low-digit tensor-core product -> screened UCB per candidate + running maximum.  Same stream / event choreography as
 // run_windows.  Leaves scr_ucb[0..M) and scr_state[0] (key of the maximum) on the device.
-static int run_screen_windows(gpso_handle* h, cudaStream_t st, const double* Xc_dev, const double* Xc_host, long long M, int S,
-                              double varsigma, cudaStream_t* product_stream_out) {
+static int run_screen_windows(gpso_handle* h, cudaStream_t st, const double* Xc_dev, const double* Xc_host, long long M, int S, bool full,
+                              double varsigma, double two_e, bool* hopeless, cudaStream_t* product_stream_out) {
+    *hopeless = false;
     const bool host = Xc_host != nullptr;
     const int d = h->d;
     const long long per_cand = (long long)h->Np * S;
@@ -1644,7 +1701,7 @@ static int run_screen_windows(gpso_handle* h, cudaStream_t st, const double* Xc_
     // gains nothing measurable (profiles/r02c_screen_trace.json: 86.1 vs 88.4 ms per 2.1e6 candidates), and the CTA-pair
     // product must not share its SMs with other blocks while its clusters are being placed (a co-resident cross-covariance
     // kernel stalled it): with the pair kernel the windows run in order on one stream.
-    const bool overlap = h->overlap && nwin > 1 && !screen_pair_enabled(h, S);
+    const bool overlap = h->overlap && nwin > 1 && !(!full && screen_pair_enabled(h, S));
     const int nbuf = overlap ? 2 : 1;
     GP_TRY(h->part32.ensure((size_t)W * h->nb * sizeof(float)));
     GP_TRY(h->scr_ucb.ensure((size_t)M * sizeof(double)));
@@ -1680,9 +1737,11 @@ static int run_screen_windows(gpso_handle* h, cudaStream_t st, const double* Xc_
     if (xs != st) CU_TRY(cudaStreamWaitEvent(xs, h->ev_start, 0));
     if (host) CU_TRY(cudaStreamWaitEvent(cs, h->ev_start, 0));
     bool cand_busy[2] = {false, false}, buf_busy[2] = {false, false};
+    long long nwin_done = nwin;
     const double beta = oz_beta(h);
     const float bscale = (float)(ldexp(1.0, 8 * S - 2) / beta);
-    const double gscale = beta * ldexp(1.0, -2 * (8 * S - 2) + 8 * (S - 1));
+    // triangular product: levels t < S, the lowest kept level has weight 256^0; full product: levels t <= 2S-2
+    const double gscale = full ? beta * ldexp(1.0, -2 * (8 * S - 2)) : beta * ldexp(1.0, -2 * (8 * S - 2) + 8 * (S - 1));
     for (long long w = 0; w < nwin; w++) {
         const int cb = (int)(w & 1);
         const int b = overlap ? cb : 0;
@@ -1714,7 +1773,11 @@ static int run_screen_windows(gpso_handle* h, cudaStream_t st, const double* Xc_
         }
         GP_TRY(prod_mark(h, st));
         GP_TRY(trace_mark(h, st, 3, w));
-        DISPATCH_SCREEN_S(S, launch_screen_product, h, st, Mw_pad / SCR_NT, Mw_pad, gscale, h->ozBb[b].as<uint8_t>());
+        if (full) {
+            launch_screen_product_v<2, true>(h, st, Mw_pad / SCR_NT, Mw_pad, gscale, h->ozBb[b].as<uint8_t>());
+        } else {
+            DISPATCH_SCREEN_S(S, launch_screen_product, h, st, Mw_pad / SCR_NT, Mw_pad, gscale, h->ozBb[b].as<uint8_t>());
+        }
         GP_TRY(check_launch(h, "ozaki_screen"));
         GP_TRY(trace_mark(h, st, 4, w));
         GP_TRY(prod_mark(h, st));
@@ -1728,8 +1791,27 @@ static int run_screen_windows(gpso_handle* h, cudaStream_t st, const double* Xc_
             buf_busy[b] = true;
         }
         h->last_windows++;
+        if (w == 0 && nwin >= 4) {
+            // early verdict on this variant: if more than 1/16 of the first window lies within 2E of the window's own best value
+            // the screen cannot separate these candidates -- stop here instead of paying for the other windows
+            GP_TRY(h->surv_list.ensure(sizeof(long long)));
+            screen_select_kernel<<<(unsigned)((Mw + 255) / 256), 256, 0, st>>>(h->scr_ucb.as<double>(), Mw, two_e,
+                                                                              h->scr_state.as<unsigned long long>(),
+                                                                              h->surv_list.as<long long>(), 0u);
+            GP_TRY(check_launch(h, "screen_select"));
+            unsigned long long st0[2] = {0, 0};
+            CU_TRY(cudaMemcpyAsync(st0, h->scr_state.p, sizeof st0, cudaMemcpyDeviceToHost, st));
+            CU_TRY(cudaStreamSynchronize(st));
+            CU_TRY(cudaMemsetAsync(h->scr_state.as<unsigned long long>() + 1, 0, sizeof(unsigned long long), st));
+            if ((long long)st0[1] * 16 > Mw) {
+                *hopeless = true;
+                h->scr_info[2] = (double)st0[1] * ((double)M / (double)Mw);  // extrapolated survivor count, for the record
+                nwin_done = 1;
+                break;
+            }
+        }
     }
-    h->scr_info[6] = (double)nwin;
+    h->scr_info[6] = (double)nwin_done;
     *product_stream_out = st;
     GP_TRY(set_l2_window(h, h->ozA.p, (size_t)h->Np * h->Np * h->oz_S));  // back on the full-precision tiles (refine pass)
     if (st != user_st) {
@@ -1875,7 +1957,7 @@ static int score_argmax(gpso_handle* h, cudaStream_t st, const double* Xc_dev, c
         bool ok = false;
         if (h->screen_mode == SCREEN_MODE_BOUND) {
             // level 0: posterior mean of every candidate, variance bounded by the prior
-            screen_error_bound(h, SCREEN_S_MAX, varsigma, &E, &e_var, &e_mean);
+            screen_error_bound(h, SCREEN_S_MAX, false, varsigma, &E, &e_var, &e_mean);
             GP_TRY(run_bound_windows(h, st, Xc_dev, Xc_host, M));
             const double width = fabs(varsigma) * h->variance * (1.0 + 2.0e-6);  // |varsigma| (v_max - v_min) with rounding slack
             h->scr_info[1] = 0.0;
@@ -1888,25 +1970,41 @@ static int score_argmax(gpso_handle* h, cudaStream_t st, const double* Xc_dev, c
                 return 0;
             }
             // too many survivors (the means do not separate the candidates) or check failed: digit screen over all candidates
-            h->scr_info[11] = h->scr_info[2];  // survivors of the bound level, kept for the record
         }
-        int S = (h->screen_mode >= 2 && h->screen_mode <= SCREEN_S_MAX) ? std::max(h->screen_mode, SCREEN_S_MIN) : screen_pick_digits(h);
-        if (S >= h->oz_S) S = 0;  // nothing to gain
-        if (S != 0) {
-            screen_error_bound(h, S, varsigma, &E, &e_var, &e_mean);
+        // forced variant, or the ladder from the rung the survivor feedback of earlier calls asked for: a rung that cannot
+        // separate these candidates (too many survivors, seen after the first window or at the end) or whose bound fails the
+        // check hands over to the next, more precise one; after the last rung the call runs the full pass
+        const bool automatic = h->screen_mode == 1 || h->screen_mode == SCREEN_MODE_BOUND;
+        for (int rung = automatic ? std::max(0, h->screen_S_cur) : 0; rung < (automatic ? SCREEN_RUNGS : 1); rung++) {
+            ScreenVariant v = SCREEN_LADDER[std::min(rung, SCREEN_RUNGS - 1)];
+            if (!automatic) {
+                if (h->screen_mode == SCREEN_MODE_FULL2) v = {2, true};
+                else v = {std::min(std::max(h->screen_mode, SCREEN_S_MIN), SCREEN_S_MAX), false};
+            }
+            if (v.S >= h->oz_S) break;  // nothing to gain
+            const int S = v.S;
+            screen_error_bound(h, S, v.full, varsigma, &E, &e_var, &e_mean);
+            if (automatic && !(e_var <= 1.0 * h->variance)) continue;  // a looser bound than the prior variance separates nothing
             cudaStream_t pst = st;
+            bool hopeless = false;
             h->prod_used = 0;
-            GP_TRY(run_screen_windows(h, st, Xc_dev, Xc_host, M, S, varsigma, &pst));
+            GP_TRY(run_screen_windows(h, st, Xc_dev, Xc_host, M, S, v.full, varsigma, 2.0 * E, &hopeless, &pst));
             h->scr_prod_marks = h->prod_used;
             h->scr_info[1] = S;
             h->scr_info[3] = E;
             h->scr_info[9] = e_var;
             h->scr_info[10] = e_mean;
-            GP_TRY(refine_survivors(h, st, Xc_dev, Xc_host, M, varsigma, 2.0 * E, E, false, M / 16, result_host, &ok));
-            // the digit count adapts to the survivor fraction (automatic mode): too many survivors or a failed check -> one
-            // digit more next time
+            h->scr_info[11] = v.full ? 1.0 : 0.0;
+            if (hopeless) {
+                h->scr_info[0] = 2.0;
+                CU_TRY(cudaStreamSynchronize(st));
+                prof_collect(h);
+            } else {
+                GP_TRY(refine_survivors(h, st, Xc_dev, Xc_host, M, varsigma, 2.0 * E, E, false, M / 16, result_host, &ok));
+            }
+            // feedback for later calls: start from the next rung when this one left more than M / 64 survivors or failed
             const long long count = (long long)h->scr_info[2];
-            if (h->screen_mode == 1 && (count * 64 > M || h->scr_info[0] == 3.0) && h->screen_S_cur < SCREEN_S_MAX) h->screen_S_cur++;
+            if (automatic && (hopeless || count * 64 > M || h->scr_info[0] == 3.0)) h->screen_S_cur = std::max(h->screen_S_cur, rung + 1);
             if (ok) {
                 h->scr_info[0] = 1.0;
                 return 0;
@@ -2334,10 +2432,10 @@ extern "C" int gpso_predict_info(gpso_handle* h, double* out3) {
 }
 
 extern "C" int gpso_set_screen_mode(gpso_handle* h, int mode) {
-    if (!h || mode < 0 || mode > SCREEN_MODE_BOUND)
-        return fail(GPSO_E_BADARG, "gpso_set_screen_mode: mode must be 0 (off), 1 (automatic), 2..4 (digits) or 5 (mean bound first)");
+    if (!h || mode < 0 || mode > SCREEN_MODE_FULL2)
+        return fail(GPSO_E_BADARG, "gpso_set_screen_mode: mode must be 0 (off), 1 (automatic), 2..4 (digits), 5 (mean bound first) or 6 (2 digits, all pairs)");
     h->screen_mode = mode;
-    h->screen_S_cur = SCREEN_S_MIN;
+    h->screen_S_cur = 0;
     h->factorized = false;  // the fp32 copies are prepared by the next gpso_factorize
     return 0;
 }

@@ -237,24 +237,35 @@ __device__ __forceinline__ uint32_t oz_put(uint32_t w, unsigned long long z, int
 // ---- A digit tiles from L^-1 ----------------------------------------------------------------------------------------
 // rowscale[i] = 2^(e_i) with max_k |Linv[i,k]| < 2^(e_i - 0) (one warp per row, k <= i only)
 // UPPER: the matrix is L^-T (row i holds column i of L^-1, k >= i)
+// rowl2 (optional): sum of squares of the row -- the error model of the screening pass wants |L^-1|_F^2 and the largest row norm
 template <bool UPPER>
 __global__ void __launch_bounds__(256) linv_rowscale_kernel(const double* __restrict__ Linv, int Np, double* __restrict__ rowscale,
-                                                            double* __restrict__ rowmax) {
+                                                            double* __restrict__ rowmax, double* __restrict__ rowl2 = nullptr) {
     int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= Np) return;
     const double* r = Linv + (size_t)row * Np;
-    double m = 0.0;
+    double m = 0.0, s2 = 0.0;
     if (UPPER) {
-        for (int k = row + lane; k < Np; k += 32) m = fmax(m, fabs(r[k]));
+        for (int k = row + lane; k < Np; k += 32) {
+            m = fmax(m, fabs(r[k]));
+            s2 = fma(r[k], r[k], s2);
+        }
     } else {
-        for (int k = lane; k <= row; k += 32) m = fmax(m, fabs(r[k]));
+        for (int k = lane; k <= row; k += 32) {
+            m = fmax(m, fabs(r[k]));
+            s2 = fma(r[k], r[k], s2);
+        }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    for (int o = 16; o > 0; o >>= 1) {
+        m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
     if (lane == 0) {
         int e = (m > 0.0 && isfinite(m)) ? ilogb(m) + 1 : 0;
         rowscale[row] = ldexp(1.0, e);
         rowmax[row] = m;
+        if (rowl2 != nullptr) rowl2[row] = s2;
     }
 }
 

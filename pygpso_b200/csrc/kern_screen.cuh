@@ -29,7 +29,10 @@ constexpr int SCR_NT = 128;  // candidates per tile of the screening product
 #define SCR_KPS 2
 #endif
 
-template <int S, int NT>
+// FULL: all S^2 digit pairs are kept (levels 0 .. 2S-2): the product of the S-digit operands is then exact and the only error
+// left is the operand rounding -- at S = 2 that is 4 pairs instead of the 6 of the triangular 3-digit product, with 16 KB
+// instead of 24 KB of operands per k-step.  (The triangular 2-digit product drops the pair (1,1), which is as large as the result.)
+template <int S, int NT, bool FULL = false>
 struct ScrCfg {
     static constexpr int A_BYTES = S * OZ_A_SLICE;
     static constexpr int B_SLICE = NT * 32;
@@ -43,7 +46,8 @@ struct ScrCfg {
     // cross-covariance block of the next window on the same SM.
     static constexpr int STAGES = (192 * 1024 / STAGE_BYTES) > 12 ? 12 : (192 * 1024 / STAGE_BYTES);
     static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
-    static constexpr int ACC_COLS = S * NT;                       // TMEM columns of one accumulator buffer
+    static constexpr int LEVELS = FULL ? 2 * S - 1 : S;           // digit-pair levels p + q kept
+    static constexpr int ACC_COLS = LEVELS * NT;                  // TMEM columns of one accumulator buffer
     static constexpr int NBUF = (2 * ACC_COLS <= OZ_TMEM_COLS) ? 2 : 1;
     static constexpr int SMEM_BYTES = RING_BYTES + 1024 + 4 * NT * (int)sizeof(float);
     static_assert(ACC_COLS <= OZ_TMEM_COLS, "accumulator levels do not fit in TMEM");
@@ -322,9 +326,10 @@ __global__ void __launch_bounds__(256, 2) crosscov_screen_kernel(const double* _
 // ---- the screening product ------------------------------------------------------------------------------------------------
 // Same roles as ozaki_kernel: warp 0 producer (cp.async.bulk + mbarrier tx), warp 1 single-thread tcgen05.mma issuer, warps
 // 2..9 epilogue.  Work unit = candidate tile x pair of row blocks (I, nb-1-I) via OzItems<OZ_TRMM> (OzParams-compatible view).
-template <int S, int NT>
+template <int S, int NT, bool FULL>
 __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_screen_kernel(ScrParams P) {
-    using Cfg = ScrCfg<S, NT>;
+    using Cfg = ScrCfg<S, NT, FULL>;
+    constexpr int LEVELS = Cfg::LEVELS;
     constexpr int STAGES = Cfg::STAGES;
     constexpr int NBUF = Cfg::NBUF;
     extern __shared__ __align__(1024) uint8_t scr_smem_raw[];
@@ -410,14 +415,29 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_screen_kernel(ScrParams P
                     for (int kk = 0; kk < Cfg::KPS; kk++) {
                         const uint32_t sa = ring_addr + (uint32_t)st * Cfg::STAGE_BYTES + kk * Cfg::A_BYTES;
                         const uint32_t sb = ring_addr + (uint32_t)st * Cfg::STAGE_BYTES + Cfg::KPS * Cfg::A_BYTES + kk * Cfg::B_BYTES;
+                        if (FULL && ks + kk == 0) {
+                            // first k-step of an item, full product: digit by digit, because one MMA cannot start a level
+                            // (p >= 1: its last B digit opens level p + S - 1) and accumulate into the others
 #pragma unroll
-                        for (int p = 0; p < S; p++) {
-                            const uint64_t ad = oz_desc(sa + p * OZ_A_SLICE);
+                            for (int p = 0; p < S; p++) {
+                                const uint64_t ad = oz_desc(sa + p * OZ_A_SLICE);
 #pragma unroll
-                            for (int q0 = 0; q0 < S - p; q0 += DPM) {
-                                const int nq = (S - p - q0 < DPM) ? S - p - q0 : DPM;
-                                oz_mma(tacc + (uint32_t)((p + q0) * NT), ad, oz_desc(sb + q0 * Cfg::B_SLICE), oz_idesc(nq * NT),
-                                       (ks + kk > 0 || p > 0) ? 1u : 0u);
+                                for (int q = 0; q < S; q++)
+                                    oz_mma(tacc + (uint32_t)((p + q) * NT), ad, oz_desc(sb + q * Cfg::B_SLICE), oz_idesc(NT),
+                                           (p == 0 || q == S - 1) ? 0u : 1u);
+                            }
+                        } else {
+#pragma unroll
+                            for (int p = 0; p < S; p++) {
+                                const uint64_t ad = oz_desc(sa + p * OZ_A_SLICE);
+                                constexpr int SQ = S;  // digits of B
+                                const int nqs = FULL ? SQ : S - p;
+#pragma unroll
+                                for (int q0 = 0; q0 < (FULL ? SQ : S - p); q0 += DPM) {
+                                    const int nq = (nqs - q0 < DPM) ? nqs - q0 : DPM;
+                                    oz_mma(tacc + (uint32_t)((p + q0) * NT), ad, oz_desc(sb + q0 * Cfg::B_SLICE), oz_idesc(nq * NT),
+                                           (ks + kk > 0 || p > 0) ? 1u : 0u);
+                                }
                             }
                         }
                     }
@@ -461,15 +481,15 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_screen_kernel(ScrParams P
             // software-pipelined drain: the TMEM loads of chunk cc+1 are in flight while chunk cc is reduced, so the issuer
             // (which waits for the hand-over when there is only one accumulator buffer) gets the columns back after the read
             // time of the tile, not after read + arithmetic
-            uint32_t r[2][S][8];
+            uint32_t r[2][LEVELS][8];
 #pragma unroll
-            for (int t = 0; t < S; t++) oz_tmem_ld8(tacc + (uint32_t)(t * NT), r[0][t]);
+            for (int t = 0; t < LEVELS; t++) oz_tmem_ld8(tacc + (uint32_t)(t * NT), r[0][t]);
 #pragma unroll
             for (int cc = 0; cc < NCH; cc++) {
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 if (cc + 1 < NCH) {
 #pragma unroll
-                    for (int t = 0; t < S; t++) oz_tmem_ld8(tacc + (uint32_t)(t * NT + (cc + 1) * 8), r[(cc + 1) & 1][t]);
+                    for (int t = 0; t < LEVELS; t++) oz_tmem_ld8(tacc + (uint32_t)(t * NT + (cc + 1) * 8), r[(cc + 1) & 1][t]);
                 } else {
                     oz_fence_before();
                     __syncwarp();
@@ -480,7 +500,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_screen_kernel(ScrParams P
                 for (int i = 0; i < 8; i++) {
                     float w = (float)(int32_t)r[cc & 1][0][i];
 #pragma unroll
-                    for (int t = 1; t < S; t++) w = fmaf(w, 256.0f, (float)(int32_t)r[cc & 1][t][i]);
+                    for (int t = 1; t < LEVELS; t++) w = fmaf(w, 256.0f, (float)(int32_t)r[cc & 1][t][i]);
                     w *= rs;
                     v[i] = w * w;
                 }

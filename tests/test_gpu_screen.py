@@ -38,7 +38,7 @@ def same_record(a, b):
 
 @pytest.mark.parametrize("kernel", ["Matern52", "SquaredExponential", "Matern32", "Matern12"])
 @pytest.mark.parametrize("N,d,M", [(1100, 4, 70_000), (2100, 6, 150_000)])
-@pytest.mark.parametrize("mode", [1, 2, 3, 4, 5])
+@pytest.mark.parametrize("mode", [1, 2, 3, 4, 5, 6])
 def test_screened_argmax_is_bit_identical(cuda, kernel, N, d, M, mode):
     X, y = synthetic(N, d, seed=N)
     h = go.Hyper(0.25 * np.sqrt(d), 1.0, 1e-3, 0.05)
@@ -51,8 +51,10 @@ def test_screened_argmax_is_bit_identical(cuda, kernel, N, d, M, mode):
     if info["path"] in ("screened", "mean-bound"):
         assert info["max_observed_deviation"] <= 0.25 * info["error_bound"]
         assert 1 <= info["survivors"] <= M // 16
-    if mode in (1, 3, 4):  # the model-chosen and the 3/4-digit screens must not need the fall-back on these problems
+    if mode in (1, 3, 4):  # the ladder and the 3/4-digit screens need no full pass here
         assert info["path"] == "screened", info
+    if mode == 6:  # forced 2-digit all-pairs screen: too coarse for these UCB spreads, the call must notice
+        assert info["digits"] == 2 and info["all_pairs"], info
 
 
 def test_screened_matches_oracle_winner(cuda):
@@ -71,7 +73,7 @@ def test_screened_matches_oracle_winner(cuda):
     assert got[0] == go.ucb_argmax(mean, var, VARSIGMA)[0]
 
 
-@pytest.mark.parametrize("mode", [1, 2, 3, 5])
+@pytest.mark.parametrize("mode", [1, 2, 3, 5, 6])
 def test_ties_near_ties_and_nan(cuda, mode):
     N, d, M = 1100, 4, 80_000
     X, y = synthetic(N, d, seed=12)
@@ -186,6 +188,11 @@ def test_c3_shape_screened_vs_full(cuda):
     ref, got, info = both(s, Xc, theta, 1)
     assert same_record(ref, got), (ref, got, info)
     assert info["path"] == "screened" and info["survivors"] < 2000, info
+    assert info["digits"] == 2 and info["all_pairs"], info  # first rung of the ladder is enough on this model
+    ref6, got6, info6 = both(s, Xc, theta, 6)
+    assert same_record(ref, got6) and info6["path"] == "screened", (ref, got6, info6)
+    ref3, got3, info3 = both(s, Xc, theta, 3)
+    assert same_record(ref, got3) and info3["path"] == "screened" and info3["survivors"] <= info6["survivors"], (info3, info6)
     ref5, got5, info5 = both(s, Xc, theta, 5)
     assert same_record(ref, got5), (ref, got5, info5)
     assert info5["path"] == "mean-bound" and info5["survivors"] < 20000, info5

@@ -46,7 +46,7 @@ def cov32(kernel, r2, var):
     return var * np.exp(-r)
 
 
-def emulate_screen(kernel, X, y, h, Xc, S):
+def emulate_screen(kernel, X, y, h, Xc, S, full=False):
     N = X.shape[0]
     K = go.kern(kernel, X, None, h) + h.noise_variance * np.eye(N)
     L = np.linalg.cholesky(K)
@@ -66,10 +66,11 @@ def emulate_screen(kernel, X, y, h, Xc, S):
     XB = np.rint(k32.astype(np.float64) * np.float32(2.0 ** (8 * S - 2) / beta)).astype(np.int64)
     b = digits_of(XB, S)
     acc = np.zeros((N, Xc.shape[0]))
+    top = 2 * S - 2 if full else S - 1  # highest digit-pair level kept (full product: all S^2 pairs)
     for p in range(S):
-        for q in range(S - p):
-            acc += (a[p] @ b[q]) * 256.0 ** (S - 1 - (p + q))  # exact integers in float64
-    gscale = beta * 2.0 ** (-2 * (8 * S - 2) + 8 * (S - 1))
+        for q in range(S if full else S - p):
+            acc += (a[p] @ b[q]) * 256.0 ** (top - (p + q))  # exact integers in float64
+    gscale = beta * 2.0 ** (-2 * (8 * S - 2) + 8 * (S - 1) - 8 * (top - (S - 1)))
     v = (acc.astype(np.float32) * (rowscale * gscale).astype(np.float32)[:, None]).astype(np.float32)
     ss = (v * v).astype(np.float32).sum(axis=0, dtype=np.float32).astype(np.float64)
     var_s = (h.variance - ss) + h.noise_variance
@@ -79,14 +80,17 @@ def emulate_screen(kernel, X, y, h, Xc, S):
     V = Linv @ Ks
     var = (h.variance - (V * V).sum(0)) + h.noise_variance
     mean = Ks.T @ alpha + h.mean_c
-    info = {"rho_max": float(rowscale.max()), "rho_l2sq": float((rowscale ** 2).sum()), "alpha_l2": float(np.linalg.norm(alpha)), "k32_err": float(np.abs(k32 - Ks).max())}
+    rowl2 = np.sqrt((Linv ** 2).sum(axis=1))
+    info = {"rho_max": float(rowscale.max()), "rho_l2sq": float((rowscale ** 2).sum()), "rowl2_max": float(rowl2.max()),
+            "frob2": float((Linv ** 2).sum()), "alpha_l2": float(np.linalg.norm(alpha)), "k32_err": float(np.abs(k32 - Ks).max())}
     return mean_s, var_s, mean, var, info
 
 
-def c_bound(N, variance, noise, rho_max, rho_l2sq, alpha_l2, S, varsigma):
+def c_bound(N, variance, noise, info, S, varsigma, full=False):
     lib = backend.load_library()
     out = (ctypes.c_double * 3)()
-    rc = lib.gpso_debug_screen_bound(N, variance, noise, rho_max, rho_l2sq, alpha_l2, S, varsigma, out)
+    fit5 = (ctypes.c_double * 5)(info["rho_max"], info["rho_l2sq"], info["rowl2_max"], info["frob2"], info["alpha_l2"])
+    rc = lib.gpso_debug_screen_bound(N, variance, noise, fit5, S, int(full), varsigma, out)
     assert rc == 0
     return tuple(out)
 
@@ -102,15 +106,15 @@ CASES = [
 
 
 @pytest.mark.parametrize("kernel,N,d,ls,variance,noise", CASES)
-@pytest.mark.parametrize("S", [2, 3, 4])
-def test_screen_error_bound_holds_with_margin(kernel, N, d, ls, variance, noise, S):
+@pytest.mark.parametrize("S,full", [(2, False), (3, False), (4, False), (2, True)])
+def test_screen_error_bound_holds_with_margin(kernel, N, d, ls, variance, noise, S, full):
     rng = np.random.default_rng(20240517)
     X = rng.random((N, d))
     y = (np.sin(3.0 * X.sum(axis=1)) + 0.01 * rng.standard_normal(N))[:, None]
     h = go.Hyper(ls, variance, noise, 0.1)
     Xc = np.vstack([rng.random((1500, d)), X[:100] + 1e-5 * rng.standard_normal((100, d))])
-    mean_s, var_s, mean, var, info = emulate_screen(kernel, X, y, h, Xc, S)
-    E, e_var, e_mean = c_bound(N, variance, noise, info["rho_max"], info["rho_l2sq"], info["alpha_l2"], S, VARSIGMA)
+    mean_s, var_s, mean, var, info = emulate_screen(kernel, X, y, h, Xc, S, full)
+    E, e_var, e_mean = c_bound(N, variance, noise, info, S, VARSIGMA, full)
     assert info["k32_err"] <= 1.0e-6 * variance  # the model assumes 2e-6 * variance for the fp32 covariance
     dv = np.abs(var_s - var).max()
     dm = np.abs(mean_s - mean).max()
