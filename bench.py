@@ -454,6 +454,7 @@ def main():
         screen["product_ms"] += info["screen_product_ms"]
         screen["windows"] += info["screen_windows"]
         screen["digits"] = info["digits"]
+        screen["all_pairs"] = bool(info["all_pairs"])
         screen["error_bound"] = info["error_bound"]
         screen["max_dev"] = max(screen["max_dev"], info["max_observed_deviation"])
     ev1.record()
@@ -563,7 +564,9 @@ def main():
         ksteps = sum(4 * (i + 1) for i in range(nb))  # k-steps of 32 over the lower-triangular row blocks
         if screened:
             S = screen["digits"]
-            pairs = S * (S + 1) // 2
+            all_pairs = screen.get("all_pairs", False)
+            pairs = S * S if all_pairs else S * (S + 1) // 2  # all digit pairs, or the triangle p + q < S
+            variant = f"{S},128,true" if all_pairs else f"{S},128"
             ops = pairs * flops64
             t_prod = screen["product_ms"] * 1e-3
             achieved = ops / t_prod / 1e12
@@ -573,13 +576,13 @@ def main():
             l2_bytes = (m_local * args.steps / 128.0) * ksteps * S * (4096 + 4096)
             roofline = {
                 "bound": "tensor",
-                "kernel": f"ozaki_screen_kernel<{S},128> (tcgen05.mma kind::i8 screening product: {S} 8-bit digits per operand, {pairs} "
+                "kernel": f"ozaki_screen_kernel<{variant}> (tcgen05.mma kind::i8 screening product: {S} 8-bit digits per operand, {pairs} "
                           "digit pairs, 128-candidate tiles, TMEM accumulators, fp32 epilogue); the survivors are re-scored by "
                           f"ozaki_kernel<{engine['slices']},OZ_TRMM>",
                 "achieved": achieved, "peak": peaks["int8_tops"], "unit": "TFLOP/s", "frac": achieved / peaks["int8_tops"],
                 "frac_at_clock": (achieved / (peaks["int8_tops"] * clock_ratio)) if clock_ratio else None,
                 "op_kind": "int8 tensor op (2 per multiply-add); algorithmic = digit_pairs * N^2 per candidate",
-                "digits": S, "digit_pairs": pairs,
+                "digits": S, "digit_pairs": pairs, "all_digit_pairs": all_pairs,
                 "traffic": None,
                 "peak_source": "measured in this run: tcgen05.mma.cta_group::1.kind::i8 M=128 N=256 issue rate on all SMs "
                                "(gpso_probe_peaks); MEASURED_PEAKS.json has no int8 entry",
@@ -639,7 +642,8 @@ def main():
         prof_json = os.path.join(ROOT, "profiles", "product_kernel_traffic.json")
         if os.path.exists(prof_json):
             try:
-                entry = json.load(open(prof_json)).get(f"{args.workload}:{'screen' if screened else engine['engine']}")
+                variant_key = f"screen{screen['digits']}{'f' if screen.get('all_pairs') else ''}" if screened else engine["engine"]
+                entry = json.load(open(prof_json)).get(f"{args.workload}:{variant_key}")
                 if entry:
                     roofline["traffic"] = entry.get("dram_bytes_per_launch")
                     roofline["traffic_source"] = entry.get("source")
@@ -668,7 +672,7 @@ def main():
             "run": {"parallelism": f"candidates sharded over {world} GPU(s)", "engine": engine,
                     "l2": "inputs larger than L2: 80 B/candidate x M candidates in HBM plus two 2 GiB rolling windows of "
                           "cross-covariance digit tiles per GPU vs 126 MB L2"},
-            "screen": {"mode": args.screen, "paths": sorted(set(screen["paths"])), "digits": screen["digits"],
+            "screen": {"mode": args.screen, "paths": sorted(set(screen["paths"])), "digits": screen["digits"], "all_digit_pairs": screen.get("all_pairs", False),
                        "survivors_per_step": screen["survivors"], "survivors_per_window": (float(np.mean(screen["survivors"])) /
                                                                                          max(screen["windows"] / max(args.steps, 1), 1)),
                        "error_bound": screen["error_bound"], "max_observed_deviation": screen["max_dev"],

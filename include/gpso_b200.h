@@ -163,6 +163,13 @@ int gpso_set_overlap(gpso_handle* h, int enabled);
  * launch per step (diagonal block, panel, trailing update).  Same tile arithmetic; the schedules differ in summation order
  * only (wide K = 512 updates, one update fused into the diagonal block), i.e. at rounding level. */
 int gpso_set_factor_mode(gpso_handle* h, int mode);
+/* mode 1 is the default and means "automatic": matrices of more than 32 tiles (N > 4096) use the HYBRID factorisation -- the
+ * matrix is split recursively at powers of two; the leaves (<= 4096 rows) go through the persistent FP64 kernel in place, the
+ * panel L21 = A21 L11^-T and the Schur complement A22 -= L21 L21^T are exact-integer products on the int8 tensor cores
+ * (8 digits per operand), and the inverse factor's level that merges the two halves follows immediately.  mode 2 = always one
+ * persistent FP64 kernel (round-1 behaviour), mode 3 = hybrid down to leaves of 2 tiles (tests).
+ * gpso_factor_info: out2 = {schedule of the last factorisation: 0 stepwise / 1 persistent / 2 hybrid, inner nodes of the hybrid}. */
+int gpso_factor_info(gpso_handle* h, int* out2);
 /* Host-only introspection (works without a GPU): the task list of the persistent factorisation kernel for a matrix of nb
  * 128-wide panels on nsm SMs, 16 ints per task (op, p, i, j, s, tile, 3 x dependency counter, 3 x value, counter to
  * signal, value / 0 = increment, 2 unused).  out may be NULL to query the sizes. */

@@ -104,6 +104,7 @@ def load_library():
         "gpso_predict_info": (i32, [H, _c_double_p]),
         "gpso_set_overlap": (i32, [H, i32]),
         "gpso_set_factor_mode": (i32, [H, i32]),
+        "gpso_factor_info": (i32, [H, ctypes.POINTER(ctypes.c_int)]),
         "gpso_debug_factor_tasks": (i32, [i32, i32, ctypes.POINTER(ctypes.c_int), i64, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]),
         "gpso_set_profile": (i32, [H, i32]),
         "gpso_last_windows": (i64, [H]),
@@ -139,7 +140,7 @@ EXPORTED_SYMBOLS = (
     "gpso_grow_count gpso_grow_leaves_host gpso_grow_leaves_dev gpso_grow_ucb_argmax gpso_grow_ucb_argmax_range gpso_state_bytes "
     "gpso_export_state_dev gpso_import_state_dev gpso_launch_count gpso_debug_fetch gpso_last_timing gpso_set_window "
     "gpso_set_profile gpso_last_windows gpso_set_predict_mode gpso_predict_info gpso_set_overlap "
-    "gpso_set_factor_mode gpso_debug_factor_tasks gpso_debug_trace gpso_set_kinv_mode gpso_set_inverse_mode gpso_set_l2_window gpso_debug_product_items "
+    "gpso_set_factor_mode gpso_factor_info gpso_debug_factor_tasks gpso_debug_trace gpso_set_kinv_mode gpso_set_inverse_mode gpso_set_l2_window gpso_debug_product_items "
     "gpso_set_screen_mode gpso_screen_info gpso_debug_screen_bound gpso_probe_peaks gpso_set_screen_pair"
 ).split()
 
@@ -323,10 +324,19 @@ class CudaSession:
         self.factorized = False
         _check(self._lib, self._lib.gpso_set_inverse_mode(self._h, int(mode)), "gpso_set_inverse_mode")
 
-    def set_factor_mode(self, persistent=True):
-        """Cholesky schedule: persistent dataflow kernel (default) or one launch per step; bit-identical results."""
+    def set_factor_mode(self, persistent=True, hybrid=None):
+        """Cholesky schedule: persistent dataflow kernel (default) or one launch per step.  ``hybrid``: None = automatic
+        (matrices above 4096 rows are split recursively: FP64 leaves, int8 tensor-core panels and Schur complements),
+        False = always one persistent FP64 kernel, True = split down to leaves of two tiles (tests)."""
         self.factorized = False
-        _check(self._lib, self._lib.gpso_set_factor_mode(self._h, int(bool(persistent))), "gpso_set_factor_mode")
+        mode = 0 if not persistent else (1 if hybrid is None else (3 if hybrid else 2))
+        _check(self._lib, self._lib.gpso_set_factor_mode(self._h, mode), "gpso_set_factor_mode")
+
+    def factor_info(self):
+        """Schedule of the last factorisation: {"schedule": "stepwise" | "persistent" | "hybrid", "nodes": inner nodes}."""
+        out = (ctypes.c_int * 2)()
+        _check(self._lib, self._lib.gpso_factor_info(self._h, out), "gpso_factor_info")
+        return {"schedule": ("stepwise", "persistent", "hybrid")[out[0]], "nodes": int(out[1])}
 
     def set_overlap(self, enabled=True):
         _check(self._lib, self._lib.gpso_set_overlap(self._h, int(bool(enabled))), "gpso_set_overlap")

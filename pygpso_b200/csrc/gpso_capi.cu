@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <array>
 #include <string>
+#include <map>
 #include <vector>
 
 #include "common.cuh"
@@ -146,12 +147,19 @@ struct gpso_handle {
     int kinv_mode = 0;      // 0 = automatic (int8 from OZ_KINV_MIN_NP), 1 = FP64 DMMA tiles, 2 = int8 tcgen05
     // int8 tensor-core inverse factor (recursive doubling, two products per level): digit tiles and row scales of the four
     // operands (L, L^-T block diagonal, L^-1 block diagonal, X^T) and the per-level tile -> CTA tables
-    DevBuf ozL, ozLT, ozLI, ozXT, rsL, rsLT, rsLI, rsXT, inv_items;
+    DevBuf ozL, ozLT, ozLI, ozXT, rsL, rsLT, rsLI, rsXT;
     struct InvLevel { int s; size_t xt_off; int xt_rounds; size_t y_off; int y_rounds; };
-    std::vector<InvLevel> inv_levels;
-    int inv_items_nb = 0;
     int inverse_mode = 0;   // 0 = automatic (int8 from OZ_INV_MIN_NP), 1 = FP64 DMMA tile tasks, 2 = int8 tcgen05
     bool chol_tasks_inv = true;  // whether the cached task list contains the inverse-factor tasks
+    // hybrid factorisation (hybrid_node): task lists / item tables per sub-matrix size, built on first use
+    struct FactorPlan { DevBuf tasks; int ntasks = 0, ncounters = 0; };
+    struct InvPlan { DevBuf items; std::vector<InvLevel> levels; };
+    struct ItemList { DevBuf items; int rounds = 0; };
+    std::map<int, FactorPlan> factor_plans;    // key 2 n + with_inverse
+    std::map<int, InvPlan> inv_plans;          // key n
+    std::map<long long, ItemList> hyb_items;   // key (kind, split, n)
+    int hybrid_mode = 0;    // 0 = automatic (matrices of more than HYB_MIN_TILES tiles), 1 = off, 2 = always (leaves of 2 tiles: tests)
+    int hybrid_nodes = 0;   // inner nodes of the last factorisation (0 = one persistent kernel)
     cudaStream_t aux_stream = nullptr;
     cudaEvent_t ev_start = nullptr, ev_xcov[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
     int overlap = 1;
@@ -274,7 +282,9 @@ static int screen_configure() {
     CU_TRY(cudaFuncSetAttribute(ozaki_screen_kernel<S, SCR_NT, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     if (S == 2) {
         CU_TRY(cudaFuncSetAttribute(ozaki_screen_kernel<2, SCR_NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ScrCfg<2, SCR_NT, true>::SMEM_BYTES));
+        CU_TRY(cudaFuncSetAttribute(ozaki_screen_kernel<2, SCR_NT, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, ScrCfg<2, SCR_NT, true, 4>::SMEM_BYTES));
         CU_TRY(cudaFuncSetAttribute(ozaki_screen_kernel<2, SCR_NT, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CU_TRY(cudaFuncSetAttribute(ozaki_screen_kernel<2, SCR_NT, true, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     }
     CU_TRY(cudaFuncSetAttribute(crosscov_screen_kernel<KERNEL_MATERN12, S, SCR_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_XCOV_SMEM_MAX));
     CU_TRY(cudaFuncSetAttribute(crosscov_screen_kernel<KERNEL_MATERN32, S, SCR_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_XCOV_SMEM_MAX));
@@ -315,7 +325,7 @@ static bool screen_pair_enabled(const gpso_handle* h, int S) {
     return h->screen_pair && S == ScrPairCfg::S && (h->nb % 2) == 0 && h->nsm >= 2;
 }
 
-template <int S, bool FULL>
+template <int S, bool FULL, int KPSV = SCR_KPS>
 static void launch_screen_product_v(gpso_handle* h, cudaStream_t st, long long nct, long long ldp, double gscale, const uint8_t* B) {
     ScrParams P;
     P.A = h->ozAs.as<uint8_t>();
@@ -329,7 +339,7 @@ static void launch_screen_product_v(gpso_handle* h, cudaStream_t st, long long n
     P.ldp = ldp;
     // ring depth: the whole budget unless GPSO_SCR_STAGES asks for less (co-residency experiments)
     static const int stages_env = getenv("GPSO_SCR_STAGES") ? atoi(getenv("GPSO_SCR_STAGES")) : 0;
-    using Cfg = ScrCfg<S, SCR_NT, FULL>;
+    using Cfg = ScrCfg<S, SCR_NT, FULL, KPSV>;
     P.stages = (stages_env >= 2 && stages_env < Cfg::STAGES) ? stages_env : Cfg::STAGES;
     static const int epi_env = getenv("GPSO_SCR_DEBUG_EPI") ? atoi(getenv("GPSO_SCR_DEBUG_EPI")) : 0;  // timing experiments only
     P.debug_epi = epi_env;
@@ -345,7 +355,7 @@ static void launch_screen_product_v(gpso_handle* h, cudaStream_t st, long long n
     const size_t smem = (size_t)P.stages * Cfg::STAGE_BYTES + (Cfg::SMEM_BYTES - Cfg::RING_BYTES);
     const long long units = nct * ((h->nb + 1) / 2);
     const int grid = (int)std::min<long long>(h->nsm, units);
-    ozaki_screen_kernel<S, SCR_NT, FULL><<<grid, OZ_THREADS, smem, st>>>(P);
+    ozaki_screen_kernel<S, SCR_NT, FULL, KPSV><<<grid, OZ_THREADS, smem, st>>>(P);
 }
 
 template <int S>
@@ -561,9 +571,14 @@ static int make_factor_tasks(int nb, int nsm, std::vector<int>& flat, int& ntask
     const int TR_ALL = nb * nb;                                    // transposes completed
     auto XTD = [nb, LV](int l, int q) { return nb * nb + 1 + l * nb + q; };
     auto YD = [nb, LV](int l, int q) { return nb * nb + 1 + LV * nb + l * nb + q; };
-    const int ncounters = nb * nb + 1 + 2 * LV * nb;
+    auto STRIP = [nb, LV](int j) { return nb * nb + 1 + 2 * LV * nb + j; };  // strips of the tile (j+1, j) completed
+    const int ncounters = nb * nb + 1 + 2 * LV * nb + nb;
     auto ops = [W](int j) { return chol_ops(j, W); };
     auto fin = [W](int j) { return chol_ops(j, W) + 1; };
+    // "tile (i, j) is final": its own counter, or for the strip-solved tile below the diagonal the strip counter
+    static const bool split = !(getenv("GPSO_PANEL_STRIPS") && atoi(getenv("GPSO_PANEL_STRIPS")) == 0);  // A/B only
+    auto FINC = [&](int i, int j) { return (split && i == j + 1) ? STRIP(j) : T(i, j); };
+    auto FINV = [&](int i, int j) { return (split && i == j + 1) ? PANEL_STRIPS : fin(j); };
 
     const double t_wide_us = 17.0 * W + 12.0;  // tile time of a wide update (DMMA at peak + tile write-back)
     const double pops_per_us = nsm / t_wide_us;
@@ -578,7 +593,7 @@ static int make_factor_tasks(int nb, int nsm, std::vector<int>& flat, int& ntask
     };
     auto wide_task = [&](int b, int i, int j) {
         const int p0 = b * W, p1 = std::min(nb, p0 + W), last = p1 - 1;
-        return FactorTask(CT_UPD, p0, i, j, p1 - p0, 0).dep(T(i, last), fin(last)).dep(T(j, last), fin(last)).dep(T(i, j), b).done(T(i, j), b + 1);
+        return FactorTask(CT_UPD, p0, i, j, p1 - p0, 0).dep(FINC(i, last), FINV(i, last)).dep(FINC(j, last), FINV(j, last)).dep(T(i, j), b).done(T(i, j), b + 1);
     };
     const int nblk = (nb + W - 1) / W;
     for (int b = 0; b < nblk; b++) {
@@ -586,7 +601,7 @@ static int make_factor_tasks(int nb, int nsm, std::vector<int>& flat, int& ntask
         for (int p = p0; p < p1; p++) {
             const int nprev = p == 0 ? 0 : (p % W != 0 ? 1 : W);
             FactorTask dg(CT_DIAG, p, p, p, nprev, 0);
-            if (p > 0) dg.dep(T(p, p), ops(p) - 1).dep(T(p, p - 1), fin(p - 1));
+            if (p > 0) dg.dep(T(p, p), ops(p) - 1).dep(FINC(p, p - 1), FINV(p, p - 1));
             q.push_back(dg.done(T(p, p), fin(p)));
             size_t narrow = 0;
             if (p > p0)
@@ -594,12 +609,18 @@ static int make_factor_tasks(int nb, int nsm, std::vector<int>& flat, int& ntask
                     for (int i = j; i < nb; i++)
                         if (!(i == p && j == p)) {
                             const int at = j / W + (p - 1) % W;  // updates tile (i,j) has received before this one
-                            q.push_back(FactorTask(CT_UPD, p - 1, i, j, 1, 0).dep(T(i, p - 1), fin(p - 1)).dep(T(j, p - 1), fin(p - 1)).dep(T(i, j), at).done(T(i, j), at + 1));
+                            q.push_back(FactorTask(CT_UPD, p - 1, i, j, 1, 0).dep(FINC(i, p - 1), FINV(i, p - 1)).dep(FINC(j, p - 1), FINV(j, p - 1)).dep(T(i, j), at).done(T(i, j), at + 1));
                             narrow++;
                         }
             cover((p > p0 ? 42.0 : 30.0 + 10.0 * nprev) - narrow * 30.0 / nsm);
-            for (int i = p + 1; i < nb; i++)
+            for (int i = p + 1; i < nb; i++) {
+                if (split && i == p + 1) {
+                    for (int k = 0; k < PANEL_STRIPS; k++)
+                        q.push_back(FactorTask(CT_PANEL, p, i, p, k + 1, 0).dep(T(p, p), fin(p)).dep(T(i, p), ops(p)).done(STRIP(p), 0));
+                    continue;
+                }
                 q.push_back(FactorTask(CT_PANEL, p, i, p, 0, 0).dep(T(p, p), fin(p)).dep(T(i, p), ops(p)).done(T(i, p), fin(p)));
+            }
             q.push_back(FactorTask(CT_TRANSPOSE, p, p, p, 0, 0).dep(T(p, p), fin(p)).done(TR_ALL, 0));
             cover(22.0);
         }
@@ -632,7 +653,7 @@ static int make_factor_tasks(int nb, int nsm, std::vector<int>& flat, int& ntask
                             FactorTask t(CT_XT, 0, 0, 0, s, off[qq] + u * nv + v);
                             t.dep(TR_ALL, nb);
                             if (s > 1) t.dep(YD(l - 1, 2 * qq), (s / 2) * (s / 2));
-                            t.dep(T(a + s + v, a + s - 1), fin(a + s - 1));
+                            t.dep(FINC(a + s + v, a + s - 1), FINV(a + s + v, a + s - 1));
                             q.push_back(t.done(XTD(l, qq), 0));
                         }
                 } else {
@@ -657,6 +678,18 @@ static int make_factor_tasks(int nb, int nsm, std::vector<int>& flat, int& ntask
     for (const FactorTask& t : q) flat.insert(flat.end(), t.w, t.w + TASK_WORDS);
     ntasks = (int)q.size();
     ncounters_out = ncounters;
+    return 0;
+}
+
+static int get_factor_plan(gpso_handle* h, int n, bool with_inverse, gpso_handle::FactorPlan** out) {
+    gpso_handle::FactorPlan& plan = h->factor_plans[2 * n + (with_inverse ? 1 : 0)];
+    if (!plan.tasks.p) {
+        std::vector<int> flat;
+        GP_TRY(make_factor_tasks(n, h->nsm > 0 ? h->nsm : 148, flat, plan.ntasks, plan.ncounters, with_inverse));
+        GP_TRY(plan.tasks.ensure(flat.size() * sizeof(int)));
+        CU_TRY(cudaMemcpy(plan.tasks.p, flat.data(), flat.size() * sizeof(int), cudaMemcpyHostToDevice));
+    }
+    *out = &plan;
     return 0;
 }
 
@@ -765,29 +798,32 @@ static int kinv_int8(gpso_handle* h, cudaStream_t st) {
 namespace {
 struct InvLevelInfo { int s; size_t xt_off; int xt_rounds; size_t y_off; int y_rounds; };
 }
+// Deal tiles (row block, 64-row tile of B, first k-step, k-steps) to G persistent CTAs, longest first, each to the CTA with the
+// least work so far; appended to `all` as a [rounds][G][4] table (-1 = none).
+static void deal_items(std::vector<std::array<int, 4>>& items, int G, std::vector<int>& all, size_t& off, int& rounds) {
+    std::stable_sort(items.begin(), items.end(), [](const std::array<int, 4>& a, const std::array<int, 4>& b) { return a[3] > b[3]; });
+    std::vector<std::vector<int>> per(G);
+    std::vector<long long> load(G, 0);
+    for (size_t i = 0; i < items.size(); i++) {
+        int best = 0;
+        for (int g = 1; g < G; g++)
+            if (load[g] < load[best]) best = g;
+        per[best].push_back((int)i);
+        load[best] += items[i][3] + 6;
+    }
+    size_t r = 0;
+    for (int g = 0; g < G; g++) r = std::max(r, per[g].size());
+    off = all.size();
+    rounds = (int)r;
+    all.resize(off + r * G * 4, -1);
+    for (int g = 0; g < G; g++)
+        for (size_t k = 0; k < per[g].size(); k++)
+            for (int c = 0; c < 4; c++) all[off + (k * G + g) * 4 + c] = items[per[g][k]][c];
+}
+
 static void make_inverse_items(int nb, int G, std::vector<int>& all, std::vector<InvLevelInfo>& levels) {
     all.clear();
     levels.clear();
-    auto deal = [&](std::vector<std::array<int, 4>>& items, size_t& off, int& rounds) {
-        std::stable_sort(items.begin(), items.end(), [](const std::array<int, 4>& a, const std::array<int, 4>& b) { return a[3] > b[3]; });
-        std::vector<std::vector<int>> per(G);
-        std::vector<long long> load(G, 0);
-        for (size_t i = 0; i < items.size(); i++) {
-            int best = 0;
-            for (int g = 1; g < G; g++)
-                if (load[g] < load[best]) best = g;
-            per[best].push_back((int)i);
-            load[best] += items[i][3] + 6;
-        }
-        size_t r = 0;
-        for (int g = 0; g < G; g++) r = std::max(r, per[g].size());
-        off = all.size();
-        rounds = (int)r;
-        all.resize(off + r * G * 4, -1);
-        for (int g = 0; g < G; g++)
-            for (size_t k = 0; k < per[g].size(); k++)
-                for (int c = 0; c < 4; c++) all[off + (k * G + g) * 4 + c] = items[per[g][k]][c];
-    };
     for (int s = 1; s < nb; s *= 2) {
         std::vector<std::array<int, 4>> xt, y;
         for (int q = 0; 2 * q * s < nb; q++) {
@@ -801,83 +837,204 @@ static void make_inverse_items(int nb, int G, std::vector<int>& all, std::vector
         }
         InvLevelInfo lv;
         lv.s = s;
-        deal(xt, lv.xt_off, lv.xt_rounds);
-        deal(y, lv.y_off, lv.y_rounds);
+        deal_items(xt, G, all, lv.xt_off, lv.xt_rounds);
+        deal_items(y, G, all, lv.y_off, lv.y_rounds);
         levels.push_back(lv);
     }
     if (all.empty()) all.resize(4, -1);
 }
 
-static int build_inverse_items(gpso_handle* h) {
-    const int nb = h->nb, G = h->nsm > 0 ? h->nsm : 148;
-    if (h->inv_items_nb == nb && h->inv_items.p) return 0;
-    std::vector<int> all;
-    std::vector<InvLevelInfo> levels;
-    make_inverse_items(nb, G, all, levels);
-    h->inv_levels.clear();
-    for (const InvLevelInfo& lv : levels) h->inv_levels.push_back({lv.s, lv.xt_off, lv.xt_rounds, lv.y_off, lv.y_rounds});
-    GP_TRY(h->inv_items.ensure(all.size() * sizeof(int)));
-    CU_TRY(cudaMemcpy(h->inv_items.p, all.data(), all.size() * sizeof(int), cudaMemcpyHostToDevice));
-    h->inv_items_nb = nb;
+static int get_inverse_plan(gpso_handle* h, int n, gpso_handle::InvPlan** out) {
+    gpso_handle::InvPlan& plan = h->inv_plans[n];
+    if (!plan.items.p) {
+        std::vector<int> all;
+        std::vector<InvLevelInfo> levels;
+        make_inverse_items(n, h->nsm > 0 ? h->nsm : 148, all, levels);
+        for (const InvLevelInfo& lv : levels) plan.levels.push_back({lv.s, lv.xt_off, lv.xt_rounds, lv.y_off, lv.y_rounds});
+        GP_TRY(plan.items.ensure(all.size() * sizeof(int)));
+        CU_TRY(cudaMemcpy(plan.items.p, all.data(), all.size() * sizeof(int), cudaMemcpyHostToDevice));
+    }
+    *out = &plan;
     return 0;
 }
 
-static int inverse_int8(gpso_handle* h, cudaStream_t st) {
-    constexpr int S = OZ_INV_S;
-    const int Np = h->Np, nb = h->nb, nks = Np / 32;
-    const size_t dig = (size_t)Np * Np * S;
+static int ensure_inverse_buffers(gpso_handle* h) {
+    const size_t dig = (size_t)h->Np * h->Np * OZ_INV_S;
     GP_TRY(h->ozL.ensure(dig));
     GP_TRY(h->ozLT.ensure(dig));
     GP_TRY(h->ozLI.ensure(dig));
     GP_TRY(h->ozXT.ensure(dig));
-    GP_TRY(h->rsL.ensure((size_t)Np * sizeof(double)));
-    GP_TRY(h->rsLT.ensure((size_t)Np * sizeof(double)));
-    GP_TRY(h->rsLI.ensure((size_t)Np * sizeof(double)));
-    GP_TRY(h->rsXT.ensure((size_t)Np * sizeof(double)));
-    GP_TRY(h->T.ensure((size_t)Np * Np * sizeof(double), true));
-    GP_TRY(build_inverse_items(h));
-    const int grid = h->nsm > 0 ? h->nsm : 148;
-    const dim3 sgrid(nks, nb);
-    auto digits = [&](const DevBuf& M, int kind, int s, DevBuf& scales, DevBuf& out, const char* what) -> int {
-        range_rowscale_kernel<<<(Np + 7) / 8, 256, 0, st>>>(M.as<double>(), Np, kind, s, nb, scales.as<double>());
-        GP_TRY(check_launch(h, what));
-        range_slices_kernel<S><<<sgrid, 256, 0, st>>>(M.as<double>(), scales.as<double>(), Np, nks, kind, s, nb, out.as<uint8_t>());
-        GP_TRY(check_launch(h, what));
-        return 0;
-    };
-    auto product = [&](const DevBuf& A, const DevBuf& rsA, const DevBuf& B, const DevBuf& rsB, size_t off, int rounds, double* out,
-                       double* out_t, double sign, const char* what) -> int {
-        OzParams P;
-        P.A = A.as<uint8_t>();
-        P.B = B.as<uint8_t>();
-        P.rowscale = rsA.as<double>();
-        P.colscale = rsB.as<double>();
-        P.part = nullptr;
-        P.gscale = ldexp(1.0, -2 * (8 * S - 2) + 8 * (S - 1));
-        P.nb = nb;
-        P.nks = nks;
-        P.nct = 2 * nb;
-        P.ldp = 0;
-        P.items = h->inv_items.as<int>() + off;
-        P.rounds = rounds;
-        P.out = out;
-        P.out_t = out_t;
-        P.sign = sign;
-        P.Np = Np;
-        ozaki_kernel<S, OZ_GEMM><<<grid, OZ_THREADS, OzCfg<S>::SMEM_BYTES, st>>>(P);
-        return check_launch(h, what);
-    };
-    GP_TRY(digits(h->K, OZR_L, 1, h->rsL, h->ozL, "digits_L"));
-    for (const gpso_handle::InvLevel& lv : h->inv_levels) {
-        if (lv.xt_rounds == 0) continue;
-        GP_TRY(digits(h->LinvT, OZR_LINVT, lv.s, h->rsLT, h->ozLT, "digits_LinvT"));
-        GP_TRY(product(h->ozLT, h->rsLT, h->ozL, h->rsL, lv.xt_off, lv.xt_rounds, h->T.as<double>(), nullptr, 1.0, "inverse_xt"));
-        GP_TRY(digits(h->T, OZR_XT, lv.s, h->rsXT, h->ozXT, "digits_XT"));
-        GP_TRY(digits(h->Linv, OZR_LINV, lv.s, h->rsLI, h->ozLI, "digits_Linv"));
-        GP_TRY(product(h->ozLI, h->rsLI, h->ozXT, h->rsXT, lv.y_off, lv.y_rounds, h->Linv.as<double>(), h->LinvT.as<double>(), -1.0,
-                       "inverse_y"));
+    GP_TRY(h->rsL.ensure((size_t)h->Np * sizeof(double)));
+    GP_TRY(h->rsLT.ensure((size_t)h->Np * sizeof(double)));
+    GP_TRY(h->rsLI.ensure((size_t)h->Np * sizeof(double)));
+    GP_TRY(h->rsXT.ensure((size_t)h->Np * sizeof(double)));
+    GP_TRY(h->T.ensure((size_t)h->Np * h->Np * sizeof(double), true));
+    return 0;
+}
+
+// Digits of the rows of the n-tile sub-matrix whose first element is M (row pitch Np), over the k-range `kind` selects.
+static int oz_range_digits(gpso_handle* h, cudaStream_t st, const double* M, int n, int kind, int s, DevBuf& scales, DevBuf& out,
+                           const char* what) {
+    const int Np = h->Np, nks = Np / 32;
+    range_rowscale_kernel<<<n * 16, 256, 0, st>>>(M, Np, kind, s, n, scales.as<double>());
+    GP_TRY(check_launch(h, what));
+    range_slices_kernel<OZ_INV_S><<<dim3(4 * n, n), 256, 0, st>>>(M, scales.as<double>(), Np, nks, kind, s, n, out.as<uint8_t>());
+    return check_launch(h, what);
+}
+
+// out[i][j] (+)= sign * sum_k A[i][k] B[j][k] over the tiles and k-ranges of an item table, on the int8 tensor cores
+static int oz_range_product(gpso_handle* h, cudaStream_t st, const DevBuf& A, const DevBuf& rsA, const DevBuf& B, const DevBuf& rsB,
+                            const int* items, int rounds, int n, double* out, double* out_t, double sign, bool accumulate,
+                            const char* what) {
+    constexpr int S = OZ_INV_S;
+    OzParams P;
+    P.A = A.as<uint8_t>();
+    P.B = B.as<uint8_t>();
+    P.rowscale = rsA.as<double>();
+    P.colscale = rsB.as<double>();
+    P.part = nullptr;
+    P.gscale = ldexp(1.0, -2 * (8 * S - 2) + 8 * (S - 1));
+    P.nb = n;
+    P.nks = h->Np / 32;
+    P.nct = 2 * n;
+    P.ldp = 0;
+    P.items = items;
+    P.rounds = rounds;
+    P.out = out;
+    P.out_t = out_t;
+    P.sign = sign;
+    P.accumulate = accumulate ? 1 : 0;
+    P.Np = h->Np;
+    ozaki_kernel<S, OZ_GEMM><<<h->nsm > 0 ? h->nsm : 148, OZ_THREADS, OzCfg<S>::SMEM_BYTES, st>>>(P);
+    return check_launch(h, what);
+}
+
+// Levels s_lo <= s < s_hi of the recursive-doubling inverse of the n-tile diagonal block that starts at tile t0 (the whole
+// matrix: t0 = 0, n = nb, all levels).  A single level (the merge of a hybrid node) only needs the L21 rows of the factor.
+static int inverse_int8(gpso_handle* h, cudaStream_t st, int t0, int n, int s_lo, int s_hi) {
+    const int Np = h->Np;
+    GP_TRY(ensure_inverse_buffers(h));
+    gpso_handle::InvPlan* plan = nullptr;
+    GP_TRY(get_inverse_plan(h, n, &plan));
+    const size_t off = (size_t)t0 * 128 * Np + (size_t)t0 * 128;
+    const double* L = h->K.as<double>() + off;
+    double* Linv = h->Linv.as<double>() + off;
+    double* LinvT = h->LinvT.as<double>() + off;
+    double* T = h->T.as<double>() + off;
+    const bool single = s_hi <= 2 * s_lo;
+    GP_TRY(oz_range_digits(h, st, L, n, single ? OZR_PANEL : OZR_L, single ? s_lo : 1, h->rsL, h->ozL, "digits_L"));
+    for (const gpso_handle::InvLevel& lv : plan->levels) {
+        if (lv.xt_rounds == 0 || lv.s < s_lo || lv.s >= s_hi) continue;
+        GP_TRY(oz_range_digits(h, st, LinvT, n, OZR_LINVT, lv.s, h->rsLT, h->ozLT, "digits_LinvT"));
+        GP_TRY(oz_range_product(h, st, h->ozLT, h->rsLT, h->ozL, h->rsL, plan->items.as<int>() + lv.xt_off, lv.xt_rounds, n, T, nullptr,
+                                1.0, false, "inverse_xt"));
+        GP_TRY(oz_range_digits(h, st, T, n, OZR_XT, lv.s, h->rsXT, h->ozXT, "digits_XT"));
+        GP_TRY(oz_range_digits(h, st, Linv, n, OZR_LINV, lv.s, h->rsLI, h->ozLI, "digits_Linv"));
+        GP_TRY(oz_range_product(h, st, h->ozLI, h->rsLI, h->ozXT, h->rsXT, plan->items.as<int>() + lv.y_off, lv.y_rounds, n, Linv, LinvT,
+                                -1.0, false, "inverse_y"));
     }
     return 0;
+}
+
+// ---- hybrid factorisation: FP64 leaves, int8 tensor-core panels and Schur complements --------------------------------------
+// The blocked Cholesky of factor_persistent_kernel is bound by its chain of dependent 128-tile steps up to N ~ 4096 and by
+// the FP64 DMMA pipe above (0.55 of its peak at N = 8192).  The exact-integer products that already build L^-1 run at ~2.5x
+// the FP64 peak in fp64-equivalent work, so a node of n tiles is split after s = the largest power of two below n:
+//      [A11      ]      L11, L11^-1            the node's first half, recursively
+//      [A21  A22 ]      L21 = A21 L11^-T       one int8 product (8 digits per operand, 62-bit fixed point per row)
+//                       A22 -= L21 L21^T       one int8 product, accumulated into the lower tiles of A22
+//                       L22, L22^-1            the second half, recursively
+//                       L21^-1 = -L22^-1 L21 L11^-1     the level-s merge of the recursive-doubling inverse (work the whole-matrix
+//                                                      inverse did anyway)
+// Leaves (<= HYB_LEAF_TILES tiles) are factorised by the persistent FP64 kernel on the sub-matrix in place; that kernel is
+// bound by its chain of 128-tile steps (~70 us each), so smaller leaves do not shorten it, they only add product launches.
+constexpr int HYB_LEAF_TILES = 32;  // 4096 rows: measured 11.8 ms per LML+grad evaluation at N = 8192 against 13.5 with leaves of 2048 and 14.1
+                                    // with one kernel; at N = 4096 one kernel (3.43 ms) beats two leaves of 2048 (3.89 ms)
+
+static int get_factor_plan(gpso_handle* h, int n, bool with_inverse, gpso_handle::FactorPlan** out);
+
+static int get_hybrid_items(gpso_handle* h, int kind, int s, int n, gpso_handle::ItemList** out) {
+    gpso_handle::ItemList& list = h->hyb_items[((long long)kind << 40) | ((long long)s << 20) | n];
+    if (!list.items.p) {
+        std::vector<std::array<int, 4>> items;
+        for (int I = s; I < n; I++) {
+            if (kind == 0) {  // L21 tile (I, J): contraction over the tiles [0, J] of L11^-1's row block J
+                for (int J = 0; J < s; J++)
+                    for (int hh = 0; hh < 2; hh++) items.push_back({I, 2 * J + hh, 0, 4 * (J + 1)});
+            } else {          // Schur tile (I, J), s <= J <= I: contraction over the s tiles of L21
+                for (int J = s; J <= I; J++)
+                    for (int hh = 0; hh < 2; hh++) items.push_back({I, 2 * J + hh, 0, 4 * s});
+            }
+        }
+        std::vector<int> all;
+        size_t off = 0;
+        deal_items(items, h->nsm > 0 ? h->nsm : 148, all, off, list.rounds);
+        GP_TRY(list.items.ensure(all.size() * sizeof(int)));
+        CU_TRY(cudaMemcpy(list.items.p, all.data(), all.size() * sizeof(int), cudaMemcpyHostToDevice));
+    }
+    *out = &list;
+    return 0;
+}
+
+static int hybrid_leaf(gpso_handle* h, cudaStream_t st, int t0, int n) {
+    const int Np = h->Np;
+    const size_t off = (size_t)t0 * 128 * Np + (size_t)t0 * 128;
+    DenseParams P;
+    P.K = h->K.as<double>() + off;
+    P.Linv = h->Linv.as<double>() + off;
+    P.LinvT = h->LinvT.as<double>() + off;
+    P.T = h->T.as<double>() + off;
+    P.Kinv = nullptr;
+    P.Np = Np;
+    P.nb = n;
+    P.p = 0;
+    P.s = 0;
+    P.pivot_off = t0 * 128;
+    const int Nsub = h->N - t0 * 128;
+    if (n == 1) {
+        diag_factor_inverse_kernel<<<1, DIAG_THREADS, DIAG_SMEM_BYTES, st>>>(P.K, P.Linv, Np, 0, Nsub, h->logdet.as<double>() + t0,
+                                                                             h->info.as<int>(), P.pivot_off);
+        GP_TRY(check_launch(h, "diag_factor_inverse"));
+        diag_transpose_kernel<<<1, 256, 0, st>>>(P.Linv, P.LinvT, Np);
+        return check_launch(h, "diag_transpose");
+    }
+    const bool inv8 = n * 128 >= OZ_INV_MIN_NP;
+    gpso_handle::FactorPlan* plan = nullptr;
+    GP_TRY(get_factor_plan(h, n, !inv8, &plan));
+    GP_TRY(h->chol_state.ensure((size_t)(2 + plan->ncounters) * sizeof(int)));
+    int* state = h->chol_state.as<int>();
+    CU_TRY(cudaMemsetAsync(state, 0, (size_t)(2 + plan->ncounters) * sizeof(int), st));
+    const int grid = std::min(plan->ntasks, h->nsm > 0 ? h->nsm : 148);
+    factor_persistent_kernel<<<grid, GTHREADS, DIAG_SMEM_BYTES, st>>>(P, Nsub, plan->tasks.as<int>(), plan->ntasks, state,
+                                                                       h->logdet.as<double>() + t0, h->info.as<int>());
+    GP_TRY(check_launch(h, "factor_persistent"));
+    if (inv8) GP_TRY(inverse_int8(h, st, t0, n, 1, n));
+    return 0;
+}
+
+static int hybrid_node(gpso_handle* h, cudaStream_t st, int t0, int n, int leaf) {
+    if (n <= leaf) return hybrid_leaf(h, st, t0, n);
+    int s = 1;
+    while (2 * s < n) s *= 2;
+    const int Np = h->Np;
+    const size_t off = (size_t)t0 * 128 * Np + (size_t)t0 * 128;
+    double* A = h->K.as<double>() + off;
+    h->hybrid_nodes++;
+    GP_TRY(hybrid_node(h, st, t0, s, leaf));
+    // L21 = A21 L11^-T
+    gpso_handle::ItemList* items = nullptr;
+    GP_TRY(oz_range_digits(h, st, A, n, OZR_PANEL, s, h->rsL, h->ozL, "digits_A21"));
+    GP_TRY(oz_range_digits(h, st, h->Linv.as<double>() + off, n, OZR_LOWER, s, h->rsLI, h->ozLI, "digits_Linv11"));
+    GP_TRY(get_hybrid_items(h, 0, s, n, &items));
+    GP_TRY(oz_range_product(h, st, h->ozL, h->rsL, h->ozLI, h->rsLI, items->items.as<int>(), items->rounds, n, A, nullptr, 1.0, false,
+                            "hybrid_panel"));
+    // A22 -= L21 L21^T (lower tiles)
+    GP_TRY(oz_range_digits(h, st, A, n, OZR_PANEL, s, h->rsL, h->ozL, "digits_L21"));
+    GP_TRY(get_hybrid_items(h, 1, s, n, &items));
+    GP_TRY(oz_range_product(h, st, h->ozL, h->rsL, h->ozL, h->rsL, items->items.as<int>(), items->rounds, n, A, nullptr, -1.0, true,
+                            "hybrid_schur"));
+    GP_TRY(hybrid_node(h, st, t0 + s, n - s, leaf));
+    return inverse_int8(h, st, t0, n, s, 2 * s);
 }
 
 // Gram -> Cholesky -> inverse factor -> [K_y^-1] -> a, alpha -> scalars.  Uses h->ls_host/variance/noise/c0.
@@ -905,7 +1062,13 @@ static int factor_pipeline(gpso_handle* h, cudaStream_t st, bool need_kinv) {
     static const int inv_min_np = getenv("GPSO_INV_MIN_NP") ? atoi(getenv("GPSO_INV_MIN_NP")) : OZ_INV_MIN_NP;     // tuning experiments only
     static const int kinv_min_np = getenv("GPSO_KINV_MIN_NP") ? atoi(getenv("GPSO_KINV_MIN_NP")) : OZ_KINV_MIN_NP;
     const bool inv8 = nb > 1 && Np <= OZ_MAX_NP && (h->inverse_mode == 2 || (h->inverse_mode == 0 && Np >= inv_min_np));
-    if (h->chol_mode == 1 && nb > 1) {
+    static const int hyb_leaf_env = getenv("GPSO_HYB_LEAF") ? atoi(getenv("GPSO_HYB_LEAF")) : 0;  // tuning experiments only
+    const int hyb_leaf = h->hybrid_mode == 2 ? 2 : (hyb_leaf_env > 0 ? hyb_leaf_env : HYB_LEAF_TILES);
+    h->hybrid_nodes = 0;
+    if (h->chol_mode == 1 && inv8 && h->hybrid_mode != 1 && nb > hyb_leaf) {
+        GP_TRY(ensure_inverse_buffers(h));
+        GP_TRY(hybrid_node(h, st, 0, nb, hyb_leaf));
+    } else if (h->chol_mode == 1 && nb > 1) {
         // one persistent launch: blocked Cholesky + L^-1 (diagonal blocks, their transposes and -- unless the int8 engine
         // takes it over below -- the recursive doubling)
         GP_TRY(build_factor_tasks(h, !inv8));
@@ -917,7 +1080,7 @@ static int factor_pipeline(gpso_handle* h, cudaStream_t st, bool need_kinv) {
         factor_persistent_kernel<<<grid, GTHREADS, DIAG_SMEM_BYTES, st>>>(P, h->N, h->chol_tasks.as<int>(), h->chol_ntasks, state,
                                                                            h->logdet.as<double>(), h->info.as<int>());
         GP_TRY(check_launch(h, "factor_persistent"));
-        if (inv8) GP_TRY(inverse_int8(h, st));
+        if (inv8) GP_TRY(inverse_int8(h, st, 0, nb, 1, nb));
     } else {
         for (int p = 0; p < nb; p++) {
             diag_factor_inverse_kernel<<<1, DIAG_THREADS, DIAG_SMEM_BYTES, st>>>(P.K, P.Linv, Np, p, h->N, h->logdet.as<double>(),
@@ -935,7 +1098,7 @@ static int factor_pipeline(gpso_handle* h, cudaStream_t st, bool need_kinv) {
         diag_transpose_kernel<<<nb, 256, 0, st>>>(P.Linv, P.LinvT, Np);
         GP_TRY(check_launch(h, "diag_transpose"));
         if (inv8) {
-            GP_TRY(inverse_int8(h, st));
+            GP_TRY(inverse_int8(h, st, 0, nb, 1, nb));
         } else if (nb > 1) {
             GP_TRY(h->T.ensure((size_t)Np * Np * sizeof(double), true));
             P.T = h->T.as<double>();
@@ -1774,7 +1937,11 @@ static int run_screen_windows(gpso_handle* h, cudaStream_t st, const double* Xc_
         GP_TRY(prod_mark(h, st));
         GP_TRY(trace_mark(h, st, 3, w));
         if (full) {
-            launch_screen_product_v<2, true>(h, st, Mw_pad / SCR_NT, Mw_pad, gscale, h->ozBb[b].as<uint8_t>());
+            // four k-steps (64 KB of operands, one tcgen05.commit) per ring stage, three stages: 41.8 vs 43.4 ms per 2.1e6
+            // candidates against two k-steps x six stages (GPSO_SCR_KPS=2 for the A/B)
+            static const int kps_env = getenv("GPSO_SCR_KPS") ? atoi(getenv("GPSO_SCR_KPS")) : 4;
+            if (kps_env == 4) launch_screen_product_v<2, true, 4>(h, st, Mw_pad / SCR_NT, Mw_pad, gscale, h->ozBb[b].as<uint8_t>());
+            else launch_screen_product_v<2, true>(h, st, Mw_pad / SCR_NT, Mw_pad, gscale, h->ozBb[b].as<uint8_t>());
         } else {
             DISPATCH_SCREEN_S(S, launch_screen_product, h, st, Mw_pad / SCR_NT, Mw_pad, gscale, h->ozBb[b].as<uint8_t>());
         }
@@ -2358,8 +2525,16 @@ extern "C" int gpso_set_overlap(gpso_handle* h, int enabled) {
 }
 
 extern "C" int gpso_set_factor_mode(gpso_handle* h, int mode) {
-    if (!h || mode < 0 || mode > 1) return fail(GPSO_E_BADARG, "gpso_set_factor_mode: bad argument");
-    h->chol_mode = mode;
+    if (!h || mode < 0 || mode > 3) return fail(GPSO_E_BADARG, "gpso_set_factor_mode: bad argument");
+    h->chol_mode = mode == 0 ? 0 : 1;
+    h->hybrid_mode = mode == 2 ? 1 : (mode == 3 ? 2 : 0);
+    return 0;
+}
+
+extern "C" int gpso_factor_info(gpso_handle* h, int* out2) {
+    if (!h || !out2) return fail(GPSO_E_BADARG, "gpso_factor_info: null argument");
+    out2[0] = h->chol_mode == 0 ? 0 : (h->hybrid_nodes > 0 ? 2 : 1);
+    out2[1] = h->hybrid_nodes;
     return 0;
 }
 

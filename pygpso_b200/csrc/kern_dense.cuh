@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(256) diag_transpose_kernel(const double* __res
 constexpr int LHP = 64 + 4;  // row pitch of a 128x64 half of the left neighbour tile
 __device__ __forceinline__ void diag_block_device(double* __restrict__ K, double* __restrict__ Linv, int Np, int p, int N,
                                                   double* __restrict__ logdet, int* __restrict__ info, double* sm,
-                                                  const double* __restrict__ Lprev = nullptr, int nprev = 0) {
+                                                  const double* __restrict__ Lprev = nullptr, int nprev = 0, int pivot_off = 0) {
     double* S = sm;                  // [TB][DP]: lower sub-blocks A -> L in place; upper sub-blocks (0,1..3) = T_pb,j scratch
     double* Xs = sm + TB * DP;       // staircase inverse: sub-block (k,j), j <= k, at Xs + XO(k) + j*SB, row pitch XP(k)
     double* colbuf = Xs + XO(4);     // [2][2][SB]
@@ -291,7 +291,7 @@ __device__ __forceinline__ void diag_block_device(double* __restrict__ K, double
     for (int pb = 0; pb < 4; pb++) {
         // ---- P1: warp 0 factors + inverts the diagonal sub-block; the other warps work in its shadow
         if (warp == 0) {
-            const double il = chol_inv_32(SBLK(pb, pb), XBLK(pb, pb), XP(pb), colbuf, lane, p * TB + pb * SB + 1, info);
+            const double il = chol_inv_32(SBLK(pb, pb), XBLK(pb, pb), XP(pb), colbuf, lane, pivot_off + p * TB + pb * SB + 1, info);
             if (p * TB + pb * SB + lane < N) logacc -= log(il);
         } else if (pb > 0) {
             if (warp == 4) {
@@ -388,9 +388,9 @@ __device__ __forceinline__ void diag_block_device(double* __restrict__ K, double
 
 __global__ void __launch_bounds__(DIAG_THREADS) diag_factor_inverse_kernel(double* __restrict__ K, double* __restrict__ Linv,
                                                                            int Np, int p, int N, double* __restrict__ logdet,
-                                                                           int* __restrict__ info) {
+                                                                           int* __restrict__ info, int pivot_off = 0) {
     extern __shared__ __align__(16) double sm[];
-    diag_block_device(K, Linv, Np, p, N, logdet, info, sm);
+    diag_block_device(K, Linv, Np, p, N, logdet, info, sm, nullptr, 0, pivot_off);
 }
 
 // ---- tile GEMM with store epilogues -------------------------------------------------------------------------------
@@ -413,6 +413,7 @@ struct DenseParams {
     int p;  // Cholesky panel
     int s;  // half-block size (in tiles) of the inverse recursion level
     int ui, uj, uk0, ukn;  // MODE_CHOL_UPD: output tile and range of panels contracted over
+    int pivot_off = 0;     // row index of the sub-matrix's first row in the whole matrix (LAPACK info of a hybrid leaf)
 };
 
 __device__ __forceinline__ void tri_index(int t, int& i, int& j) {  // t -> (i >= j), row-major lower enumeration
@@ -542,6 +543,60 @@ __global__ void __launch_bounds__(GTHREADS, 1) dense_gemm_kernel(DenseParams P) 
     gemm_tile_device<MODE>(P, blockIdx.x, smem);
 }
 
+// ---- the panel tile the next diagonal block waits for, in four row strips -------------------------------------------------
+// L[p+1,p] = A[p+1,p] L_pp^-T sits on the critical chain DIAG(p) -> PANEL(p+1,p) -> DIAG(p+1): 25 us as one 128x128x128 tile on
+// one SM.  Cut into PANEL_STRIPS strips of 32 rows, each on its own SM (whole operands in shared memory: 32 x 128 of A, the
+// lower triangle of L_pp^-1; warp w owns 16 output columns and only multiplies up to its last column), the chain waits ~8 us.
+constexpr int PANEL_STRIPS = 4;
+constexpr int PANEL_STRIP_ROWS = TB / PANEL_STRIPS;
+__device__ __forceinline__ void panel_strip_device(const DenseParams& P, int p, int strip, double* smem) {
+    static_assert(PANEL_STRIP_ROWS == 32, "warp tiling below assumes 32-row strips");
+    double* sA = smem;                          // [32][DP]
+    double* sB = smem + PANEL_STRIP_ROWS * DP;  // [128][DP]
+    const int Np = P.Np, tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    double* Atile = P.K + ((size_t)(p + 1) * TB + strip * PANEL_STRIP_ROWS) * Np + (size_t)p * TB;
+    const double* Btile = P.Linv + (size_t)p * TB * Np + (size_t)p * TB;
+    __syncthreads();  // previous user of the shared memory is done
+    for (int c = tid; c < PANEL_STRIP_ROWS * (TB / 2); c += GTHREADS) {
+        const int r = c >> 6, k2 = (c & 63) * 2;
+        cp_async16(sA + r * DP + k2, Atile + (size_t)r * Np + k2);
+    }
+    for (int c = tid; c < TB * (TB / 2); c += GTHREADS) {
+        const int r = c >> 6, k2 = (c & 63) * 2;
+        if (k2 < ((r >> 4) + 1) * 16) cp_async16(sB + r * DP + k2, Btile + (size_t)r * Np + k2);  // columns a warp reads for row r
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    // column block of this warp: the two warps of an SM sub-partition (w, w + 4) take blocks (w, 7 - w): equal DMMA counts
+    const int cb = warp < 4 ? warp : 11 - warp;
+    double acc[4][2][2];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 2; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+    const double* pa = sA + g * DP + t;
+    const double* pb = sB + (cb * 16 + g) * DP + t;
+    const int nkk = (cb + 1) * 4;  // k <= last column of the block (L_pp^-1 is lower triangular)
+    for (int kk = 0; kk < nkk; kk++) {
+        double af[4], bf[2];
+#pragma unroll
+        for (int i = 0; i < 4; i++) af[i] = pa[i * 8 * DP + kk * 4];
+#pragma unroll
+        for (int j = 0; j < 2; j++) bf[j] = pb[j * 8 * DP + kk * 4];
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = 0; j < 2; j++) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 2; j++)
+            *reinterpret_cast<double2*>(Atile + (size_t)(i * 8 + g) * Np + cb * 16 + j * 8 + 2 * t) = make_double2(acc[i][j][0], acc[i][j][1]);
+}
+
 // ---- persistent factorisation: one CTA per SM, tile tasks with explicit dependencies ----------------------------------
 // One launch runs the blocked Cholesky AND the inverse factor.  The host (gpso_capi.cu: build_factor_tasks) writes every
 // task with the counters it waits for and the counter it signals; the kernel is an interpreter.
@@ -553,6 +608,8 @@ __global__ void __launch_bounds__(GTHREADS, 1) dense_gemm_kernel(DenseParams P) 
 // A counter per tile counts the operations completed on it (ops(j) = bj + j - bj*W updates, final at ops(j) + 1).  The
 // last update of a diagonal tile (narrow, or wide for the first panel of a block) is fused into its DIAG task.
 //   DIAG(p)       waits tile (p,p) at ops(p)-1 and tile (p,p-1) final       PANEL(i,p)  waits (p,p) final, (i,p) at ops(p)
+//   The tile (p+1,p) is solved in PANEL_STRIPS row strips (tasks PANEL with s = strip + 1) that count up their own counter
+//   STRIP(p); whoever reads that tile waits for STRIP(p) = PANEL_STRIPS instead of the tile counter.
 //   UPD(i,j,p)    waits (i,p), (j,p) final, (i,j) at bj + p - bj*W          WIDE(i,j,b) waits (i,q), (j,q) final (q = last
 //                                                                            panel of b), (i,j) at b
 // Inverse factor by recursive doubling (level s merges the inverses of tile ranges [a, a+s) and [a+s, a+2s)):
@@ -620,7 +677,9 @@ __global__ void __launch_bounds__(GTHREADS, 1) factor_persistent_kernel(DensePar
         const int op = s_t[0], p = s_t[1], i = s_t[2], j = s_t[3], sx = s_t[4], tile = s_t[5], done_idx = s_t[12], done_val = s_t[13];
         if (op == CT_DIAG) {
             const double* Lprev = sx ? P.K + (size_t)p * TB * P.Np + (size_t)(p - sx) * TB : nullptr;
-            diag_block_device(P.K, P.Linv, P.Np, p, N, logdet, info, smem, Lprev, sx);
+            diag_block_device(P.K, P.Linv, P.Np, p, N, logdet, info, smem, Lprev, sx, P.pivot_off);
+        } else if (op == CT_PANEL && sx > 0) {
+            panel_strip_device(P, p, sx - 1, smem);  // strip sx - 1 of the tile (p + 1, p)
         } else if (op == CT_PANEL) {
             DenseParams Q = P;
             Q.p = p;

@@ -76,6 +76,7 @@ struct OzParams {
     const double* colscale;  // OZ_GEMM: row scales of the B operand (its rows are the output columns)
     double* out_t;           // OZ_GEMM: optional second, transposed copy of the output (out_t[col][row])
     double sign;             // OZ_GEMM: +1 / -1
+    int accumulate;          // OZ_GEMM: 1 = out += sign * product (Schur-complement update of the hybrid factorisation), 0 = store
 };
 
 // What one launch of the product kernel computes
@@ -299,8 +300,11 @@ __global__ void __launch_bounds__(256) linv_slices_kernel(const double* __restri
 //   OZR_LINV   L^-1 rows of the second half of a pair, k in tiles [b0, I]   (lower part of the block: operand of Y = L22^-1 X)
 //   OZR_XT     X^T rows of the first half of a pair,  k in tiles [a+s, min(a+2s, nb))
 //   OZR_L      rows of the Cholesky factor, k in tiles [0, I)   (strictly below the diagonal tile: the L21 blocks)
+// and of the hybrid factorisation (gpso_capi.cu: hybrid_node), for a node split after s tiles:
+//   OZR_PANEL  rows I >= s, k in tiles [0, s)      (A21, later L21: operand of L21 = A21 L11^-T, of the Schur update and of X^T)
+//   OZR_LOWER  rows I <  s, k in tiles [0, I]      (L11^-1: operand of L21 = A21 L11^-T)
 // Each row is scaled by a power of two above its largest entry IN THAT RANGE, then cut into S balanced 8-bit digits.
-constexpr int OZR_LINVT = 0, OZR_LINV = 1, OZR_XT = 2, OZR_L = 3;
+constexpr int OZR_LINVT = 0, OZR_LINV = 1, OZR_XT = 2, OZR_L = 3, OZR_PANEL = 4, OZR_LOWER = 5;
 
 __device__ __forceinline__ void ozr_tile_range(int kind, int I, int s, int nb, int& t0, int& t1) {
     const int b0 = (I / s) * s, b1 = min(b0 + s, nb), a = (I / (2 * s)) * (2 * s);
@@ -310,6 +314,10 @@ __device__ __forceinline__ void ozr_tile_range(int kind, int I, int s, int nb, i
         t0 = b0, t1 = (I >= a + s) ? I + 1 : b0;    // only second-half rows are read (operand of Y)
     } else if (kind == OZR_XT) {
         t0 = a + s, t1 = (I < a + s) ? min(a + 2 * s, nb) : a + s;  // second-half rows: empty
+    } else if (kind == OZR_PANEL) {
+        t0 = 0, t1 = (I >= s) ? s : 0;
+    } else if (kind == OZR_LOWER) {
+        t0 = 0, t1 = (I < s) ? I + 1 : 0;
     } else {
         t0 = 0, t1 = I;
     }
@@ -632,8 +640,16 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_kernel(OzParams P) {
                     const double4 c1 = *reinterpret_cast<const double4*>(cs + col0 + 4);
                     const double o[8] = {v[0] * c0.x, v[1] * c0.y, v[2] * c0.z, v[3] * c0.w, v[4] * c1.x, v[5] * c1.y, v[6] * c1.z, v[7] * c1.w};
                     double2* dst = reinterpret_cast<double2*>(P.out + (size_t)row * P.Np + col0);
+                    if (MODE == OZ_GEMM && P.accumulate) {
 #pragma unroll
-                    for (int i = 0; i < 4; i++) dst[i] = make_double2(o[2 * i], o[2 * i + 1]);
+                        for (int i = 0; i < 4; i++) {
+                            const double2 c = dst[i];
+                            dst[i] = make_double2(c.x + o[2 * i], c.y + o[2 * i + 1]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 4; i++) dst[i] = make_double2(o[2 * i], o[2 * i + 1]);
+                    }
                     if (MODE == OZ_GEMM && P.out_t != nullptr) {
                         // lanes hold consecutive rows: 256 contiguous bytes per column
 #pragma unroll

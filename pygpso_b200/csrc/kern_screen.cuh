@@ -32,14 +32,14 @@ constexpr int SCR_NT = 128;  // candidates per tile of the screening product
 // FULL: all S^2 digit pairs are kept (levels 0 .. 2S-2): the product of the S-digit operands is then exact and the only error
 // left is the operand rounding -- at S = 2 that is 4 pairs instead of the 6 of the triangular 3-digit product, with 16 KB
 // instead of 24 KB of operands per k-step.  (The triangular 2-digit product drops the pair (1,1), which is as large as the result.)
-template <int S, int NT, bool FULL = false>
+template <int S, int NT, bool FULL = false, int KPSV = SCR_KPS>
 struct ScrCfg {
     static constexpr int A_BYTES = S * OZ_A_SLICE;
     static constexpr int B_SLICE = NT * 32;
     static constexpr int B_BYTES = S * B_SLICE;
     // k-steps (of 32) per ring stage: one bulk copy of A and one of B per stage (consecutive k-steps are contiguous in both
     // digit buffers) and ONE tcgen05.commit per stage -- every row block has a multiple of 4 k-steps
-    static constexpr int KPS = SCR_KPS;
+    static constexpr int KPS = KPSV;
     static constexpr int STAGE_BYTES = KPS * (A_BYTES + B_BYTES);
     // the ring is what hides the L2 latency: bytes in flight / latency is the operand bandwidth this CTA can draw (24 KB
     // chunks, 8 in flight reach 20 TB/s chip-wide, profiles/r01_i8_tcgen05_probe.txt).  192 KB leave room for one
@@ -326,9 +326,9 @@ __global__ void __launch_bounds__(256, 2) crosscov_screen_kernel(const double* _
 // ---- the screening product ------------------------------------------------------------------------------------------------
 // Same roles as ozaki_kernel: warp 0 producer (cp.async.bulk + mbarrier tx), warp 1 single-thread tcgen05.mma issuer, warps
 // 2..9 epilogue.  Work unit = candidate tile x pair of row blocks (I, nb-1-I) via OzItems<OZ_TRMM> (OzParams-compatible view).
-template <int S, int NT, bool FULL>
+template <int S, int NT, bool FULL, int KPSV = SCR_KPS>
 __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_screen_kernel(ScrParams P) {
-    using Cfg = ScrCfg<S, NT, FULL>;
+    using Cfg = ScrCfg<S, NT, FULL, KPSV>;
     constexpr int LEVELS = Cfg::LEVELS;
     constexpr int STAGES = Cfg::STAGES;
     constexpr int NBUF = Cfg::NBUF;

@@ -46,12 +46,24 @@ def test_queue_is_topological_and_complete(nb):
             ctr[t[12]] = t[13]
         else:
             ctr[t[12]] += 1
-    # every tile of the lower triangle is final, every transpose done
+    # every tile of the lower triangle is final, every transpose done; the tile below each diagonal block is solved in four
+    # row strips that count up their own counter (everything that reads the tile waits for that one)
+    strip = lambda j: nb * nb + 1 + 2 * 8 * nb + j
     for i in range(nb):
         for j in range(i + 1):
-            assert ctr[i * nb + j] == ops(j) + 1, (i, j, int(ctr[i * nb + j]))
+            if i == j + 1:
+                assert ctr[i * nb + j] == ops(j) and ctr[strip(j)] == 4, (i, j, int(ctr[i * nb + j]), int(ctr[strip(j)]))
+            else:
+                assert ctr[i * nb + j] == ops(j) + 1, (i, j, int(ctr[i * nb + j]))
     assert ctr[nb * nb] == nb
-    assert seen["DIAG"] == nb and seen["TRANSPOSE"] == nb and seen["PANEL"] == nb * (nb - 1) // 2
+    assert seen["DIAG"] == nb and seen["TRANSPOSE"] == nb and seen["PANEL"] == nb * (nb - 1) // 2 + 3 * (nb - 1)
+    for t in tasks:
+        if OPS[int(t[0])] == "PANEL" and t[4] > 0:
+            assert t[2] == t[1] + 1 and 1 <= t[4] <= 4 and t[12] == strip(t[1]) and t[13] == 0, t.tolist()
+        for k in range(3):  # nobody waits for the tile counter of a strip-solved tile to become final
+            c, v = int(t[6 + k]), int(t[9 + k])
+            if 0 <= c < nb * nb and c // nb == c % nb + 1:
+                assert v <= ops(c % nb), t.tolist()
     # the inverse recursion: XT and Y tiles of every level, s * nv per pair
     expect = 0
     s = 1
@@ -70,10 +82,11 @@ def test_single_panel_matrix_has_no_scheduler_tasks_beyond_the_block():
     assert [OPS[int(t[0])] for t in tasks] == ["DIAG", "TRANSPOSE"]
 
 
-@pytest.mark.parametrize("nb,chain_slack,work_slack", [(16, 1.03, None), (32, 1.03, None), (64, None, 1.30)])
+@pytest.mark.parametrize("nb,chain_slack,work_slack", [(16, 1.15, None), (32, 1.15, None), (64, None, 1.30)])
 def test_schedule_quality_in_the_discrete_event_replay(nb, chain_slack, work_slack):
     """tools/factor_sim.py replays the queue with the measured task durations on 148 workers.  Up to N = 4096 the
-    factorisation is bound by the DIAG -> PANEL chain and the queue must not add to it; at N = 8192 the makespan has to stay
+    factorisation is bound by the DIAG -> PANEL chain (the panel tile on it is solved in four strips on four SMs) and the queue
+    must not add more than 15 % to it; at N = 8192 the makespan has to stay
     within 30 % of the work bound (its chain-bound tail costs ~20 %).  Guards the look-ahead ordering of the host builder."""
     import os
     import sys

@@ -87,7 +87,7 @@ def c4_reference():
 
 
 @pytest.mark.parametrize("ard", [False, True])
-@pytest.mark.parametrize("engines", ["int8", "dmma", "int8-stepwise"])
+@pytest.mark.parametrize("engines", ["int8", "int8-persistent", "dmma", "int8-stepwise"])
 def test_c4_shape_lml_grad_vs_oracle(cuda, c4_reference, ard, engines):
     """LML within 1e-9 * max(|LML|, N), gradient within 1e-6 * max(|g|, 1) at the shape the evals/s figure is quoted on."""
     X, y = c4_reference["X"], c4_reference["y"]
@@ -99,8 +99,12 @@ def test_c4_shape_lml_grad_vs_oracle(cuda, c4_reference, ard, engines):
         s.set_inverse_mode(1)
     elif engines == "int8-stepwise":
         s.set_factor_mode(False)
+    elif engines == "int8-persistent":
+        s.set_factor_mode(True, hybrid=False)
     f, g = s.neg_lml_and_grad(u)
+    schedule = s.factor_info()["schedule"]
     s.close()
+    assert schedule == {"int8": "hybrid", "int8-persistent": "persistent", "dmma": "persistent", "int8-stepwise": "stepwise"}[engines]
     assert abs(f - f_ref) <= 1e-9 * max(abs(f_ref), N), (f, f_ref, abs(f - f_ref) / max(abs(f_ref), N))
     err = np.abs(g - g_ref) / np.maximum(np.abs(g_ref), 1.0)
     assert np.all(err <= 1e-6), (float(err.max()), g, g_ref)

@@ -2,7 +2,7 @@
 """
 Discrete-event replay of the persistent factorisation kernel's task queue (no GPU): 148 workers draw tickets in queue
 order, each waits for the counters its task names, runs for the task's duration and signals.  Task durations are the
-measured ones (profiles/r01s3_ncu_summary.md): DIAG 35 us + 10 us per fused update panel, PANEL 25 us,
+measured ones (profiles/r01s3_ncu_summary.md): DIAG 35 us + 10 us per fused update panel, PANEL 25 us (8 us per row strip of the tile below the diagonal block),
 narrow update 31 us, wide update 17 W + 12 us, TRANSPOSE 5 us.  Prints the makespan, the critical chain
 (sum over panels of DIAG + PANEL) and the work bound (sum of durations / workers), for the library's own queue and for
 other panels-per-block W (GPSO_CHOL_W is read when the library builds a queue, so each W runs in a subprocess).
@@ -28,7 +28,7 @@ def duration_us(t):
     if op == DIAG:
         return 35.0 + 10.0 * s
     if op == PANEL:
-        return 25.0
+        return 8.0 if s > 0 else 25.0  # s > 0: one of the four row strips of the tile below the diagonal block
     if op == UPD:
         return 31.0 if s == 1 else 17.0 * s + 12.0
     if op == TRANSPOSE:
@@ -80,7 +80,7 @@ def simulate(nb, nsm=148, with_inverse=False):
             reach[c].sort()
         heapq.heappush(free, (done, w))
         end = max(end, done)
-    chain = sum(duration_us(t) for t in tasks if t[0] == DIAG) + 25.0 * (nb - 1)
+    chain = sum(duration_us(t) for t in tasks if t[0] == DIAG) + 8.0 * (nb - 1)
     return {"nb": nb, "tasks": len(tasks), "makespan_us": end, "work_bound_us": busy / nsm, "chain_us": chain,
             "idle_waiting_us_per_worker": wait_total / nsm}
 

@@ -1,5 +1,5 @@
 """LML+grad closure timing at given shapes (run on the GPU box; under `ncu --metrics gpu__time_duration.sum` it yields
-the per-kernel launch list of one evaluation).  usage: python tools/lml_profile.py N d [evals] [--factorize]"""
+the per-kernel launch list of one evaluation).  usage: python tools/lml_profile.py N d [evals] [--factorize] [--no-hybrid] [--stepwise]"""
 import os
 import sys
 import time
@@ -31,6 +31,8 @@ def main():
     s.set_data(X, y)
     if "--stepwise" in sys.argv:
         s.set_factor_mode(False)
+    if "--no-hybrid" in sys.argv:
+        s.set_factor_mode(True, hybrid=False)
     if "--kinv-dmma" in sys.argv:
         s.set_kinv_mode(1)
     if "--kinv-int8" in sys.argv:
@@ -57,7 +59,7 @@ def main():
         wall = (time.perf_counter() - t) / evals * 1e3
         dev /= evals
         print(f"N={N} d={d}: neg_lml_grad wall {wall:.3f} ms device {dev:.3f} ms -> {N ** 3 / dev * 1e-9:.2f} TFLOP/s (N^3), "
-              f"launches/eval {s.launch_count() // (evals + 1)}  f={f:.12g} g={g}")
+              f"launches/eval {s.launch_count() // (evals + 1)} {s.factor_info()}  f={f:.12g} g={g}")
     s.close()
 
 

@@ -55,7 +55,7 @@ def main():
                 "path": info["path"], "survivors": info["survivors"], "windows": info["screen_windows"], "E": info["error_bound"],
                 "max_dev": info["max_observed_deviation"]}
 
-    for digits in (3, 2, 4, 6) if len(sys.argv) < 4 else (3, 6):  # 6 = two digits, all four digit pairs
+    for digits in (3, 2, 4, 6) if len(sys.argv) < 4 else ((6,) if sys.argv[3] == "2f" else (3, 6)):  # 6 = two digits, all four digit pairs
         sess.set_screen_mode(digits)
         sess.factorize(theta)
         rec = {}
