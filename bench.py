@@ -173,6 +173,17 @@ def bench_lml_grad(cuda, peaks, cpu=True, shapes=((4096, 10), (8192, 20)), evals
             f, g = sess.neg_lml_and_grad(u + 1e-3 * (i + 1))
             dev_ms += sess.last_timing_ms()[0]
         wall = time.perf_counter() - t0
+        factor_info = sess.factor_info()
+        # the same closure with ONE persistent FP64 kernel for the whole matrix (round-1 schedule; only differs above 4096 rows)
+        one_ms = None
+        if factor_info["schedule"] == "hybrid":
+            sess.set_factor_mode(True, hybrid=False)
+            sess.neg_lml_and_grad(u)
+            one_ms = 0.0
+            for i in range(evals):
+                sess.neg_lml_and_grad(u + 1e-3 * (i + 1))
+                one_ms += sess.last_timing_ms()[0]
+            one_ms /= evals
         # the same closure with the step-by-step launches (gpso_set_factor_mode 0) beside the persistent tile scheduler
         sess.set_factor_mode(False)
         sess.neg_lml_and_grad(u)
@@ -183,14 +194,20 @@ def bench_lml_grad(cuda, peaks, cpu=True, shapes=((4096, 10), (8192, 20)), evals
         sess.set_factor_mode(True)
         rec = {"N": N, "d": d, "evals_per_s": evals / wall, "device_ms_per_eval": dev_ms / evals,
                "device_ms_per_eval_stepwise_launches": step_ms / evals,
-               "schedule": "blocked Cholesky as ONE persistent kernel on FP64 DMMA (task queue + per-tile dependency counters); "
+               "device_ms_per_eval_one_fp64_kernel": one_ms,
+               "factorisation": factor_info,
+               "schedule": ("hybrid Cholesky: leaves of <= 4096 rows by the persistent FP64 DMMA kernel (task queue + per-tile "
+                            "dependency counters, the panel tile on the chain in four row strips), panel solve and Schur complement "
+                            "as exact-integer products on the int8 tensor cores; " if factor_info["schedule"] == "hybrid" else
+                            "blocked Cholesky as ONE persistent kernel on FP64 DMMA (task queue + per-tile dependency counters, the "
+                            "panel tile on the chain in four row strips); ") +
                            "L^-1 by recursive doubling and K_y^-1 = L^-T L^-1 as exact-integer products on the int8 tensor cores",
                "library_bar_ms": {4096: {"cusolver_dpotrf": 1.675, "cusolver_dpotri": 14.005},
                                   8192: {"cusolver_dpotrf": 7.753, "cusolver_dpotri": 61.528}}.get(N),
                "fp64_equivalent_tflops": (float(N) ** 3 / (dev_ms / evals * 1e-3)) / 1e12, "fp64_peak_tflops": fp64_peak,
                "ratio_to_fp64_peak": (float(N) ** 3 / (dev_ms / evals * 1e-3)) / 1e12 / fp64_peak,
-               "ratio_note": "N^3/3 flops (Cholesky) run on the FP64 pipe, 2N^3/3 (L^-1, K_y^-1) as int8 tensor-core products: the "
-                             "ratio to the FP64 pipe peak can exceed 1",
+               "ratio_note": "N^3/3 flops (Cholesky) run on the FP64 pipe (above 4096 rows: only the leaves), 2N^3/3 (L^-1, K_y^-1) as "
+                             "int8 tensor-core products: the ratio to the FP64 pipe peak can exceed 1",
                "neg_lml": f}
         if cpu:
             from oracle import gpr_oracle as go  # CPU leg of the LML side measurement (checker + baseline)

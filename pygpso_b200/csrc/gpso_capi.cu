@@ -564,7 +564,10 @@ struct FactorTask {
 static int make_factor_tasks(int nb, int nsm, std::vector<int>& flat, int& ntasks, int& ncounters_out, bool with_inverse = true) {
     // panels per block of the two-level blocking; GPSO_CHOL_W overrides it for scheduling experiments (tools/factor_sim.py)
     static const int w_env = getenv("GPSO_CHOL_W") ? atoi(getenv("GPSO_CHOL_W")) : 0;
-    const int W = w_env > 0 ? w_env : (nb >= 48 ? 4 : 2);
+    // up to 47 panels (the leaves of the hybrid factorisation, every matrix up to N = 4096) the factorisation is bound by its
+    // chains of dependent tile tasks, not by the DMMA pipe: unblocked updates (W = 1) keep the off-diagonal chain PANEL -> UPDATE
+    // -> PANEL at 56 us per step (W = 2: 63 us); measured 3.28 vs 3.40 ms per LML+grad evaluation at N = 4096, 1.38 vs 1.52 at 2048
+    const int W = w_env > 0 ? w_env : (nb >= 48 ? 4 : 1);
     if (nb < 1 || nb > 255) return fail(GPSO_E_BADARG, "matrix too large for the tile scheduler (more than 255 panels)");
     const int LV = 8;  // levels of the inverse recursion: s = 1 .. 128
     auto T = [nb](int i, int j) { return i * nb + j; };          // tile counters
@@ -572,7 +575,8 @@ static int make_factor_tasks(int nb, int nsm, std::vector<int>& flat, int& ntask
     auto XTD = [nb, LV](int l, int q) { return nb * nb + 1 + l * nb + q; };
     auto YD = [nb, LV](int l, int q) { return nb * nb + 1 + LV * nb + l * nb + q; };
     auto STRIP = [nb, LV](int j) { return nb * nb + 1 + 2 * LV * nb + j; };  // strips of the tile (j+1, j) completed
-    const int ncounters = nb * nb + 1 + 2 * LV * nb + nb;
+    auto PRE = [nb, LV](int p) { return nb * nb + 1 + 2 * LV * nb + nb + p; };    // early part of the last wide update of tile (p, p)
+    const int ncounters = nb * nb + 1 + 2 * LV * nb + 2 * nb;
     auto ops = [W](int j) { return chol_ops(j, W); };
     auto fin = [W](int j) { return chol_ops(j, W) + 1; };
     // "tile (i, j) is final": its own counter, or for the strip-solved tile below the diagonal the strip counter
@@ -599,9 +603,14 @@ static int make_factor_tasks(int nb, int nsm, std::vector<int>& flat, int& ntask
     for (int b = 0; b < nblk; b++) {
         const int p0 = b * W, p1 = std::min(nb, p0 + W);
         for (int p = p0; p < p1; p++) {
-            const int nprev = p == 0 ? 0 : (p % W != 0 ? 1 : W);
+            // the first diagonal tile of a block still lacks the wide update of the previous block: all but the last panel of
+            // it were applied by an ordinary task while the chain was busy with that panel (PRE, queued below), so that every
+            // DIAG fuses exactly one panel (10 us on the chain instead of 10 W)
+            const bool pre_done = split && W >= 2 && p > 0 && p % W == 0;
+            const int nprev = p == 0 ? 0 : ((p % W != 0 || pre_done) ? 1 : W);
             FactorTask dg(CT_DIAG, p, p, p, nprev, 0);
             if (p > 0) dg.dep(T(p, p), ops(p) - 1).dep(FINC(p, p - 1), FINV(p, p - 1));
+            if (pre_done) dg.dep(PRE(p), 1);
             q.push_back(dg.done(T(p, p), fin(p)));
             size_t narrow = 0;
             if (p > p0)
@@ -612,15 +621,23 @@ static int make_factor_tasks(int nb, int nsm, std::vector<int>& flat, int& ntask
                             q.push_back(FactorTask(CT_UPD, p - 1, i, j, 1, 0).dep(FINC(i, p - 1), FINV(i, p - 1)).dep(FINC(j, p - 1), FINV(j, p - 1)).dep(T(i, j), at).done(T(i, j), at + 1));
                             narrow++;
                         }
-            cover((p > p0 ? 42.0 : 30.0 + 10.0 * nprev) - narrow * 30.0 / nsm);
-            for (int i = p + 1; i < nb; i++) {
-                if (split && i == p + 1) {
-                    for (int k = 0; k < PANEL_STRIPS; k++)
-                        q.push_back(FactorTask(CT_PANEL, p, i, p, k + 1, 0).dep(T(p, p), fin(p)).dep(T(i, p), ops(p)).done(STRIP(p), 0));
-                    continue;
-                }
-                q.push_back(FactorTask(CT_PANEL, p, i, p, 0, 0).dep(T(p, p), fin(p)).dep(T(i, p), ops(p)).done(T(i, p), fin(p)));
+            // the successors of DIAG(p) on the chain take their tickets BEFORE the filler updates and wait for it on their SMs:
+            // the four strips of tile (p+1, p) (DIAG(p+1) waits for them) and PANEL(p+2, p) (the update of tile (p+2, p+1),
+            // which the strips of the next step wait for); five idle SMs for one DIAG instead of a chain that waits for a free one
+            auto panel_task = [&](int i) {
+                return FactorTask(CT_PANEL, p, i, p, 0, 0).dep(T(p, p), fin(p)).dep(T(i, p), ops(p)).done(T(i, p), fin(p));
+            };
+            int first_late = p + 1;
+            if (split && p + 1 < nb) {
+                for (int k = 0; k < PANEL_STRIPS; k++)
+                    q.push_back(FactorTask(CT_PANEL, p, p + 1, p, k + 1, 0).dep(T(p, p), fin(p)).dep(T(p + 1, p), ops(p)).done(STRIP(p), 0));
+                if (p + 2 < nb) q.push_back(panel_task(p + 2));
+                first_late = p + 3;
             }
+            cover((p > p0 ? 42.0 : 30.0 + 10.0 * nprev) - narrow * 30.0 / nsm);
+            for (int i = first_late; i < nb; i++) q.push_back(panel_task(i));
+            if (split && W >= 2 && p == p1 - 2 && p1 - p0 == W && p1 < nb)
+                q.push_back(FactorTask(CT_UPD, p0, p1, p1, W - 1, 0).dep(T(p1, p), fin(p)).dep(T(p1, p1), b).done(PRE(p1), 1));
             q.push_back(FactorTask(CT_TRANSPOSE, p, p, p, 0, 0).dep(T(p, p), fin(p)).done(TR_ALL, 0));
             cover(22.0);
         }

@@ -601,7 +601,7 @@ __device__ __forceinline__ void panel_strip_device(const DenseParams& P, int p, 
 // One launch runs the blocked Cholesky AND the inverse factor.  The host (gpso_capi.cu: build_factor_tasks) writes every
 // task with the counters it waits for and the counter it signals; the kernel is an interpreter.
 //
-// Cholesky.  Two-level blocking: panels are grouped in blocks of W (4 from 48 panels up, else 2).  A tile (i, j) in block
+// Cholesky.  Two-level blocking: panels are grouped in blocks of W (4 from 48 panels up, else 1 = unblocked).  A tile (i, j) in block
 // column bj = j / W receives, in this order, bj "wide" updates (one per earlier block, K = W * 128: the read-modify-write of
 // the tile -- 8 us at the ~14 B/clk an SM can store -- is paid once per W panels), then j - bj*W "narrow" updates from the
 // earlier panels of its own block (K = 128), then its final operation (factor+invert if i == j, panel solve otherwise).

@@ -81,7 +81,10 @@ def simulate(nb, nsm=148, with_inverse=False):
         heapq.heappush(free, (done, w))
         end = max(end, done)
     chain = sum(duration_us(t) for t in tasks if t[0] == DIAG) + 8.0 * (nb - 1)
-    return {"nb": nb, "tasks": len(tasks), "makespan_us": end, "work_bound_us": busy / nsm, "chain_us": chain,
+    # the other chain of dependent tasks: PANEL(i, p) -> narrow UPDATE of tile (i, p+1) -> PANEL(i, p+1) ... on the rows just below
+    # the diagonal (25 + 31 us per step with unblocked updates)
+    update_chain = (25.0 + 31.0) * (nb - 1)
+    return {"nb": nb, "tasks": len(tasks), "makespan_us": end, "work_bound_us": busy / nsm, "chain_us": chain, "update_chain_us": update_chain,
             "idle_waiting_us_per_worker": wait_total / nsm}
 
 
