@@ -65,6 +65,14 @@ constexpr int OZ_MAX_NP = 8192;                // int32 accumulators stay exact:
 constexpr int OZ_KINV_S = 7;                   // digits per operand of the int8 K_y^-1 = L^-T L^-1 product (54-bit fixed point per row)
 constexpr int OZ_KINV_MIN_NP = 512;            // automatic mode; measured down to N = 512 (LML+grad 0.553 -> 0.498 ms there, 1.13 -> 1.01 ms at 1024)
 constexpr int OZ_INV_S = 8;                    // digits per operand of the int8 inverse-factor products (62-bit fixed point per row)
+// Levels s < cap tiles of the inverse recursion stay in the persistent FP64 kernel, queued as soon as their inputs are (they
+// run on the SMs the chain-bound factorisation leaves idle); the int8 engine takes the levels above.  Measured per LML+grad
+// evaluation: N = 300 0.40 -> 0.31 ms, 600 0.54 -> 0.47, 1024 0.73 -> 0.68 (cap 8 = everything in the kernel up to 1024 rows);
+// at 4096 rows the FP64 merges start to get in the chain's way (cap 4 / 8 / 16: 3.23 / 3.26 / 3.41 ms).
+static inline int oz_inv_dmma_cap(int n_tiles) {
+    static const int cap_env = getenv("GPSO_INV_DMMA_CAP") ? atoi(getenv("GPSO_INV_DMMA_CAP")) : 0;  // tuning experiments only
+    return cap_env > 0 ? cap_env : (n_tiles >= 24 ? 4 : 8);
+}
 constexpr int OZ_INV_MIN_NP = 512;             // automatic mode; measured down to N = 512 (0.498 -> 0.474 ms there, 2.05 -> 1.75 ms at 2048)
 constexpr double OZ_TARGET = 0.02;             // accepted (estimated error) / (parity tolerance 1e-8 * variance)
 // screen-and-refine arg-max (kern_screen.cuh)
@@ -150,12 +158,12 @@ struct gpso_handle {
     DevBuf ozL, ozLT, ozLI, ozXT, rsL, rsLT, rsLI, rsXT;
     struct InvLevel { int s; size_t xt_off; int xt_rounds; size_t y_off; int y_rounds; };
     int inverse_mode = 0;   // 0 = automatic (int8 from OZ_INV_MIN_NP), 1 = FP64 DMMA tile tasks, 2 = int8 tcgen05
-    bool chol_tasks_inv = true;  // whether the cached task list contains the inverse-factor tasks
+    int chol_tasks_cap = -1;     // levels s < cap of the inverse recursion are in the cached task list
     // hybrid factorisation (hybrid_node): task lists / item tables per sub-matrix size, built on first use
     struct FactorPlan { DevBuf tasks; int ntasks = 0, ncounters = 0; };
     struct InvPlan { DevBuf items; std::vector<InvLevel> levels; };
     struct ItemList { DevBuf items; int rounds = 0; };
-    std::map<int, FactorPlan> factor_plans;    // key 2 n + with_inverse
+    std::map<int, FactorPlan> factor_plans;    // key 2048 n + levels of the inverse done by the kernel (cap)
     std::map<int, InvPlan> inv_plans;          // key n
     std::map<long long, ItemList> hyb_items;   // key (kind, split, n)
     int hybrid_mode = 0;    // 0 = automatic (matrices of more than HYB_MIN_TILES tiles), 1 = off, 2 = always (leaves of 2 tiles: tests)
@@ -561,7 +569,7 @@ struct FactorTask {
 };
 }  // namespace
 
-static int make_factor_tasks(int nb, int nsm, std::vector<int>& flat, int& ntasks, int& ncounters_out, bool with_inverse = true) {
+static int make_factor_tasks(int nb, int nsm, std::vector<int>& flat, int& ntasks, int& ncounters_out, int inv_cap = 1 << 30) {
     // panels per block of the two-level blocking; GPSO_CHOL_W overrides it for scheduling experiments (tools/factor_sim.py)
     static const int w_env = getenv("GPSO_CHOL_W") ? atoi(getenv("GPSO_CHOL_W")) : 0;
     // up to 47 panels (the leaves of the hybrid factorisation, every matrix up to N = 4096) the factorisation is bound by its
@@ -576,7 +584,8 @@ static int make_factor_tasks(int nb, int nsm, std::vector<int>& flat, int& ntask
     auto YD = [nb, LV](int l, int q) { return nb * nb + 1 + LV * nb + l * nb + q; };
     auto STRIP = [nb, LV](int j) { return nb * nb + 1 + 2 * LV * nb + j; };  // strips of the tile (j+1, j) completed
     auto PRE = [nb, LV](int p) { return nb * nb + 1 + 2 * LV * nb + nb + p; };    // early part of the last wide update of tile (p, p)
-    const int ncounters = nb * nb + 1 + 2 * LV * nb + 2 * nb;
+    auto TRC = [nb, LV](int p) { return nb * nb + 1 + 2 * LV * nb + 2 * nb + p; };  // transposes of the tiles 0 .. p done
+    const int ncounters = nb * nb + 1 + 2 * LV * nb + 3 * nb;
     auto ops = [W](int j) { return chol_ops(j, W); };
     auto fin = [W](int j) { return chol_ops(j, W) + 1; };
     // "tile (i, j) is final": its own counter, or for the strip-solved tile below the diagonal the strip counter
@@ -598,6 +607,54 @@ static int make_factor_tasks(int nb, int nsm, std::vector<int>& flat, int& ntask
     auto wide_task = [&](int b, int i, int j) {
         const int p0 = b * W, p1 = std::min(nb, p0 + W), last = p1 - 1;
         return FactorTask(CT_UPD, p0, i, j, p1 - p0, 0).dep(FINC(i, last), FINV(i, last)).dep(FINC(j, last), FINV(j, last)).dep(T(i, j), b).done(T(i, j), b + 1);
+    };
+    // ---- inverse factor by recursive doubling, levels s < inv_cap (the int8 engine takes the levels above): level s merges
+    // the inverses of the tile ranges [a, a+s) and [a+s, a+s+nv), a = 2 q s.  The tasks of a pair enter the queue as soon as
+    // the Cholesky step that completes their inputs has been queued -- X^T = L11^-T L21^T after the last panel of the first
+    // half, the merge L21^-1 = -L22^-1 X after the last tile of the pair -- so that they run on the SMs the chain-bound
+    // factorisation leaves idle instead of after it.
+    int nlevels = 0;
+    for (int s = 1; s < nb && s < inv_cap; s *= 2) nlevels++;
+    if (nlevels > LV) return fail(GPSO_E_BADARG, "matrix too large for the inverse recursion of the tile scheduler");
+    std::vector<std::vector<int>> pair_off(nlevels);  // first tile index of pair q in the kernel's enumeration, per level
+    for (int s = 1, l = 0; l < nlevels; s *= 2, l++) {
+        int total = 0;
+        for (int qq = 0; 2 * qq * s < nb; qq++) {
+            pair_off[l].push_back(total);
+            total += s * trtri_pair_vtiles(nb, s, qq);
+        }
+    }
+    auto inverse_tasks_ready_after = [&](int p) {
+        for (int s = 1, l = 0; l < nlevels; s *= 2, l++)
+            for (int qq = 0; 2 * qq * s < nb; qq++) {
+                const int nv = trtri_pair_vtiles(nb, s, qq), a = 2 * qq * s;
+                if (nv == 0) continue;
+                if (a + s + nv - 1 == p) {  // the pair is complete: merge
+                    for (int v = nv - 1; v >= 0; v--)  // large v = long contraction first
+                        for (int u = 0; u < s; u++) {
+                            FactorTask t(CT_Y, 0, 0, 0, s, pair_off[l][qq] + u * nv + v);
+                            t.dep(XTD(l, qq), s * nv);
+                            if (nv == 1) {
+                                t.dep(T(a + s, a + s), fin(a + s));
+                            } else {
+                                int s2 = 1, l2 = 0;
+                                while (s2 * 2 < nv) { s2 *= 2; l2++; }
+                                t.dep(YD(l2, (a + s) / (2 * s2)), s2 * (nv - s2));
+                            }
+                            q.push_back(t.done(YD(l, qq), 0));
+                        }
+                }
+                if (a + s - 1 == p) {  // the first half and the rows of L21 up to its last column are complete: X^T
+                    for (int u = 0; u < s; u++)  // small u = long contraction first
+                        for (int v = 0; v < nv; v++) {
+                            FactorTask t(CT_XT, 0, 0, 0, s, pair_off[l][qq] + u * nv + v);
+                            t.dep(TRC(a + s - 1), 1);
+                            if (s > 1) t.dep(YD(l - 1, 2 * qq), (s / 2) * (s / 2));
+                            t.dep(FINC(a + s + v, a + s - 1), FINV(a + s + v, a + s - 1));
+                            q.push_back(t.done(XTD(l, qq), 0));
+                        }
+                }
+            }
     };
     const int nblk = (nb + W - 1) / W;
     for (int b = 0; b < nblk; b++) {
@@ -638,7 +695,13 @@ static int make_factor_tasks(int nb, int nsm, std::vector<int>& flat, int& ntask
             for (int i = first_late; i < nb; i++) q.push_back(panel_task(i));
             if (split && W >= 2 && p == p1 - 2 && p1 - p0 == W && p1 < nb)
                 q.push_back(FactorTask(CT_UPD, p0, p1, p1, W - 1, 0).dep(T(p1, p), fin(p)).dep(T(p1, p1), b).done(PRE(p1), 1));
-            q.push_back(FactorTask(CT_TRANSPOSE, p, p, p, 0, 0).dep(T(p, p), fin(p)).done(TR_ALL, 0));
+            {
+                FactorTask tr(CT_TRANSPOSE, p, p, p, 0, 0);
+                tr.dep(T(p, p), fin(p));
+                if (p > 0) tr.dep(TRC(p - 1), 1);
+                q.push_back(tr.done(TRC(p), 1));
+            }
+            inverse_tasks_ready_after(p);
             cover(22.0);
         }
         cover(1e30);  // flush
@@ -651,45 +714,6 @@ static int make_factor_tasks(int nb, int nsm, std::vector<int>& flat, int& ntask
         for (int j = next_end; j < nb; j++)
             for (int i = j; i < nb; i++) wide.push_back(wide_task(b, i, j));
     }
-    // ---- inverse factor: level s merges [a, a+s) and [a+s, a+s+nv), a = 2 q s
-    for (int s = 1, l = 0; with_inverse && s < nb; s *= 2, l++) {
-        if (l >= LV) return fail(GPSO_E_BADARG, "matrix too large for the inverse recursion of the tile scheduler");
-        std::vector<int> off;  // first tile index of pair q in the kernel's enumeration
-        int total = 0;
-        for (int qq = 0; 2 * qq * s < nb; qq++) {
-            off.push_back(total);
-            total += s * trtri_pair_vtiles(nb, s, qq);
-        }
-        for (int pass = 0; pass < 2; pass++)
-            for (int qq = 0; 2 * qq * s < nb; qq++) {
-                const int nv = trtri_pair_vtiles(nb, s, qq), a = 2 * qq * s;
-                if (nv == 0) continue;
-                if (pass == 0) {
-                    for (int u = 0; u < s; u++)  // small u = long contraction first
-                        for (int v = 0; v < nv; v++) {
-                            FactorTask t(CT_XT, 0, 0, 0, s, off[qq] + u * nv + v);
-                            t.dep(TR_ALL, nb);
-                            if (s > 1) t.dep(YD(l - 1, 2 * qq), (s / 2) * (s / 2));
-                            t.dep(FINC(a + s + v, a + s - 1), FINV(a + s + v, a + s - 1));
-                            q.push_back(t.done(XTD(l, qq), 0));
-                        }
-                } else {
-                    for (int v = nv - 1; v >= 0; v--)  // large v = long contraction first
-                        for (int u = 0; u < s; u++) {
-                            FactorTask t(CT_Y, 0, 0, 0, s, off[qq] + u * nv + v);
-                            t.dep(XTD(l, qq), s * nv);
-                            if (nv == 1) {
-                                t.dep(T(a + s, a + s), fin(a + s));
-                            } else {
-                                int s2 = 1, l2 = 0;
-                                while (s2 * 2 < nv) { s2 *= 2; l2++; }
-                                t.dep(YD(l2, (a + s) / (2 * s2)), s2 * (nv - s2));
-                            }
-                            q.push_back(t.done(YD(l, qq), 0));
-                        }
-                }
-            }
-    }
     flat.clear();
     flat.reserve(q.size() * TASK_WORDS);
     for (const FactorTask& t : q) flat.insert(flat.end(), t.w, t.w + TASK_WORDS);
@@ -698,11 +722,12 @@ static int make_factor_tasks(int nb, int nsm, std::vector<int>& flat, int& ntask
     return 0;
 }
 
-static int get_factor_plan(gpso_handle* h, int n, bool with_inverse, gpso_handle::FactorPlan** out) {
-    gpso_handle::FactorPlan& plan = h->factor_plans[2 * n + (with_inverse ? 1 : 0)];
+static int get_factor_plan(gpso_handle* h, int n, int inv_cap, gpso_handle::FactorPlan** out) {
+    inv_cap = std::min(inv_cap, 1 << 10);
+    gpso_handle::FactorPlan& plan = h->factor_plans[2048 * n + inv_cap];
     if (!plan.tasks.p) {
         std::vector<int> flat;
-        GP_TRY(make_factor_tasks(n, h->nsm > 0 ? h->nsm : 148, flat, plan.ntasks, plan.ncounters, with_inverse));
+        GP_TRY(make_factor_tasks(n, h->nsm > 0 ? h->nsm : 148, flat, plan.ntasks, plan.ncounters, inv_cap));
         GP_TRY(plan.tasks.ensure(flat.size() * sizeof(int)));
         CU_TRY(cudaMemcpy(plan.tasks.p, flat.data(), flat.size() * sizeof(int), cudaMemcpyHostToDevice));
     }
@@ -710,12 +735,12 @@ static int get_factor_plan(gpso_handle* h, int n, bool with_inverse, gpso_handle
     return 0;
 }
 
-static int build_factor_tasks(gpso_handle* h, bool with_inverse) {
-    if (h->chol_tasks_nb == h->nb && h->chol_tasks_inv == with_inverse) return 0;
+static int build_factor_tasks(gpso_handle* h, int inv_cap) {
+    if (h->chol_tasks_nb == h->nb && h->chol_tasks_cap == inv_cap) return 0;
     std::vector<int> flat;
     int ntasks = 0, ncounters = 0;
-    GP_TRY(make_factor_tasks(h->nb, h->nsm > 0 ? h->nsm : 148, flat, ntasks, ncounters, with_inverse));
-    h->chol_tasks_inv = with_inverse;
+    GP_TRY(make_factor_tasks(h->nb, h->nsm > 0 ? h->nsm : 148, flat, ntasks, ncounters, inv_cap));
+    h->chol_tasks_cap = inv_cap;
     GP_TRY(h->chol_tasks.ensure(flat.size() * sizeof(int)));
     GP_TRY(h->chol_state.ensure((size_t)(2 + ncounters) * sizeof(int)));
     CU_TRY(cudaMemcpy(h->chol_tasks.p, flat.data(), flat.size() * sizeof(int), cudaMemcpyHostToDevice));
@@ -968,7 +993,7 @@ static int inverse_int8(gpso_handle* h, cudaStream_t st, int t0, int n, int s_lo
 constexpr int HYB_LEAF_TILES = 32;  // 4096 rows: measured 11.8 ms per LML+grad evaluation at N = 8192 against 13.5 with leaves of 2048 and 14.1
                                     // with one kernel; at N = 4096 one kernel (3.43 ms) beats two leaves of 2048 (3.89 ms)
 
-static int get_factor_plan(gpso_handle* h, int n, bool with_inverse, gpso_handle::FactorPlan** out);
+static int get_factor_plan(gpso_handle* h, int n, int inv_cap, gpso_handle::FactorPlan** out);
 
 static int get_hybrid_items(gpso_handle* h, int kind, int s, int n, gpso_handle::ItemList** out) {
     gpso_handle::ItemList& list = h->hyb_items[((long long)kind << 40) | ((long long)s << 20) | n];
@@ -1015,9 +1040,10 @@ static int hybrid_leaf(gpso_handle* h, cudaStream_t st, int t0, int n) {
         diag_transpose_kernel<<<1, 256, 0, st>>>(P.Linv, P.LinvT, Np);
         return check_launch(h, "diag_transpose");
     }
-    const bool inv8 = n * 128 >= OZ_INV_MIN_NP;
+    const int inv_cap = oz_inv_dmma_cap(n);
+    const bool inv8 = n * 128 >= OZ_INV_MIN_NP && inv_cap < n;
     gpso_handle::FactorPlan* plan = nullptr;
-    GP_TRY(get_factor_plan(h, n, !inv8, &plan));
+    GP_TRY(get_factor_plan(h, n, inv8 ? inv_cap : (1 << 30), &plan));
     GP_TRY(h->chol_state.ensure((size_t)(2 + plan->ncounters) * sizeof(int)));
     int* state = h->chol_state.as<int>();
     CU_TRY(cudaMemsetAsync(state, 0, (size_t)(2 + plan->ncounters) * sizeof(int), st));
@@ -1025,7 +1051,7 @@ static int hybrid_leaf(gpso_handle* h, cudaStream_t st, int t0, int n) {
     factor_persistent_kernel<<<grid, GTHREADS, DIAG_SMEM_BYTES, st>>>(P, Nsub, plan->tasks.as<int>(), plan->ntasks, state,
                                                                        h->logdet.as<double>() + t0, h->info.as<int>());
     GP_TRY(check_launch(h, "factor_persistent"));
-    if (inv8) GP_TRY(inverse_int8(h, st, t0, n, 1, n));
+    if (inv8) GP_TRY(inverse_int8(h, st, t0, n, inv_cap, n));
     return 0;
 }
 
@@ -1088,7 +1114,8 @@ static int factor_pipeline(gpso_handle* h, cudaStream_t st, bool need_kinv) {
     } else if (h->chol_mode == 1 && nb > 1) {
         // one persistent launch: blocked Cholesky + L^-1 (diagonal blocks, their transposes and -- unless the int8 engine
         // takes it over below -- the recursive doubling)
-        GP_TRY(build_factor_tasks(h, !inv8));
+        const int inv_cap = inv8 ? oz_inv_dmma_cap(nb) : (1 << 30);
+        GP_TRY(build_factor_tasks(h, inv_cap));
         GP_TRY(h->T.ensure((size_t)Np * Np * sizeof(double), true));
         P.T = h->T.as<double>();
         int* state = h->chol_state.as<int>();
@@ -1097,7 +1124,7 @@ static int factor_pipeline(gpso_handle* h, cudaStream_t st, bool need_kinv) {
         factor_persistent_kernel<<<grid, GTHREADS, DIAG_SMEM_BYTES, st>>>(P, h->N, h->chol_tasks.as<int>(), h->chol_ntasks, state,
                                                                            h->logdet.as<double>(), h->info.as<int>());
         GP_TRY(check_launch(h, "factor_persistent"));
-        if (inv8) GP_TRY(inverse_int8(h, st, 0, nb, 1, nb));
+        if (inv8 && inv_cap < nb) GP_TRY(inverse_int8(h, st, 0, nb, inv_cap, nb));
     } else {
         for (int p = 0; p < nb; p++) {
             diag_factor_inverse_kernel<<<1, DIAG_THREADS, DIAG_SMEM_BYTES, st>>>(P.K, P.Linv, Np, p, h->N, h->logdet.as<double>(),

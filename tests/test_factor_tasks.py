@@ -55,7 +55,8 @@ def test_queue_is_topological_and_complete(nb):
                 assert ctr[i * nb + j] == ops(j) and ctr[strip(j)] == 4, (i, j, int(ctr[i * nb + j]), int(ctr[strip(j)]))
             else:
                 assert ctr[i * nb + j] == ops(j) + 1, (i, j, int(ctr[i * nb + j]))
-    assert ctr[nb * nb] == nb
+    trc = lambda p: nb * nb + 1 + 2 * 8 * nb + 2 * nb + p  # transposes are chained: counter p = tiles 0 .. p transposed
+    assert all(ctr[trc(p)] == 1 for p in range(nb))
     assert seen["DIAG"] == nb and seen["TRANSPOSE"] == nb and seen["PANEL"] == nb * (nb - 1) // 2 + 3 * (nb - 1)
     for t in tasks:
         if OPS[int(t[0])] == "PANEL" and t[4] > 0:
