@@ -170,6 +170,10 @@ int gpso_set_factor_mode(gpso_handle* h, int mode);
  * persistent FP64 kernel (round-1 behaviour), mode 3 = hybrid down to leaves of 2 tiles (tests).
  * gpso_factor_info: out2 = {schedule of the last factorisation: 0 stepwise / 1 persistent / 2 hybrid, inner nodes of the hybrid}. */
 int gpso_factor_info(gpso_handle* h, int* out2);
+/* Device memory of destroyed handles is kept in a per-device pool (up to 24 GB) and handed to the next handle: the optimiser
+ * creates one handle per fit, and cudaMalloc / cudaFree of a handle's ~40 buffers cost more than a small fit.  This call gives
+ * the cached blocks of `device` back to the driver (cached_bytes_before, if not NULL, receives how much that was). */
+int gpso_trim_pool(int device, int64_t* cached_bytes_before);
 /* Host-only introspection (works without a GPU): the task list of the persistent factorisation kernel for a matrix of nb
  * 128-wide panels on nsm SMs, 16 ints per task (op, p, i, j, s, tile, 3 x dependency counter, 3 x value, counter to
  * signal, value / 0 = increment, 2 unused).  out may be NULL to query the sizes. */
@@ -186,7 +190,10 @@ int gpso_set_window(gpso_handle* h, int64_t candidates);
  * |varsigma| * kernel variance below the best mean cannot win) and hands its survivors to the full-precision engine; when the
  * means do not separate the candidates it continues with the automatic digit screen; 6 = forced 2-digit screen with all four
  * digit pairs (the first rung of the automatic ladder: 2 digits / all pairs, then 3 and 4 digits / triangular).  Takes effect
- * at the next gpso_factorize.  gpso_predict_y_* and gpso_ucb_topk_* never screen. */
+ * at the next gpso_factorize.  gpso_predict_y_* and gpso_ucb_topk_* never screen.  The rung the automatic ladder ended on
+ * (or "no rung separates these candidates") is remembered per matrix size for the process, because the optimiser opens a new
+ * handle for every fit; every 32nd call starts one rung lower again, and an explicit call of this function restarts the ladder
+ * for the handle's matrix size.  That state only changes the cost of a call, never the record it returns. */
 int gpso_set_screen_mode(gpso_handle* h, int mode);
 /* last fused arg-max call: out[0] path (0 unscreened, 1 screened, 2 full pass: too many survivors, 3 full pass: bound check
  * failed, 4 mean-bound level + refine), out[1] screening digits (0 for path 4), out[2] survivors, out[3] error bound E, out[4] largest |refined - screened| UCB over

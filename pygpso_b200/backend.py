@@ -105,6 +105,7 @@ def load_library():
         "gpso_set_overlap": (i32, [H, i32]),
         "gpso_set_factor_mode": (i32, [H, i32]),
         "gpso_factor_info": (i32, [H, ctypes.POINTER(ctypes.c_int)]),
+        "gpso_trim_pool": (i32, [i32, ctypes.POINTER(ctypes.c_int64)]),
         "gpso_debug_factor_tasks": (i32, [i32, i32, ctypes.POINTER(ctypes.c_int), i64, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]),
         "gpso_set_profile": (i32, [H, i32]),
         "gpso_last_windows": (i64, [H]),
@@ -140,7 +141,7 @@ EXPORTED_SYMBOLS = (
     "gpso_grow_count gpso_grow_leaves_host gpso_grow_leaves_dev gpso_grow_ucb_argmax gpso_grow_ucb_argmax_range gpso_state_bytes "
     "gpso_export_state_dev gpso_import_state_dev gpso_launch_count gpso_debug_fetch gpso_last_timing gpso_set_window "
     "gpso_set_profile gpso_last_windows gpso_set_predict_mode gpso_predict_info gpso_set_overlap "
-    "gpso_set_factor_mode gpso_factor_info gpso_debug_factor_tasks gpso_debug_trace gpso_set_kinv_mode gpso_set_inverse_mode gpso_set_l2_window gpso_debug_product_items "
+    "gpso_set_factor_mode gpso_factor_info gpso_trim_pool gpso_debug_factor_tasks gpso_debug_trace gpso_set_kinv_mode gpso_set_inverse_mode gpso_set_l2_window gpso_debug_product_items "
     "gpso_set_screen_mode gpso_screen_info gpso_debug_screen_bound gpso_probe_peaks gpso_set_screen_pair"
 ).split()
 
@@ -412,6 +413,12 @@ class CudaBackend:
 
     def open_session(self, kernel, n_lengthscales, has_mean):
         return CudaSession(self._lib, self.device, kernel, n_lengthscales, has_mean)
+
+    def trim_pool(self):
+        """Give the device memory cached from closed sessions back to the driver; returns the number of bytes released."""
+        before = ctypes.c_int64(0)
+        _check(self._lib, self._lib.gpso_trim_pool(self.device, ctypes.byref(before)), "gpso_trim_pool")
+        return int(before.value)
 
     def probe_peaks(self):
         """Pipe peaks of this GPU measured now: int8 tensor TOP/s, FP64 DMMA TFLOP/s, L2 -> shared memory GB/s."""

@@ -15,6 +15,7 @@
 #include <array>
 #include <string>
 #include <map>
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -85,19 +86,87 @@ constexpr int SCREEN_S_MIN = 2, SCREEN_S_MAX = 4;
 constexpr int SCREEN_MODE_BOUND = 5;           // gpso_set_screen_mode: mean-bound level first, then the automatic digit screen
 constexpr int SCREEN_MODE_FULL2 = 6;           // gpso_set_screen_mode: forced 2-digit full product
 
+// ---- device memory: blocks are recycled through a per-device pool ------------------------------------------------------------
+// The optimiser opens a new handle for every fit (the reference builds a new GPflow model per update); a handle owns ~40
+// buffers, and cudaMalloc / cudaFree cost 0.1-1 ms each and synchronise the device.  Released blocks therefore go to a free
+// list (per device, rounded sizes: powers of two up to 1 MB, multiples of 2 MB above) and are handed out again to requests of
+// nearly the same size.  Nothing is in flight on a block when it enters the list: gpso_destroy synchronises the device before
+// the buffers go, and a buffer that grows does the same before it lets go of its old block.
+namespace {
+constexpr size_t POOL_MAX_CACHED = 24ULL << 30;  // bytes kept per device; beyond this released blocks are freed
+constexpr int POOL_MAX_DEV = 64;
+struct DevPool {
+    std::mutex mu;
+    std::multimap<size_t, void*> blocks[POOL_MAX_DEV];
+    size_t cached[POOL_MAX_DEV] = {0};
+    static size_t rounded(size_t bytes) {
+        if (bytes <= (1u << 20)) {
+            size_t r = 512;
+            while (r < bytes) r <<= 1;
+            return r;
+        }
+        const size_t g = 2u << 20;
+        return (bytes + g - 1) / g * g;
+    }
+    void* take(int dev, size_t want, size_t* got) {  // want is a rounded size; blocks up to 25 % larger qualify
+        if (dev < 0 || dev >= POOL_MAX_DEV) return nullptr;
+        std::lock_guard<std::mutex> lock(mu);
+        auto it = blocks[dev].lower_bound(want);
+        if (it == blocks[dev].end() || it->first > want + want / 4) return nullptr;
+        void* p = it->second;
+        *got = it->first;
+        cached[dev] -= it->first;
+        blocks[dev].erase(it);
+        return p;
+    }
+    bool give(int dev, void* p, size_t bytes) {
+        static const bool enabled = !(getenv("GPSO_POOL") && atoi(getenv("GPSO_POOL")) == 0);  // A/B measurements only
+        if (!enabled || dev < 0 || dev >= POOL_MAX_DEV) return false;
+        std::lock_guard<std::mutex> lock(mu);
+        if (cached[dev] + bytes > POOL_MAX_CACHED) return false;
+        blocks[dev].emplace(bytes, p);
+        cached[dev] += bytes;
+        return true;
+    }
+    void flush(int dev) {  // out of memory: give everything back to the driver
+        if (dev < 0 || dev >= POOL_MAX_DEV) return;
+        std::lock_guard<std::mutex> lock(mu);
+        for (auto& kv : blocks[dev]) cudaFree(kv.second);
+        blocks[dev].clear();
+        cached[dev] = 0;
+    }
+};
+DevPool g_pool;
+}  // namespace
+
 struct DevBuf {
     void* p = nullptr;
-    size_t cap = 0;
+    size_t cap = 0;    // bytes the owner may use
+    size_t block = 0;  // size of the pool block behind p
+    int dev = -1;
     int ensure(size_t bytes, bool zero = false) {
         if (bytes <= cap) return 0;
-        if (p) cudaFree(p);
-        p = nullptr;
-        cap = 0;
-        cudaError_t e = cudaMalloc(&p, bytes);
-        if (e != cudaSuccess) {
-            char b[256];
-            snprintf(b, sizeof b, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
-            return fail(GPSO_E_NOMEM, b);
+        if (p) {
+            cudaDeviceSynchronize();  // kernels of this handle may still read the old block
+            release();
+        }
+        cudaGetDevice(&dev);
+        const size_t want = DevPool::rounded(bytes);
+        p = g_pool.take(dev, want, &block);
+        if (!p) {
+            cudaError_t e = cudaMalloc(&p, want);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                g_pool.flush(dev);
+                e = cudaMalloc(&p, want);
+            }
+            if (e != cudaSuccess) {
+                p = nullptr;
+                char b[256];
+                snprintf(b, sizeof b, "cudaMalloc(%zu bytes) failed: %s", want, cudaGetErrorString(e));
+                return fail(GPSO_E_NOMEM, b);
+            }
+            block = want;
         }
         cap = bytes;
         if (zero) {
@@ -108,14 +177,15 @@ struct DevBuf {
         return 0;
     }
     void release() {
-        if (p) cudaFree(p);
+        if (p && !g_pool.give(dev, p, block)) cudaFree(p);
         p = nullptr;
         cap = 0;
+        block = 0;
     }
     DevBuf() = default;
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
-    ~DevBuf() { release(); }  // every buffer of a handle goes with it (gpso_destroy sets the device first)
+    ~DevBuf() { release(); }  // every buffer of a handle goes with it (gpso_destroy synchronises the device first)
     template <class T>
     T* as() const {
         return reinterpret_cast<T*>(p);
@@ -1369,8 +1439,8 @@ extern "C" int gpso_destroy(gpso_handle* h) {
     if (!h) return 0;
     cudaSetDevice(h->device);
     // a handle whose creation failed half-way arrives here too: every stream / event may still be null
-    for (cudaStream_t st : {h->stream, h->copy_stream, h->aux_stream})
-        if (st) cudaStreamSynchronize(st);
+    // the buffers go back to the pool, not to the driver: nothing may be in flight on them, whichever stream the caller used
+    cudaDeviceSynchronize();
     auto drop = [](cudaEvent_t e) {
         if (e) cudaEventDestroy(e);
     };
@@ -1853,6 +1923,8 @@ static void screen_error_bound(const gpso_handle* h, int S, bool full, double va
 // feedback of earlier calls asked for.  A rung is tried when its variance bound is below the kernel variance (a screen with
 // a looser bound cannot separate anything); how well it separates THESE candidates only the survivor count can tell.
 struct ScreenVariant { int S; bool full; };
+struct ScreenHint { int rung = 0; unsigned calls = 0; };
+static ScreenHint g_screen_hint[65];  // per matrix size in tiles; performance state only (see score_argmax)
 static const ScreenVariant SCREEN_LADDER[] = {{2, true}, {3, false}, {4, false}};
 constexpr int SCREEN_RUNGS = 3;
 
@@ -2186,7 +2258,17 @@ static int score_argmax(gpso_handle* h, cudaStream_t st, const double* Xc_dev, c
         // separate these candidates (too many survivors, seen after the first window or at the end) or whose bound fails the
         // check hands over to the next, more precise one; after the last rung the call runs the full pass
         const bool automatic = h->screen_mode == 1 || h->screen_mode == SCREEN_MODE_BOUND;
-        for (int rung = automatic ? std::max(0, h->screen_S_cur) : 0; rung < (automatic ? SCREEN_RUNGS : 1); rung++) {
+        // The optimiser builds a new model (a new handle) for every fit: the rung the previous handles ended on is kept per
+        // matrix size for the process, so that a run whose candidates no cheap rung can separate does not walk the ladder again
+        // after every fit.  Every 32nd call starts one rung lower again (the verdict may change as the data grow).  Only the
+        // cost depends on this state; the record returned never does.
+        ScreenHint& hint = g_screen_hint[std::min(h->nb, 64)];
+        int first = 0;
+        if (automatic) {
+            first = std::max(std::max(0, h->screen_S_cur), hint.rung);
+            if (first > 0 && (++hint.calls % 32u) == 0u) first--;
+        }
+        for (int rung = first; rung < (automatic ? SCREEN_RUNGS : 1); rung++) {
             ScreenVariant v = SCREEN_LADDER[std::min(rung, SCREEN_RUNGS - 1)];
             if (!automatic) {
                 if (h->screen_mode == SCREEN_MODE_FULL2) v = {2, true};
@@ -2215,7 +2297,11 @@ static int score_argmax(gpso_handle* h, cudaStream_t st, const double* Xc_dev, c
             }
             // feedback for later calls: start from the next rung when this one left more than M / 64 survivors or failed
             const long long count = (long long)h->scr_info[2];
-            if (automatic && (hopeless || count * 64 > M || h->scr_info[0] == 3.0)) h->screen_S_cur = std::max(h->screen_S_cur, rung + 1);
+            if (automatic) {
+                const bool weak = hopeless || count * 64 > M || h->scr_info[0] == 3.0;
+                h->screen_S_cur = weak ? rung + 1 : rung;
+                hint.rung = h->screen_S_cur;
+            }
             if (ok) {
                 h->scr_info[0] = 1.0;
                 return 0;
@@ -2575,6 +2661,20 @@ extern "C" int gpso_set_factor_mode(gpso_handle* h, int mode) {
     return 0;
 }
 
+extern "C" int gpso_trim_pool(int device, int64_t* cached_bytes_before) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n || device >= POOL_MAX_DEV)
+        return fail(GPSO_E_BADARG, "gpso_trim_pool: device index out of range");
+    CU_TRY(cudaSetDevice(device));
+    CU_TRY(cudaDeviceSynchronize());
+    if (cached_bytes_before) {
+        std::lock_guard<std::mutex> lock(g_pool.mu);
+        *cached_bytes_before = (int64_t)g_pool.cached[device];
+    }
+    g_pool.flush(device);
+    return 0;
+}
+
 extern "C" int gpso_factor_info(gpso_handle* h, int* out2) {
     if (!h || !out2) return fail(GPSO_E_BADARG, "gpso_factor_info: null argument");
     out2[0] = h->chol_mode == 0 ? 0 : (h->hybrid_nodes > 0 ? 2 : 1);
@@ -2655,6 +2755,7 @@ extern "C" int gpso_set_screen_mode(gpso_handle* h, int mode) {
         return fail(GPSO_E_BADARG, "gpso_set_screen_mode: mode must be 0 (off), 1 (automatic), 2..4 (digits), 5 (mean bound first) or 6 (2 digits, all pairs)");
     h->screen_mode = mode;
     h->screen_S_cur = 0;
+    if (h->nb > 0) g_screen_hint[std::min(h->nb, 64)] = ScreenHint();  // an explicit call restarts the ladder for this matrix size
     h->factorized = false;  // the fp32 copies are prepared by the next gpso_factorize
     return 0;
 }

@@ -49,6 +49,34 @@ def test_create_destroy_does_not_leak(cuda):
     assert free0 - free1 < 32 * 2 ** 20, (free0, free1)
 
 
+def test_closed_sessions_feed_the_next_one_and_trim_returns_the_memory(cuda):
+    """Blocks of a closed session stay in the library's pool (the optimiser opens one session per fit) and can be handed back."""
+    import torch
+
+    N, d = 700, 3
+    X, y = synthetic(N, d, seed=6)
+    theta = np.array([0.5, 1.0, 1e-3, 0.0])
+    cuda.trim_pool()
+    torch.cuda.synchronize()
+    free_empty, _ = torch.cuda.mem_get_info(cuda.device)
+    s = open_session(cuda, "Matern52", X, y)
+    s.factorize(theta)
+    first = s.ucb_argmax(np.random.default_rng(0).random((2000, d)), VARSIGMA)
+    s.close()
+    free_cached, _ = torch.cuda.mem_get_info(cuda.device)
+    assert free_cached < free_empty  # the closed session's blocks are still held
+    s = open_session(cuda, "Matern52", X, y)
+    s.factorize(theta)
+    again = s.ucb_argmax(np.random.default_rng(0).random((2000, d)), VARSIGMA)
+    s.close()
+    free_reused, _ = torch.cuda.mem_get_info(cuda.device)
+    assert again == first  # recycled (not zeroed) blocks do not change the result
+    assert free_cached - free_reused < 4 * 2 ** 20, (free_cached, free_reused)  # the second session ran on the first one's blocks
+    released = cuda.trim_pool()
+    free_after, _ = torch.cuda.mem_get_info(cuda.device)
+    assert released > 0 and free_after >= free_cached + released - 4 * 2 ** 20, (released, free_after, free_cached)
+
+
 def test_predict_after_loss_evaluation_refactorises(cuda):
     """predict -> training_loss (overwrites the device factor) -> predict at unchanged hyper-parameters."""
     X, y = synthetic(300, 3, seed=5)

@@ -64,6 +64,7 @@ def test_screened_matches_oracle_winner(cuda):
     h = go.Hyper(0.5, 1.2, 1e-3, 0.0)
     Xc = np.random.default_rng(7).random((M, d))
     s = open_session(cuda, "Matern52", X, y)
+    s.set_screen_mode(1)  # automatic (the default), ladder restarted for this matrix size
     s.factorize(theta_of(h))
     got = s.ucb_argmax(Xc, VARSIGMA)
     info = s.screen_info()
@@ -126,6 +127,35 @@ def test_plateau_falls_back_to_full_pass(cuda):
         ref, got, info = both(s, Xc, theta_of(h), mode)
         assert same_record(ref, got), (ref, got, info)
         assert info["path"].startswith("full pass"), info
+    s.close()
+
+
+def test_ladder_verdict_survives_the_handle(cuda):
+    """The optimiser opens a new session for every fit.  The rung the ladder ended on is kept per matrix size for the process:
+    after a call no rung could separate, a NEW session of the same size goes straight to the full pass (same record), and an
+    explicit gpso_set_screen_mode restarts the ladder."""
+    N, d, M = 1100, 3, 70_000
+    X, y = synthetic(N, d, seed=2)
+    theta = theta_of(go.Hyper(0.05, 1.0, 1e-3, 0.0))
+    Xc = 50.0 + np.random.default_rng(5).random((M, d))  # plateau: prior mean and variance everywhere
+    s = open_session(cuda, "Matern52", X, y)
+    ref, got, info = both(s, Xc, theta, 1)
+    s.close()
+    assert same_record(ref, got) and info["path"].startswith("full pass"), info
+    s = open_session(cuda, "Matern52", X, y)  # default mode, no explicit call: inherits the verdict
+    s.factorize(theta)
+    got2 = s.ucb_argmax(Xc, VARSIGMA)
+    info2 = s.screen_info()
+    assert same_record(ref, got2) and info2["path"] == "unscreened", info2
+    s.set_screen_mode(1)
+    s.factorize(theta)
+    got3 = s.ucb_argmax(Xc, VARSIGMA)
+    info3 = s.screen_info()
+    s.close()
+    assert same_record(ref, got3) and info3["path"].startswith("full pass"), info3
+    # leave the ladder of this matrix size restarted for the tests that follow
+    s = open_session(cuda, "Matern52", X, y)
+    s.set_screen_mode(1)
     s.close()
 
 
