@@ -239,6 +239,7 @@ struct gpso_handle {
     int hybrid_mode = 0;    // 0 = automatic (matrices of more than HYB_MIN_TILES tiles), 1 = off, 2 = always (leaves of 2 tiles: tests)
     int hybrid_nodes = 0;   // inner nodes of the last factorisation (0 = one persistent kernel)
     cudaStream_t aux_stream = nullptr;
+    cudaEvent_t ev_probe = nullptr;  // early verdict of a screening rung (run_screen_windows)
     cudaEvent_t ev_start = nullptr, ev_xcov[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
     int overlap = 1;
     int predict_mode = 0;   // 0 = automatic, 1 = FP64 DMMA product, 2 = int8 tcgen05 product
@@ -1392,6 +1393,7 @@ static int init_handle(gpso_handle* h, int device, int kernel_id, int ard, int m
     CU_TRY(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
     CU_TRY(cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
     CU_TRY(cudaEventCreateWithFlags(&h->ev_start, cudaEventDisableTiming));
+    CU_TRY(cudaEventCreateWithFlags(&h->ev_probe, cudaEventDisableTiming));
     for (int i = 0; i < 2; i++) {
         CU_TRY(cudaEventCreateWithFlags(&h->ev_copy[i], cudaEventDisableTiming));
         CU_TRY(cudaEventCreateWithFlags(&h->ev_used[i], cudaEventDisableTiming));
@@ -1451,6 +1453,7 @@ extern "C" int gpso_destroy(gpso_handle* h) {
         drop(h->ev_free[i]);
     }
     drop(h->ev_start);
+    drop(h->ev_probe);
     drop(h->ev_t0);
     drop(h->ev_t1);
     for (cudaEvent_t e : h->prof_events) drop(e);
@@ -2016,7 +2019,8 @@ static int run_screen_windows(gpso_handle* h, cudaStream_t st, const double* Xc_
     if (xs != st) CU_TRY(cudaStreamWaitEvent(xs, h->ev_start, 0));
     if (host) CU_TRY(cudaStreamWaitEvent(cs, h->ev_start, 0));
     bool cand_busy[2] = {false, false}, buf_busy[2] = {false, false};
-    long long nwin_done = nwin;
+    long long nwin_done = nwin, probe_rows = 0;
+    unsigned long long* probe = reinterpret_cast<unsigned long long*>(h->host_rec + MAX_LS + 14);  // pinned, unused during the pass
     const double beta = oz_beta(h);
     const float bscale = (float)(ldexp(1.0, 8 * S - 2) / beta);
     // triangular product: levels t < S, the lowest kept level has weight 256^0; full product: levels t <= 2S-2
@@ -2076,20 +2080,24 @@ static int run_screen_windows(gpso_handle* h, cudaStream_t st, const double* Xc_
         h->last_windows++;
         if (w == 0 && nwin >= 4) {
             // early verdict on this variant: if more than 1/16 of the first window lies within 2E of the window's own best value
-            // the screen cannot separate these candidates -- stop here instead of paying for the other windows
+            // the screen cannot separate these candidates -- stop instead of paying for the other windows.  The count is
+            // queued behind window 0 and read (pinned record) once window 1 has been queued, so the pipeline never drains.
             GP_TRY(h->surv_list.ensure(sizeof(long long)));
             screen_select_kernel<<<(unsigned)((Mw + 255) / 256), 256, 0, st>>>(h->scr_ucb.as<double>(), Mw, two_e,
                                                                               h->scr_state.as<unsigned long long>(),
                                                                               h->surv_list.as<long long>(), 0u);
             GP_TRY(check_launch(h, "screen_select"));
-            unsigned long long st0[2] = {0, 0};
-            CU_TRY(cudaMemcpyAsync(st0, h->scr_state.p, sizeof st0, cudaMemcpyDeviceToHost, st));
-            CU_TRY(cudaStreamSynchronize(st));
+            CU_TRY(cudaMemcpyAsync(probe, h->scr_state.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
             CU_TRY(cudaMemsetAsync(h->scr_state.as<unsigned long long>() + 1, 0, sizeof(unsigned long long), st));
-            if ((long long)st0[1] * 16 > Mw) {
+            CU_TRY(cudaEventRecord(h->ev_probe, st));
+            probe_rows = Mw;
+        }
+        if (w == 1 && probe_rows > 0) {
+            CU_TRY(cudaEventSynchronize(h->ev_probe));
+            if ((long long)probe[1] * 16 > probe_rows) {
                 *hopeless = true;
-                h->scr_info[2] = (double)st0[1] * ((double)M / (double)Mw);  // extrapolated survivor count, for the record
-                nwin_done = 1;
+                h->scr_info[2] = (double)probe[1] * ((double)M / (double)probe_rows);  // extrapolated survivor count, for the record
+                nwin_done = 2;
                 break;
             }
         }
