@@ -550,6 +550,7 @@ static int configure_kernels() {
     CU_TRY(cudaFuncSetAttribute(predict_trmm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     CU_TRY(cudaFuncSetAttribute(diag_factor_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM_BYTES));
     CU_TRY(cudaFuncSetAttribute(factor_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM_BYTES));
+    CU_TRY(cudaFuncSetAttribute(diag_transpose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_TRANSPOSE_SMEM));
     CU_TRY(cudaFuncSetAttribute(ozaki_kernel<OZ_KINV_S, OZ_LAUUM>, cudaFuncAttributeMaxDynamicSharedMemorySize, OzCfg<OZ_KINV_S>::SMEM_BYTES));
     CU_TRY(cudaFuncSetAttribute(ozaki_kernel<OZ_INV_S, OZ_GEMM>, cudaFuncAttributeMaxDynamicSharedMemorySize, OzCfg<OZ_INV_S>::SMEM_BYTES));
     CU_TRY(cudaFuncSetAttribute(crosscov_screen_kernel<KERNEL_MATERN12, 0, SCR_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_XCOV_SMEM_MAX));
@@ -1108,7 +1109,7 @@ static int hybrid_leaf(gpso_handle* h, cudaStream_t st, int t0, int n) {
         diag_factor_inverse_kernel<<<1, DIAG_THREADS, DIAG_SMEM_BYTES, st>>>(P.K, P.Linv, Np, 0, Nsub, h->logdet.as<double>() + t0,
                                                                              h->info.as<int>(), P.pivot_off);
         GP_TRY(check_launch(h, "diag_factor_inverse"));
-        diag_transpose_kernel<<<1, 256, 0, st>>>(P.Linv, P.LinvT, Np);
+        diag_transpose_kernel<<<1, 256, DIAG_TRANSPOSE_SMEM, st>>>(P.Linv, P.LinvT, Np);
         return check_launch(h, "diag_transpose");
     }
     const int inv_cap = oz_inv_dmma_cap(n);
@@ -1210,7 +1211,7 @@ static int factor_pipeline(gpso_handle* h, cudaStream_t st, bool need_kinv) {
                 GP_TRY(check_launch(h, "chol_trailing"));
             }
         }
-        diag_transpose_kernel<<<nb, 256, 0, st>>>(P.Linv, P.LinvT, Np);
+        diag_transpose_kernel<<<nb, 256, DIAG_TRANSPOSE_SMEM, st>>>(P.Linv, P.LinvT, Np);
         GP_TRY(check_launch(h, "diag_transpose"));
         if (inv8) {
             GP_TRY(inverse_int8(h, st, 0, nb, 1, nb));

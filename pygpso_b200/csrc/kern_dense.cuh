@@ -221,21 +221,39 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // (L_pp^-1)^T for every diagonal block, after the factorisation loop (grid = nb): LinvT_pp[r][c] = Linv_pp[c][r]
+// (L_pp^-1)^T -> LinvT: the lower 32x32 sub-blocks of the diagonal tile go through shared memory in ONE round (all global loads
+// in flight together, one barrier, coalesced stores).  Sub-block by sub-block with two barriers each, this was 24 us of pure
+// latency -- a quarter of an N = 100 evaluation and the tail of every small factorisation.
+constexpr int TRP = TB + 1;                                            // odd pitch: conflict-free transposed reads
+constexpr int DIAG_TRANSPOSE_SMEM = TB * TRP * (int)sizeof(double);    // 132 096 B
 __device__ __forceinline__ void diag_transpose_device(const double* __restrict__ Linv, double* __restrict__ LinvT, int Np, int p,
-                                                      double* tile /* 32 x 33 doubles of shared memory */) {
+                                                      double* tile /* TB x TRP doubles of shared memory */) {
     const size_t base = (size_t)p * TB * Np + (size_t)p * TB;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    __syncthreads();  // previous user of the shared memory is done
+#pragma unroll
     for (int bi = 0; bi < 4; bi++)
-        for (int bj = 0; bj <= bi; bj++) {
-            __syncthreads();
-            for (int r = ty; r < 32; r += 8) tile[r * 33 + tx] = __ldcg(Linv + base + (size_t)(bi * 32 + r) * Np + bj * 32 + tx);
-            __syncthreads();
-            for (int r = ty; r < 32; r += 8) LinvT[base + (size_t)(bj * 32 + r) * Np + bi * 32 + tx] = tile[tx * 33 + r];
-        }
+#pragma unroll
+        for (int bj = 0; bj <= bi; bj++)
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int r = bi * 32 + ty + 8 * k, c = bj * 32 + tx;
+                tile[r * TRP + c] = __ldcg(Linv + base + (size_t)r * Np + c);  // written by another SM: through L2
+            }
+    __syncthreads();
+#pragma unroll
+    for (int bi = 0; bi < 4; bi++)
+#pragma unroll
+        for (int bj = 0; bj <= bi; bj++)
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int c = bj * 32 + ty + 8 * k, r = bi * 32 + tx;
+                LinvT[base + (size_t)c * Np + r] = tile[r * TRP + c];
+            }
 }
 __global__ void __launch_bounds__(256) diag_transpose_kernel(const double* __restrict__ Linv, double* __restrict__ LinvT, int Np) {
-    __shared__ double tile[32 * 33];
-    diag_transpose_device(Linv, LinvT, Np, blockIdx.x, tile);
+    extern __shared__ __align__(16) double transpose_tile[];
+    diag_transpose_device(Linv, LinvT, Np, blockIdx.x, transpose_tile);
 }
 
 // Lprev != nullptr: the tile still lacks its last update; it is applied here, in shared memory, before the factorisation:
