@@ -551,6 +551,7 @@ static int configure_kernels() {
     CU_TRY(cudaFuncSetAttribute(diag_factor_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM_BYTES));
     CU_TRY(cudaFuncSetAttribute(factor_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM_BYTES));
     CU_TRY(cudaFuncSetAttribute(diag_transpose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_TRANSPOSE_SMEM));
+    CU_TRY(cudaFuncSetAttribute(grow_leaves_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, leaf_smem_bytes(LEAF_MAXD)));
     CU_TRY(cudaFuncSetAttribute(ozaki_kernel<OZ_KINV_S, OZ_LAUUM>, cudaFuncAttributeMaxDynamicSharedMemorySize, OzCfg<OZ_KINV_S>::SMEM_BYTES));
     CU_TRY(cudaFuncSetAttribute(ozaki_kernel<OZ_INV_S, OZ_GEMM>, cudaFuncAttributeMaxDynamicSharedMemorySize, OzCfg<OZ_INV_S>::SMEM_BYTES));
     CU_TRY(cudaFuncSetAttribute(crosscov_screen_kernel<KERNEL_MATERN12, 0, SCR_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_XCOV_SMEM_MAX));
@@ -2443,7 +2444,7 @@ static int grow_launch(const double* bounds_host, int d, int depth, double* out_
     GP_TRY(bdev.ensure(sizeof(double) * 2 * LEAF_MAXD));
     CU_TRY(cudaMemcpyAsync(bdev.p, bounds_host, sizeof(double) * 2 * d, cudaMemcpyHostToDevice, st));
     long long rows = gpso_grow_count(depth);
-    grow_leaves_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, st>>>(bdev.as<double>(), d, depth, rows, out_dev);
+    grow_leaves_kernel<<<(unsigned)((rows + 127) / 128), LEAF_THREADS, leaf_smem_bytes(d), st>>>(bdev.as<double>(), d, depth, rows, out_dev);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(GPSO_E_CUDA, std::string("launch of grow_leaves failed: ") + cudaGetErrorString(e));
     return 0;
@@ -2451,6 +2452,7 @@ static int grow_launch(const double* bounds_host, int d, int depth, double* out_
 
 extern "C" int gpso_grow_leaves_dev(int device, const double* bounds_host, int d, int depth, double* out_dev, void* stream) {
     CU_TRY(cudaSetDevice(device));
+    GP_TRY(configure_kernels_once(device));
     DevBuf b;
     int rc = grow_launch(bounds_host, d, depth, out_dev, (cudaStream_t)stream, b);
     if (rc == 0) {
@@ -2464,6 +2466,7 @@ extern "C" int gpso_grow_leaves_dev(int device, const double* bounds_host, int d
 extern "C" int gpso_grow_leaves_host(int device, const double* bounds_host, int d, int depth, double* out_host) {
     if (!out_host) return fail(GPSO_E_BADARG, "gpso_grow_leaves_host: null output");
     CU_TRY(cudaSetDevice(device));
+    GP_TRY(configure_kernels_once(device));
     long long rows = gpso_grow_count(depth);
     if (rows <= 0) return fail(GPSO_E_BADARG, "gpso_grow_leaves_host: bad depth");
     DevBuf out, b;
@@ -2504,7 +2507,7 @@ extern "C" int gpso_grow_ucb_argmax_range(gpso_handle* h, const double* bounds_h
     if (depth < 1 || depth > 20) return fail(GPSO_E_BADARG, "gpso_grow_ucb_argmax: depth must be in 1..20");
     CU_TRY(cudaEventRecord(h->ev_t0, st));
     CU_TRY(cudaMemcpyAsync(bdev, bounds_host, sizeof(double) * 2 * d, cudaMemcpyHostToDevice, st));
-    grow_leaves_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, st>>>(bdev, d, depth, rows, h->leaves.as<double>(), row0);
+    grow_leaves_kernel<<<(unsigned)((rows + 127) / 128), LEAF_THREADS, leaf_smem_bytes(d), st>>>(bdev, d, depth, rows, h->leaves.as<double>(), row0);
     GP_TRY(check_launch(h, "grow_leaves"));
     GP_TRY(score_argmax(h, st, h->leaves.as<double>(), nullptr, rows, varsigma, result_host));
     CU_TRY(cudaEventRecord(h->ev_t1, st));

@@ -481,7 +481,7 @@ def test_argmax_numpy_semantics_with_nan(cuda):
 # ---------------------------------------------------------------------------------------------------------------------
 # leaf generator
 # ---------------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("d,depth", [(1, 1), (2, 5), (3, 7), (10, 8)])
+@pytest.mark.parametrize("d,depth", [(1, 1), (2, 5), (3, 7), (10, 8), (33, 6), (64, 7)])
 def test_grow_leaves_bit_exact_small(cuda, d, depth):
     space = ParameterSpace(parameter_bounds=[[0, 1]] * d, parameter_names=[f"p{i}" for i in range(d)])
     child = space.ternary_split()[0]
