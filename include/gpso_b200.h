@@ -170,6 +170,14 @@ int gpso_set_factor_mode(gpso_handle* h, int mode);
  * persistent FP64 kernel (round-1 behaviour), mode 3 = hybrid down to leaves of 2 tiles (tests).
  * gpso_factor_info: out2 = {schedule of the last factorisation: 0 stepwise / 1 persistent / 2 hybrid, inner nodes of the hybrid}. */
 int gpso_factor_info(gpso_handle* h, int* out2);
+/* Host-only introspection (works without a GPU) of the hybrid factorisation of nb tiles with leaves of at most `leaf` tiles:
+ * the steps in execution order, four ints each {op, first tile, tiles, split}: op 0 = leaf (persistent FP64 kernel + its
+ * inverse), 1 = panel L21 = A21 L11^-T, 2 = Schur complement A22 -= L21 L21^T, 3 = merge of the two halves' inverses.  Returns
+ * the number of steps (out may be NULL).  gpso_debug_hybrid_items: the tile -> CTA table of a panel (kind 0) or Schur (kind 1)
+ * product of a node of n tiles split after s: [rounds][nsm][4] ints (row block, 64-row tile of B, first k-step, k-steps; row
+ * block < 0 = empty slot); returns the number of ints. */
+int64_t gpso_debug_hybrid_plan(int nb, int leaf, int* out, int64_t capacity);
+int64_t gpso_debug_hybrid_items(int kind, int s, int n, int nsm, int* out, int64_t capacity, int* rounds);
 /* Device memory of destroyed handles is kept in a per-device pool (up to 24 GB) and handed to the next handle: the optimiser
  * creates one handle per fit, and cudaMalloc / cudaFree of a handle's ~40 buffers cost more than a small fit.  This call gives
  * the cached blocks of `device` back to the driver (cached_bytes_before, if not NULL, receives how much that was). */

@@ -1068,27 +1068,75 @@ constexpr int HYB_LEAF_TILES = 32;  // 4096 rows: measured 11.8 ms per LML+grad 
 
 static int get_factor_plan(gpso_handle* h, int n, int inv_cap, gpso_handle::FactorPlan** out);
 
+// Tile table of one hybrid product for a node of n tiles split after s.  kind 0: L21 tile (I, J), I >= s > J, contraction over
+// the tiles [0, J] of row block J of L11^-1;  kind 1: Schur tile (I, J), s <= J <= I, contraction over the s tiles of L21.
+static void make_hybrid_items(int kind, int s, int n, int G, std::vector<int>& all, int& rounds) {
+    std::vector<std::array<int, 4>> items;
+    for (int I = s; I < n; I++) {
+        if (kind == 0) {
+            for (int J = 0; J < s; J++)
+                for (int hh = 0; hh < 2; hh++) items.push_back({I, 2 * J + hh, 0, 4 * (J + 1)});
+        } else {
+            for (int J = s; J <= I; J++)
+                for (int hh = 0; hh < 2; hh++) items.push_back({I, 2 * J + hh, 0, 4 * s});
+        }
+    }
+    all.clear();
+    size_t off = 0;
+    deal_items(items, G, all, off, rounds);
+}
+
 static int get_hybrid_items(gpso_handle* h, int kind, int s, int n, gpso_handle::ItemList** out) {
     gpso_handle::ItemList& list = h->hyb_items[((long long)kind << 40) | ((long long)s << 20) | n];
     if (!list.items.p) {
-        std::vector<std::array<int, 4>> items;
-        for (int I = s; I < n; I++) {
-            if (kind == 0) {  // L21 tile (I, J): contraction over the tiles [0, J] of L11^-1's row block J
-                for (int J = 0; J < s; J++)
-                    for (int hh = 0; hh < 2; hh++) items.push_back({I, 2 * J + hh, 0, 4 * (J + 1)});
-            } else {          // Schur tile (I, J), s <= J <= I: contraction over the s tiles of L21
-                for (int J = s; J <= I; J++)
-                    for (int hh = 0; hh < 2; hh++) items.push_back({I, 2 * J + hh, 0, 4 * s});
-            }
-        }
         std::vector<int> all;
-        size_t off = 0;
-        deal_items(items, h->nsm > 0 ? h->nsm : 148, all, off, list.rounds);
+        make_hybrid_items(kind, s, n, h->nsm > 0 ? h->nsm : 148, all, list.rounds);
         GP_TRY(list.items.ensure(all.size() * sizeof(int)));
         CU_TRY(cudaMemcpy(list.items.p, all.data(), all.size() * sizeof(int), cudaMemcpyHostToDevice));
     }
     *out = &list;
     return 0;
+}
+
+// The hybrid factorisation of n tiles starting at tile t0 as a flat list of steps {op, t0, n, s} in execution order
+// (tests/test_hybrid_plan.py replays it in numpy).  A node splits after s = the largest power of two below n.
+constexpr int HYB_LEAF = 0, HYB_PANEL = 1, HYB_SCHUR = 2, HYB_MERGE = 3;
+static void plan_hybrid(int t0, int n, int leaf, std::vector<std::array<int, 4>>& ops) {
+    if (n <= leaf) {
+        ops.push_back({HYB_LEAF, t0, n, 0});
+        return;
+    }
+    int s = 1;
+    while (2 * s < n) s *= 2;
+    plan_hybrid(t0, s, leaf, ops);
+    ops.push_back({HYB_PANEL, t0, n, s});
+    ops.push_back({HYB_SCHUR, t0, n, s});
+    plan_hybrid(t0 + s, n - s, leaf, ops);
+    ops.push_back({HYB_MERGE, t0, n, s});
+}
+
+extern "C" int64_t gpso_debug_hybrid_plan(int nb, int leaf, int* out, int64_t capacity) {
+    if (nb < 1 || leaf < 1) {
+        fail(GPSO_E_BADARG, "gpso_debug_hybrid_plan: bad argument");
+        return -1;
+    }
+    std::vector<std::array<int, 4>> ops;
+    plan_hybrid(0, nb, leaf, ops);
+    if (out)
+        for (size_t i = 0; i < ops.size() && (int64_t)(4 * i + 3) < capacity; i++)
+            for (int c = 0; c < 4; c++) out[4 * i + c] = ops[i][c];
+    return (int64_t)ops.size();
+}
+
+extern "C" int64_t gpso_debug_hybrid_items(int kind, int s, int n, int nsm, int* out, int64_t capacity, int* rounds) {
+    if (kind < 0 || kind > 1 || s < 1 || n <= s || nsm < 1 || !rounds) {
+        fail(GPSO_E_BADARG, "gpso_debug_hybrid_items: bad argument");
+        return -1;
+    }
+    std::vector<int> all;
+    make_hybrid_items(kind, s, n, nsm, all, *rounds);
+    if (out) std::copy(all.begin(), all.begin() + std::min<int64_t>(capacity, (int64_t)all.size()), out);
+    return (int64_t)all.size();
 }
 
 static int hybrid_leaf(gpso_handle* h, cudaStream_t st, int t0, int n) {
@@ -1128,29 +1176,39 @@ static int hybrid_leaf(gpso_handle* h, cudaStream_t st, int t0, int n) {
     return 0;
 }
 
-static int hybrid_node(gpso_handle* h, cudaStream_t st, int t0, int n, int leaf) {
-    if (n <= leaf) return hybrid_leaf(h, st, t0, n);
-    int s = 1;
-    while (2 * s < n) s *= 2;
+static int hybrid_node(gpso_handle* h, cudaStream_t st, int t0_root, int n_root, int leaf) {
+    std::vector<std::array<int, 4>> ops;
+    plan_hybrid(t0_root, n_root, leaf, ops);
     const int Np = h->Np;
-    const size_t off = (size_t)t0 * 128 * Np + (size_t)t0 * 128;
-    double* A = h->K.as<double>() + off;
-    h->hybrid_nodes++;
-    GP_TRY(hybrid_node(h, st, t0, s, leaf));
-    // L21 = A21 L11^-T
-    gpso_handle::ItemList* items = nullptr;
-    GP_TRY(oz_range_digits(h, st, A, n, OZR_PANEL, s, h->rsL, h->ozL, "digits_A21"));
-    GP_TRY(oz_range_digits(h, st, h->Linv.as<double>() + off, n, OZR_LOWER, s, h->rsLI, h->ozLI, "digits_Linv11"));
-    GP_TRY(get_hybrid_items(h, 0, s, n, &items));
-    GP_TRY(oz_range_product(h, st, h->ozL, h->rsL, h->ozLI, h->rsLI, items->items.as<int>(), items->rounds, n, A, nullptr, 1.0, false,
-                            "hybrid_panel"));
-    // A22 -= L21 L21^T (lower tiles)
-    GP_TRY(oz_range_digits(h, st, A, n, OZR_PANEL, s, h->rsL, h->ozL, "digits_L21"));
-    GP_TRY(get_hybrid_items(h, 1, s, n, &items));
-    GP_TRY(oz_range_product(h, st, h->ozL, h->rsL, h->ozL, h->rsL, items->items.as<int>(), items->rounds, n, A, nullptr, -1.0, true,
-                            "hybrid_schur"));
-    GP_TRY(hybrid_node(h, st, t0 + s, n - s, leaf));
-    return inverse_int8(h, st, t0, n, s, 2 * s);
+    for (const std::array<int, 4>& op : ops) {
+        const int t0 = op[1], n = op[2], s = op[3];
+        const size_t off = (size_t)t0 * 128 * Np + (size_t)t0 * 128;
+        double* A = h->K.as<double>() + off;
+        gpso_handle::ItemList* items = nullptr;
+        switch (op[0]) {
+            case HYB_LEAF:
+                GP_TRY(hybrid_leaf(h, st, t0, n));
+                break;
+            case HYB_PANEL:  // L21 = A21 L11^-T
+                h->hybrid_nodes++;
+                GP_TRY(oz_range_digits(h, st, A, n, OZR_PANEL, s, h->rsL, h->ozL, "digits_A21"));
+                GP_TRY(oz_range_digits(h, st, h->Linv.as<double>() + off, n, OZR_LOWER, s, h->rsLI, h->ozLI, "digits_Linv11"));
+                GP_TRY(get_hybrid_items(h, 0, s, n, &items));
+                GP_TRY(oz_range_product(h, st, h->ozL, h->rsL, h->ozLI, h->rsLI, items->items.as<int>(), items->rounds, n, A, nullptr, 1.0,
+                                        false, "hybrid_panel"));
+                break;
+            case HYB_SCHUR:  // A22 -= L21 L21^T (lower tiles)
+                GP_TRY(oz_range_digits(h, st, A, n, OZR_PANEL, s, h->rsL, h->ozL, "digits_L21"));
+                GP_TRY(get_hybrid_items(h, 1, s, n, &items));
+                GP_TRY(oz_range_product(h, st, h->ozL, h->rsL, h->ozL, h->rsL, items->items.as<int>(), items->rounds, n, A, nullptr, -1.0,
+                                        true, "hybrid_schur"));
+                break;
+            default:         // L21^-1 = -L22^-1 L21 L11^-1: the level-s merge of the recursive-doubling inverse
+                GP_TRY(inverse_int8(h, st, t0, n, s, 2 * s));
+                break;
+        }
+    }
+    return 0;
 }
 
 // Gram -> Cholesky -> inverse factor -> [K_y^-1] -> a, alpha -> scalars.  Uses h->ls_host/variance/noise/c0.
