@@ -74,6 +74,8 @@ static inline int oz_inv_dmma_cap(int n_tiles) {
     static const int cap_env = getenv("GPSO_INV_DMMA_CAP") ? atoi(getenv("GPSO_INV_DMMA_CAP")) : 0;  // tuning experiments only
     return cap_env > 0 ? cap_env : (n_tiles >= 24 ? 4 : 8);
 }
+constexpr int OZ_HYB_S = 7;                    // digits per operand of the hybrid factorisation's panel and Schur products: 54-bit fixed point per
+                                               // row, the rounding of an fp64 product of the same operands (the K_y^-1 product uses the same)
 constexpr int OZ_INV_MIN_NP = 512;             // automatic mode; measured down to N = 512 (0.498 -> 0.474 ms there, 2.05 -> 1.75 ms at 2048)
 constexpr double OZ_TARGET = 0.02;             // accepted (estimated error) / (parity tolerance 1e-8 * variance)
 // screen-and-refine arg-max (kern_screen.cuh)
@@ -554,6 +556,7 @@ static int configure_kernels() {
     CU_TRY(cudaFuncSetAttribute(grow_leaves_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, leaf_smem_bytes(LEAF_MAXD)));
     CU_TRY(cudaFuncSetAttribute(ozaki_kernel<OZ_KINV_S, OZ_LAUUM>, cudaFuncAttributeMaxDynamicSharedMemorySize, OzCfg<OZ_KINV_S>::SMEM_BYTES));
     CU_TRY(cudaFuncSetAttribute(ozaki_kernel<OZ_INV_S, OZ_GEMM>, cudaFuncAttributeMaxDynamicSharedMemorySize, OzCfg<OZ_INV_S>::SMEM_BYTES));
+    CU_TRY(cudaFuncSetAttribute(ozaki_kernel<OZ_HYB_S, OZ_GEMM>, cudaFuncAttributeMaxDynamicSharedMemorySize, OzCfg<OZ_HYB_S>::SMEM_BYTES));
     CU_TRY(cudaFuncSetAttribute(crosscov_screen_kernel<KERNEL_MATERN12, 0, SCR_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_XCOV_SMEM_MAX));
     CU_TRY(cudaFuncSetAttribute(crosscov_screen_kernel<KERNEL_MATERN32, 0, SCR_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_XCOV_SMEM_MAX));
     CU_TRY(cudaFuncSetAttribute(crosscov_screen_kernel<KERNEL_MATERN52, 0, SCR_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_XCOV_SMEM_MAX));
@@ -988,20 +991,21 @@ static int ensure_inverse_buffers(gpso_handle* h) {
 }
 
 // Digits of the rows of the n-tile sub-matrix whose first element is M (row pitch Np), over the k-range `kind` selects.
-static int oz_range_digits(gpso_handle* h, cudaStream_t st, const double* M, int n, int kind, int s, DevBuf& scales, DevBuf& out,
-                           const char* what) {
+template <int S>
+static int oz_range_digits_t(gpso_handle* h, cudaStream_t st, const double* M, int n, int kind, int s, DevBuf& scales, DevBuf& out,
+                             const char* what) {
     const int Np = h->Np, nks = Np / 32;
     range_rowscale_kernel<<<n * 16, 256, 0, st>>>(M, Np, kind, s, n, scales.as<double>());
     GP_TRY(check_launch(h, what));
-    range_slices_kernel<OZ_INV_S><<<dim3(4 * n, n), 256, 0, st>>>(M, scales.as<double>(), Np, nks, kind, s, n, out.as<uint8_t>());
+    range_slices_kernel<S><<<dim3(4 * n, n), 256, 0, st>>>(M, scales.as<double>(), Np, nks, kind, s, n, out.as<uint8_t>());
     return check_launch(h, what);
 }
 
 // out[i][j] (+)= sign * sum_k A[i][k] B[j][k] over the tiles and k-ranges of an item table, on the int8 tensor cores
-static int oz_range_product(gpso_handle* h, cudaStream_t st, const DevBuf& A, const DevBuf& rsA, const DevBuf& B, const DevBuf& rsB,
-                            const int* items, int rounds, int n, double* out, double* out_t, double sign, bool accumulate,
-                            const char* what) {
-    constexpr int S = OZ_INV_S;
+template <int S>
+static int oz_range_product_t(gpso_handle* h, cudaStream_t st, const DevBuf& A, const DevBuf& rsA, const DevBuf& B, const DevBuf& rsB,
+                              const int* items, int rounds, int n, double* out, double* out_t, double sign, bool accumulate,
+                              const char* what) {
     OzParams P;
     P.A = A.as<uint8_t>();
     P.B = B.as<uint8_t>();
@@ -1022,6 +1026,19 @@ static int oz_range_product(gpso_handle* h, cudaStream_t st, const DevBuf& A, co
     P.Np = h->Np;
     ozaki_kernel<S, OZ_GEMM><<<h->nsm > 0 ? h->nsm : 148, OZ_THREADS, OzCfg<S>::SMEM_BYTES, st>>>(P);
     return check_launch(h, what);
+}
+
+// digits = OZ_INV_S (8: inverse-factor products) or OZ_HYB_S (7: panel solve and Schur complement of the hybrid factorisation)
+static int oz_range_digits(gpso_handle* h, cudaStream_t st, const double* M, int n, int kind, int s, DevBuf& scales, DevBuf& out,
+                           const char* what, int digits = OZ_INV_S) {
+    return digits == 7 ? oz_range_digits_t<7>(h, st, M, n, kind, s, scales, out, what)
+                       : oz_range_digits_t<OZ_INV_S>(h, st, M, n, kind, s, scales, out, what);
+}
+static int oz_range_product(gpso_handle* h, cudaStream_t st, const DevBuf& A, const DevBuf& rsA, const DevBuf& B, const DevBuf& rsB,
+                            const int* items, int rounds, int n, double* out, double* out_t, double sign, bool accumulate,
+                            const char* what, int digits = OZ_INV_S) {
+    return digits == 7 ? oz_range_product_t<7>(h, st, A, rsA, B, rsB, items, rounds, n, out, out_t, sign, accumulate, what)
+                       : oz_range_product_t<OZ_INV_S>(h, st, A, rsA, B, rsB, items, rounds, n, out, out_t, sign, accumulate, what);
 }
 
 // Levels s_lo <= s < s_hi of the recursive-doubling inverse of the n-tile diagonal block that starts at tile t0 (the whole
@@ -1180,6 +1197,7 @@ static int hybrid_node(gpso_handle* h, cudaStream_t st, int t0_root, int n_root,
     std::vector<std::array<int, 4>> ops;
     plan_hybrid(t0_root, n_root, leaf, ops);
     const int Np = h->Np;
+    static const int hyb_s = (getenv("GPSO_HYB_S") && atoi(getenv("GPSO_HYB_S")) == 8) ? 8 : OZ_HYB_S;  // A/B measurements only
     for (const std::array<int, 4>& op : ops) {
         const int t0 = op[1], n = op[2], s = op[3];
         const size_t off = (size_t)t0 * 128 * Np + (size_t)t0 * 128;
@@ -1191,17 +1209,17 @@ static int hybrid_node(gpso_handle* h, cudaStream_t st, int t0_root, int n_root,
                 break;
             case HYB_PANEL:  // L21 = A21 L11^-T
                 h->hybrid_nodes++;
-                GP_TRY(oz_range_digits(h, st, A, n, OZR_PANEL, s, h->rsL, h->ozL, "digits_A21"));
-                GP_TRY(oz_range_digits(h, st, h->Linv.as<double>() + off, n, OZR_LOWER, s, h->rsLI, h->ozLI, "digits_Linv11"));
+                GP_TRY(oz_range_digits(h, st, A, n, OZR_PANEL, s, h->rsL, h->ozL, "digits_A21", hyb_s));
+                GP_TRY(oz_range_digits(h, st, h->Linv.as<double>() + off, n, OZR_LOWER, s, h->rsLI, h->ozLI, "digits_Linv11", hyb_s));
                 GP_TRY(get_hybrid_items(h, 0, s, n, &items));
                 GP_TRY(oz_range_product(h, st, h->ozL, h->rsL, h->ozLI, h->rsLI, items->items.as<int>(), items->rounds, n, A, nullptr, 1.0,
-                                        false, "hybrid_panel"));
+                                        false, "hybrid_panel", hyb_s));
                 break;
             case HYB_SCHUR:  // A22 -= L21 L21^T (lower tiles)
-                GP_TRY(oz_range_digits(h, st, A, n, OZR_PANEL, s, h->rsL, h->ozL, "digits_L21"));
+                GP_TRY(oz_range_digits(h, st, A, n, OZR_PANEL, s, h->rsL, h->ozL, "digits_L21", hyb_s));
                 GP_TRY(get_hybrid_items(h, 1, s, n, &items));
                 GP_TRY(oz_range_product(h, st, h->ozL, h->rsL, h->ozL, h->rsL, items->items.as<int>(), items->rounds, n, A, nullptr, -1.0,
-                                        true, "hybrid_schur"));
+                                        true, "hybrid_schur", hyb_s));
                 break;
             default:         // L21^-1 = -L22^-1 L21 L11^-1: the level-s merge of the recursive-doubling inverse
                 GP_TRY(inverse_int8(h, st, t0, n, s, 2 * s));
