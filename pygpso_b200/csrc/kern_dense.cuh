@@ -41,7 +41,7 @@ constexpr int SP = SB + 4;             // row pitch of stand-alone 32x32 tiles (
 // the inverse is kept as a "staircase": sub-block row k holds k+1 sub-blocks with row pitch XP(k) (== 4 mod 16)
 __host__ __device__ constexpr int XP(int k) { return SB * (k + 1) + 4; }
 __host__ __device__ constexpr int XO(int k) { return SB * (16 * k * (k + 1) + 4 * k); }
-constexpr int DIAG_SMEM_DOUBLES = TB * DP + XO(4) /* inverse */ + 4 * SB /* column + diagonal broadcast, x2 */;
+constexpr int DIAG_SMEM_DOUBLES = TB * DP + XO(4) /* inverse */ + 6 * SB /* column + diagonal broadcast, x3 */;
 constexpr int DIAG_SMEM_BYTES = DIAG_SMEM_DOUBLES * (int)sizeof(double);
 
 // 1/sqrt(d) and 1/d together: hardware seed y (MUFU.RSQ64H, ~2^-22) and e = 1 - d y^2, then
@@ -87,14 +87,16 @@ __device__ __forceinline__ void warp_bar() { asm volatile("bar.warp.sync 0xfffff
 //   a[k] = row `lane` of the sub-block (lower part), becomes row `lane` of L;  dg = the lane's own diagonal entry
 //   s[k] = sum_{j<k} L[k][j] X[j][lane]  (lane owns column `lane` of X = L^-1)
 // Column J of the partially reduced block (cb) and the partially reduced diagonal (dgb) are published in shared memory
-// (double buffered).  Dependent chain per column:  d_J -> (1/sqrt(d_J), 1/d_J) -> d_J+1 = dgb[J+1] - cb[J+1]^2 / d_J,
+// (three buffers in rotation).  Dependent chain per column:  d_J -> (1/sqrt(d_J), 1/d_J) -> d_J+1 = dgb[J+1] - cb[J+1]^2 / d_J,
 // i.e. one seed + five FP64 operations; the shared-memory hop (a[J+1] update -> publish -> read back) runs beside it.
 template <int J>
 struct CholInvCol {
     static __device__ __forceinline__ void run(double (&a)[SB], double (&s)[SB], double& dg, double d, double y, unsigned cb_addr,
                                                double* D, double* X, int xp, int lane, int& bad, double& my_il) {
-        const unsigned cb = cb_addr + (J & 1) * 2 * SB * 8;          // this column:   cb[0..31], dgb[32..63]
-        const unsigned cbn = cb_addr + ((J + 1) & 1) * 2 * SB * 8;   // next column
+        // three buffers in rotation: column J still reads its buffer after the barrier below (the tail of its update loop), and
+        // the next stores into that buffer come from column J+2, i.e. behind column J+1's barrier
+        const unsigned cb = cb_addr + (J % 3) * 2 * SB * 8;          // this column:   cb[0..31], dgb[32..63]
+        const unsigned cbn = cb_addr + ((J + 1) % 3) * 2 * SB * 8;   // next column
         bad = (bad == 0 && !(d > 0.0)) ? J + 1 : bad;
         double il, ild;
         rsqrt_rcp_finish(d, y, il, ild);
@@ -142,7 +144,7 @@ struct CholInvCol<SB> {
 };
 
 // D: 32x32 sub-block in the big array (pitch DP), overwritten by L (lower); X: its inverse (pitch xp, zeros above);
-// colbuf: 4*SB doubles, 16-byte aligned.  Returns 1/L_jj of row `lane`.
+// colbuf: 6*SB doubles, 16-byte aligned.  Returns 1/L_jj of row `lane`.
 __device__ __noinline__ double chol_inv_32(double* D, double* X, int xp, double* colbuf, int lane, int pivot_base, int* info) {
     double a[SB], s[SB];
     DIAG_STAMP(20);
@@ -266,7 +268,7 @@ __device__ __forceinline__ void diag_block_device(double* __restrict__ K, double
                                                   const double* __restrict__ Lprev = nullptr, int nprev = 0, int pivot_off = 0) {
     double* S = sm;                  // [TB][DP]: lower sub-blocks A -> L in place; upper sub-blocks (0,1..3) = T_pb,j scratch
     double* Xs = sm + TB * DP;       // staircase inverse: sub-block (k,j), j <= k, at Xs + XO(k) + j*SB, row pitch XP(k)
-    double* colbuf = Xs + XO(4);     // [2][2][SB]
+    double* colbuf = Xs + XO(4);     // [3][2][SB]
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const size_t base = (size_t)p * TB * Np + (size_t)p * TB;
