@@ -45,6 +45,27 @@ def main():
         rec = s.ucb_argmax(Xc, 1.8)
         print("screen", mode, rec[0], s.screen_info()["path"], s.screen_info()["survivors"])
         s.close()
+    # windows with side-stream overlap, the early verdict, the mean-bound level, top-k, both full-precision engines
+    for mode, window in ((1, 8192), (5, 16384)):
+        s = cuda.open_session("Matern52", 1, True)
+        s.set_data(X, y)
+        s.set_screen_mode(mode)
+        s.factorize(np.array([0.4, 1.2, 1e-3, 0.1]))
+        s.set_window(window)
+        rec = s.ucb_argmax(Xc, 1.8)
+        top = s.ucb_topk(Xc[:9000], 1.8, 5)
+        print("windows", mode, rec[0], s.screen_info()["path"], s.screen_info()["screen_windows"], int(top[0, 0]))
+        s.set_predict_mode(1, 0)  # FP64 DMMA engine
+        s.factorize(np.array([0.4, 1.2, 1e-3, 0.1]))
+        mean, var = s.predict_y(Xc[:3000])
+        print("dmma", float(mean[0]), float(var[0]))
+        s.close()
+    s = cuda.open_session("SquaredExponential", d, True)  # ARD gradient, int8 inverse and K_y^-1 at nine tiles
+    X9 = rng.random((1100, d))
+    s.set_data(X9, np.sin(3 * X9.sum(1))[:, None])
+    f, g = s.neg_lml_and_grad(np.array([0.0] * d + [0.5, -6.0, 0.1]))
+    print("ard", f, g[:2])
+    s.close()
     print("released", cuda.trim_pool())
 
 
