@@ -667,8 +667,12 @@ def main():
                 variant_key = f"screen{screen['digits']}{'f' if screen.get('all_pairs') else ''}" if screened else engine["engine"]
                 entry = json.load(open(prof_json)).get(f"{args.workload}:{variant_key}")
                 if entry:
-                    roofline["traffic"] = entry.get("dram_bytes_per_launch")
-                    roofline["traffic_source"] = entry.get("source")
+                    # the capture is one full window; the launches of a step are not all full (ramp-up and tail windows):
+                    # scaled to the average number of candidates per launch of this run
+                    per_launch = m_local * args.steps / max(roofline.get("launches", 1), 1)
+                    scale = per_launch / entry["candidates_per_launch"] if entry.get("candidates_per_launch") else 1.0
+                    roofline["traffic"] = entry.get("dram_bytes_per_launch") * scale
+                    roofline["traffic_source"] = entry.get("source") + f"; scaled by {scale:.3f} = candidates per launch of this run / of the capture"
             except Exception:
                 pass
         hbm_peak = None

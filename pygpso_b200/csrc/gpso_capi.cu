@@ -2063,6 +2063,25 @@ static int run_screen_windows(gpso_handle* h, cudaStream_t st, const double* Xc_
     // kernel stalled it): with the pair kernel the windows run in order on one stream.
     const bool overlap = h->overlap && nwin > 1 && !(!full && screen_pair_enabled(h, S));
     const int nbuf = overlap ? 2 : 1;
+    // Window list.  With the overlap the cross-covariance of the FIRST window is the one stage nothing hides (1.6 ms of a
+    // 32 ms step when eight GPUs share the candidates): the pipeline ramps up through a quarter and a half window.
+    std::vector<std::pair<long long, long long>> wins;  // (first candidate, candidates)
+    {
+        long long off = 0;
+        if (overlap && nwin >= 3 && h->window_override == 0)
+            for (long long ramp : {W / 4, W / 2}) {
+                const long long r = ramp / 1024 * 1024;
+                if (r >= 1024 && off + r < M) {
+                    wins.emplace_back(off, r);
+                    off += r;
+                }
+            }
+        // the rest in equal windows (no short tail launch)
+        const long long rest = M - off, nrest = (rest + W - 1) / W;
+        const long long each = h->window_override == 0 ? std::min(W, ((rest + nrest - 1) / nrest + 1023) / 1024 * 1024) : W;
+        for (; off < M; off += each) wins.emplace_back(off, std::min(each, M - off));
+    }
+    const long long nwin_total = (long long)wins.size();
     GP_TRY(h->part32.ensure((size_t)W * h->nb * sizeof(float)));
     GP_TRY(h->scr_ucb.ensure((size_t)M * sizeof(double)));
     GP_TRY(h->scr_state.ensure(4 * sizeof(unsigned long long)));
@@ -2097,17 +2116,17 @@ static int run_screen_windows(gpso_handle* h, cudaStream_t st, const double* Xc_
     if (xs != st) CU_TRY(cudaStreamWaitEvent(xs, h->ev_start, 0));
     if (host) CU_TRY(cudaStreamWaitEvent(cs, h->ev_start, 0));
     bool cand_busy[2] = {false, false}, buf_busy[2] = {false, false};
-    long long nwin_done = nwin, probe_rows = 0;
+    long long nwin_done = nwin_total, probe_rows = 0;
     unsigned long long* probe = reinterpret_cast<unsigned long long*>(h->host_rec + MAX_LS + 14);  // pinned, unused during the pass
     const double beta = oz_beta(h);
     const float bscale = (float)(ldexp(1.0, 8 * S - 2) / beta);
     // triangular product: levels t < S, the lowest kept level has weight 256^0; full product: levels t <= 2S-2
     const double gscale = full ? beta * ldexp(1.0, -2 * (8 * S - 2)) : beta * ldexp(1.0, -2 * (8 * S - 2) + 8 * (S - 1));
-    for (long long w = 0; w < nwin; w++) {
+    for (long long w = 0; w < nwin_total; w++) {
         const int cb = (int)(w & 1);
         const int b = overlap ? cb : 0;
-        const long long off = w * W;
-        const long long Mw = std::min(W, M - off);
+        const long long off = wins[(size_t)w].first;
+        const long long Mw = wins[(size_t)w].second;
         const long long Mw_pad = ((Mw + SCR_NT - 1) / SCR_NT) * SCR_NT;
         const double* src;
         if (host) {
@@ -2156,7 +2175,7 @@ static int run_screen_windows(gpso_handle* h, cudaStream_t st, const double* Xc_
             buf_busy[b] = true;
         }
         h->last_windows++;
-        if (w == 0 && nwin >= 4) {
+        if (w == 0 && nwin_total >= 4) {
             // early verdict on this variant: if more than 1/16 of the first window lies within 2E of the window's own best value
             // the screen cannot separate these candidates -- stop instead of paying for the other windows.  The count is
             // queued behind window 0 and read (pinned record) once window 1 has been queued, so the pipeline never drains.
