@@ -1997,8 +1997,6 @@ static void screen_error_bound(const gpso_handle* h, int S, bool full, double va
     screen_error_model(f, S, full ? 1 : 0, varsigma, e_total, e_var_out, e_mean_out);
 }
 
-// automatic mode: the fewest digits whose variance bound is a screening-grade 5 % of the kernel variance, never below the
-// count the survivor feedback of earlier calls asked for
 // The ladder of screening variants, cheapest first: 2 digits with all four digit pairs (16 KB of operands per k-step, exact
 // product of 14-bit operands), then the triangular products of 3 and 4 digits.  screen_S_cur is the rung the survivor
 // feedback of earlier calls asked for.  A rung is tried when its variance bound is below the kernel variance (a screen with
@@ -2008,18 +2006,6 @@ struct ScreenHint { int rung = 0; unsigned calls = 0; };
 static ScreenHint g_screen_hint[65];  // per matrix size in tiles; performance state only (see score_argmax)
 static const ScreenVariant SCREEN_LADDER[] = {{2, true}, {3, false}, {4, false}};
 constexpr int SCREEN_RUNGS = 3;
-
-[[maybe_unused]] static bool screen_pick_variant(const gpso_handle* h, ScreenVariant* out) {
-    for (int r = std::max(0, h->screen_S_cur); r < SCREEN_RUNGS; r++) {
-        double e = 0.0, ev = 0.0, em = 0.0;
-        screen_error_bound(h, SCREEN_LADDER[r].S, SCREEN_LADDER[r].full, 0.0, &e, &ev, &em);
-        if (ev <= 1.0 * h->variance) {
-            *out = SCREEN_LADDER[r];
-            return true;
-        }
-    }
-    return false;
-}
 
 // Host-only (no GPU needed): the error bound of the screening pass for a fit with N training points, the given kernel / noise
 // variance, largest power-of-two row scale of L^-1, sum of the squared row scales and |alpha|_2.  out3 = {E, E_var, E_mean}.
