@@ -176,6 +176,10 @@ int gpso_factor_info(gpso_handle* h, int* out2);
  * the number of steps (out may be NULL).  gpso_debug_hybrid_items: the tile -> CTA table of a panel (kind 0) or Schur (kind 1)
  * product of a node of n tiles split after s: [rounds][nsm][4] ints (row block, 64-row tile of B, first k-step, k-steps; row
  * block < 0 = empty slot); returns the number of ints. */
+/* Host-only: the windows (first candidate, candidates) a screening pass cuts M candidates into, for windows of at most W
+ * candidates; ramp = the quarter / half window ramp-up used with the stream overlap, even = equal windows instead of a short
+ * tail.  Returns the number of windows (out may be NULL; 2 int64 per window). */
+int64_t gpso_debug_screen_windows(int64_t M, int64_t W, int ramp, int even, int64_t* out, int64_t capacity);
 int64_t gpso_debug_hybrid_plan(int nb, int leaf, int* out, int64_t capacity);
 int64_t gpso_debug_hybrid_items(int kind, int s, int n, int nsm, int* out, int64_t capacity, int* rounds);
 /* Device memory of destroyed handles is kept in a per-device pool (up to 24 GB) and handed to the next handle: the optimiser

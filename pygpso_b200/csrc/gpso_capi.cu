@@ -2033,6 +2033,40 @@ static bool screen_applicable(const gpso_handle* h, long long M) {
 // The screening pass over all candidates: per window [H2D] -> fp32 cross-covariance digits (+ mean) on the side stream ->
 // low-digit tensor-core product -> screened UCB per candidate + running maximum.  Same stream / event choreography as
 // run_windows.  Leaves scr_ucb[0..M) and scr_state[0] (key of the maximum) on the device.
+// Window list of a screening pass over M candidates with windows of at most W (a multiple of 1024).  With the stream overlap
+// the cross-covariance of the FIRST window is the one stage nothing hides (1.6 ms of a 32 ms step when eight GPUs share the
+// candidates): the pipeline ramps up through a quarter and a half window; the rest is split evenly (no short tail launch).
+static void make_screen_windows(long long M, long long W, bool ramp, bool even, std::vector<std::pair<long long, long long>>& wins) {
+    wins.clear();
+    long long off = 0;
+    if (ramp && (M + W - 1) / W >= 3)
+        for (long long part : {W / 4, W / 2}) {
+            const long long r = part / 1024 * 1024;
+            if (r >= 1024 && off + r < M) {
+                wins.emplace_back(off, r);
+                off += r;
+            }
+        }
+    const long long rest = M - off, nrest = (rest + W - 1) / W;
+    const long long each = (even && nrest > 0) ? std::min(W, ((rest + nrest - 1) / nrest + 1023) / 1024 * 1024) : W;
+    for (; off < M; off += each) wins.emplace_back(off, std::min(each, M - off));
+}
+
+extern "C" int64_t gpso_debug_screen_windows(int64_t M, int64_t W, int ramp, int even, int64_t* out, int64_t capacity) {
+    if (M <= 0 || W < 1024 || W % 1024 != 0) {
+        fail(GPSO_E_BADARG, "gpso_debug_screen_windows: need M > 0 and W a positive multiple of 1024");
+        return -1;
+    }
+    std::vector<std::pair<long long, long long>> wins;
+    make_screen_windows(M, W, ramp != 0, even != 0, wins);
+    if (out)
+        for (size_t i = 0; i < wins.size() && (int64_t)(2 * i + 1) < capacity; i++) {
+            out[2 * i] = wins[i].first;
+            out[2 * i + 1] = wins[i].second;
+        }
+    return (int64_t)wins.size();
+}
+
 static int run_screen_windows(gpso_handle* h, cudaStream_t st, const double* Xc_dev, const double* Xc_host, long long M, int S, bool full,
                               double varsigma, double two_e, bool* hopeless, cudaStream_t* product_stream_out) {
     *hopeless = false;
@@ -2049,24 +2083,8 @@ static int run_screen_windows(gpso_handle* h, cudaStream_t st, const double* Xc_
     // kernel stalled it): with the pair kernel the windows run in order on one stream.
     const bool overlap = h->overlap && nwin > 1 && !(!full && screen_pair_enabled(h, S));
     const int nbuf = overlap ? 2 : 1;
-    // Window list.  With the overlap the cross-covariance of the FIRST window is the one stage nothing hides (1.6 ms of a
-    // 32 ms step when eight GPUs share the candidates): the pipeline ramps up through a quarter and a half window.
     std::vector<std::pair<long long, long long>> wins;  // (first candidate, candidates)
-    {
-        long long off = 0;
-        if (overlap && nwin >= 3 && h->window_override == 0)
-            for (long long ramp : {W / 4, W / 2}) {
-                const long long r = ramp / 1024 * 1024;
-                if (r >= 1024 && off + r < M) {
-                    wins.emplace_back(off, r);
-                    off += r;
-                }
-            }
-        // the rest in equal windows (no short tail launch)
-        const long long rest = M - off, nrest = (rest + W - 1) / W;
-        const long long each = h->window_override == 0 ? std::min(W, ((rest + nrest - 1) / nrest + 1023) / 1024 * 1024) : W;
-        for (; off < M; off += each) wins.emplace_back(off, std::min(each, M - off));
-    }
+    make_screen_windows(M, W, overlap && h->window_override == 0, h->window_override == 0, wins);
     const long long nwin_total = (long long)wins.size();
     GP_TRY(h->part32.ensure((size_t)W * h->nb * sizeof(float)));
     GP_TRY(h->scr_ucb.ensure((size_t)M * sizeof(double)));
