@@ -222,7 +222,7 @@ struct gpso_handle {
     // int8 tensor-core (tcgen05) variance product: digit tiles of L^-1 and of the cross-covariance window
     DevBuf ozA, ozBb[2], wmeanb[2], rowscale, rowmax, rowl2;
     // int8 tensor-core K_y^-1 = L^-T L^-1 (fit path): digit tiles of L^-T, its row scales, the tile -> CTA table
-    DevBuf ozT, colscale, colmax, lauum_items;
+    DevBuf ozT, colscale, colmax, lauum_items, kinv_part;
     int lauum_items_nb = 0, lauum_rounds = 0;
     int kinv_mode = 0;      // 0 = automatic (int8 from OZ_KINV_MIN_NP), 1 = FP64 DMMA tiles, 2 = int8 tcgen05
     // int8 tensor-core inverse factor (recursive doubling, two products per level): digit tiles and row scales of the four
@@ -549,6 +549,7 @@ static int configure_kernels() {
     CU_TRY(cudaFuncSetAttribute(dense_gemm_kernel<MODE_TRTRI_XT>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     CU_TRY(cudaFuncSetAttribute(dense_gemm_kernel<MODE_TRTRI_Y>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     CU_TRY(cudaFuncSetAttribute(dense_gemm_kernel<MODE_LAUUM>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+    CU_TRY(cudaFuncSetAttribute(dense_gemm_kernel<MODE_LAUUM_PART>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     CU_TRY(cudaFuncSetAttribute(predict_trmm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     CU_TRY(cudaFuncSetAttribute(diag_factor_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM_BYTES));
     CU_TRY(cudaFuncSetAttribute(factor_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM_BYTES));
@@ -1314,8 +1315,21 @@ static int factor_pipeline(gpso_handle* h, cudaStream_t st, bool need_kinv) {
         if (int8) {
             GP_TRY(kinv_int8(h, st));
         } else {
-            dense_gemm_kernel<MODE_LAUUM><<<nb*(nb + 1) / 2, GTHREADS, GEMM_SMEM_BYTES, st>>>(P);
-            GP_TRY(check_launch(h, "lauum"));
+            static const bool split = !(getenv("GPSO_LAUUM_SPLIT") && atoi(getenv("GPSO_LAUUM_SPLIT")) == 0);  // A/B only
+            if (split && nb >= 2 && nb <= 4) {
+                // every 128-wide k-chunk of every tile on its own SM, then a fixed-order sum (kern_dense.cuh: lauum_reduce_kernel)
+                int chunks = 0;
+                for (int i = 0; i < nb; i++) chunks += (i + 1) * (nb - i);
+                GP_TRY(h->kinv_part.ensure((size_t)chunks * 128 * 128 * sizeof(double)));
+                P.part = h->kinv_part.as<double>();
+                dense_gemm_kernel<MODE_LAUUM_PART><<<chunks, GTHREADS, GEMM_SMEM_BYTES, st>>>(P);
+                GP_TRY(check_launch(h, "lauum_part"));
+                lauum_reduce_kernel<<<nb*(nb + 1) / 2, 256, 0, st>>>(P.part, nb, Np, P.Kinv);
+                GP_TRY(check_launch(h, "lauum_reduce"));
+            } else {
+                dense_gemm_kernel<MODE_LAUUM><<<nb*(nb + 1) / 2, GTHREADS, GEMM_SMEM_BYTES, st>>>(P);
+                GP_TRY(check_launch(h, "lauum"));
+            }
         }
     }
     residual_kernel<<<(Np + 255) / 256, 256, 0, st>>>(h->y.as<double>(), h->c0, h->N, Np, h->resid.as<double>());

@@ -420,7 +420,8 @@ enum GemmMode {
     MODE_TRTRI_XT = 2,    // T[u-blk, v-blk] = LinvT11 * L21^T  (= X^T)        per pair of half-blocks of size s
     MODE_TRTRI_Y = 3,     // Linv21 = -(Linv22 * X), LinvT12 = Linv21^T
     MODE_LAUUM = 4,       // Kinv[i,j] = sum_{k >= i} LinvT[i][k] LinvT[j][k]   tiles: j <= i
-    MODE_CHOL_UPD = 5     // A[ui,uj] -= L[ui, uk0..uk0+ukn) * L[uj, same panels]^T   one tile, K = ukn * 128
+    MODE_CHOL_UPD = 5,    // A[ui,uj] -= L[ui, uk0..uk0+ukn) * L[uj, same panels]^T   one tile, K = ukn * 128
+    MODE_LAUUM_PART = 6   // one 128-wide k-chunk of a LAUUM tile into the partial buffer (small matrices: see lauum_reduce_kernel)
 };
 
 struct DenseParams {
@@ -434,6 +435,7 @@ struct DenseParams {
     int s;  // half-block size (in tiles) of the inverse recursion level
     int ui, uj, uk0, ukn;  // MODE_CHOL_UPD: output tile and range of panels contracted over
     int pivot_off = 0;     // row index of the sub-matrix's first row in the whole matrix (LAPACK info of a hybrid leaf)
+    double* part = nullptr;  // MODE_LAUUM_PART: [chunk][128][128] partial products
 };
 
 __device__ __forceinline__ void tri_index(int t, int& i, int& j) {  // t -> (i >= j), row-major lower enumeration
@@ -511,6 +513,19 @@ __device__ __forceinline__ void gemm_tile_device(const DenseParams& P, const int
             orow = (a + s + vt) * TB;
             ocol = (a + ut) * TB;
         }
+    } else if (MODE == MODE_LAUUM_PART) {
+        // chunk enumeration: tiles (i, j <= i) row-major, per tile the nb - i chunks k in [(i + c) TB, (i + c + 1) TB)
+        int i = 0, t = tile;
+        for (;; i++) {
+            const int cnt = (i + 1) * (P.nb - i);
+            if (t < cnt) break;
+            t -= cnt;
+        }
+        const int j = t / (P.nb - i), c = t - j * (P.nb - i);
+        w.A = P.LinvT + (size_t)i * TB * Np;
+        w.B = P.LinvT + (size_t)j * TB * Np;
+        w.kbeg = (i + c) * TB;
+        w.kend = w.kbeg + TB;
     } else {  // MODE_LAUUM
         int i, j;
         tri_index(tile, i, j);
@@ -549,6 +564,9 @@ __device__ __forceinline__ void gemm_tile_device(const DenseParams& P, const int
                 *dst = make_double2(-v0, -v1);
                 P.LinvT[(size_t)c * Np + r] = -v0;
                 P.LinvT[(size_t)(c + 1) * Np + r] = -v1;
+            } else if (MODE == MODE_LAUUM_PART) {
+                double2* dst = reinterpret_cast<double2*>(P.part + (size_t)tile * TB * TB + (size_t)(r - orow) * TB + (c - ocol));
+                *dst = make_double2(v0, v1);
             } else {
                 double2* dst = reinterpret_cast<double2*>(P.Kinv + (size_t)r * Np + c);
                 *dst = make_double2(v0, v1);
@@ -561,6 +579,28 @@ template <int MODE>
 __global__ void __launch_bounds__(GTHREADS, 1) dense_gemm_kernel(DenseParams P) {
     extern __shared__ double smem[];
     gemm_tile_device<MODE>(P, blockIdx.x, smem);
+}
+
+// K_y^-1 of a matrix of two to four tiles: the longest LAUUM tile contracts over the whole matrix on ONE SM (63 us of a 300 us
+// evaluation at N = 300).  dense_gemm_kernel<MODE_LAUUM_PART> gives every 128-wide k-chunk of every tile its own SM; this kernel
+// adds the chunks of a tile in ascending k (fixed order: the result does not depend on scheduling).  grid = tiles (i, j <= i).
+__global__ void __launch_bounds__(256) lauum_reduce_kernel(const double* __restrict__ part, int nb, int Np, double* __restrict__ Kinv) {
+    int i, j;
+    tri_index(blockIdx.x, i, j);
+    int first = 0;
+    for (int ii = 0; ii < i; ii++) first += (ii + 1) * (nb - ii);
+    first += j * (nb - i);
+    const int chunks = nb - i;
+    for (int e = threadIdx.x * 2; e < TB * TB; e += 512) {
+        double2 acc = *reinterpret_cast<const double2*>(part + (size_t)first * TB * TB + e);
+        for (int c = 1; c < chunks; c++) {
+            const double2 v = *reinterpret_cast<const double2*>(part + (size_t)(first + c) * TB * TB + e);
+            acc.x += v.x;
+            acc.y += v.y;
+        }
+        const int r = e >> 7, col = e & 127;
+        *reinterpret_cast<double2*>(Kinv + (size_t)(i * TB + r) * Np + j * TB + col) = acc;
+    }
 }
 
 // ---- the panel tile the next diagonal block waits for, in four row strips -------------------------------------------------
