@@ -190,6 +190,9 @@ int gpso_trim_pool(int device, int64_t* cached_bytes_before);
  * 128-wide panels on nsm SMs, 16 ints per task (op, p, i, j, s, tile, 3 x dependency counter, 3 x value, counter to
  * signal, value / 0 = increment, 2 unused).  out may be NULL to query the sizes. */
 int gpso_debug_factor_tasks(int nb, int nsm, int* out, int64_t capacity_words, int* ntasks, int* ncounters);
+/* the same list with only the levels s < inv_cap (in tiles) of the inverse recursion in it -- what the library runs when the
+ * int8 engine takes the levels above (inv_cap 8, or 4 from 24 tiles; 0 = Cholesky tasks only) */
+int gpso_debug_factor_tasks_cap(int nb, int nsm, int inv_cap, int* out, int64_t capacity_words, int* ntasks, int* ncounters);
 /* tuning knob: candidates per rolling window (0 = automatic) */
 int gpso_set_window(gpso_handle* h, int64_t candidates);
 /* Screen-and-refine form of the fused arg-max calls (gpso_ucb_argmax_*, gpso_grow_ucb_argmax; replaces the same reference call

@@ -110,6 +110,7 @@ def load_library():
         "gpso_debug_hybrid_plan": (i64, [i32, i32, ctypes.POINTER(ctypes.c_int), i64]),
         "gpso_debug_hybrid_items": (i64, [i32, i32, i32, i32, ctypes.POINTER(ctypes.c_int), i64, ctypes.POINTER(ctypes.c_int)]),
         "gpso_debug_factor_tasks": (i32, [i32, i32, ctypes.POINTER(ctypes.c_int), i64, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]),
+        "gpso_debug_factor_tasks_cap": (i32, [i32, i32, i32, ctypes.POINTER(ctypes.c_int), i64, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]),
         "gpso_set_profile": (i32, [H, i32]),
         "gpso_last_windows": (i64, [H]),
         "gpso_debug_trace": (i64, [H, _c_double_p, i64]),
@@ -144,7 +145,7 @@ EXPORTED_SYMBOLS = (
     "gpso_grow_count gpso_grow_leaves_host gpso_grow_leaves_dev gpso_grow_ucb_argmax gpso_grow_ucb_argmax_range gpso_state_bytes "
     "gpso_export_state_dev gpso_import_state_dev gpso_launch_count gpso_debug_fetch gpso_last_timing gpso_set_window "
     "gpso_set_profile gpso_last_windows gpso_set_predict_mode gpso_predict_info gpso_set_overlap "
-    "gpso_set_factor_mode gpso_factor_info gpso_trim_pool gpso_debug_screen_windows gpso_debug_hybrid_plan gpso_debug_hybrid_items gpso_debug_factor_tasks gpso_debug_trace gpso_set_kinv_mode gpso_set_inverse_mode gpso_set_l2_window gpso_debug_product_items "
+    "gpso_set_factor_mode gpso_factor_info gpso_trim_pool gpso_debug_screen_windows gpso_debug_hybrid_plan gpso_debug_hybrid_items gpso_debug_factor_tasks gpso_debug_factor_tasks_cap gpso_debug_trace gpso_set_kinv_mode gpso_set_inverse_mode gpso_set_l2_window gpso_debug_product_items "
     "gpso_set_screen_mode gpso_screen_info gpso_debug_screen_bound gpso_probe_peaks gpso_set_screen_pair"
 ).split()
 

@@ -829,10 +829,14 @@ static int build_factor_tasks(gpso_handle* h, int inv_cap) {
 
 // Host-only introspection (no GPU needed): the task list for a matrix of nb panels on nsm SMs, TASK_WORDS ints per task.
 // Used by the CPU tests to check that the queue is a topological order of its own dependencies.
+extern "C" int gpso_debug_factor_tasks_cap(int nb, int nsm, int inv_cap, int* out, int64_t capacity_words, int* ntasks, int* ncounters);
 extern "C" int gpso_debug_factor_tasks(int nb, int nsm, int* out, int64_t capacity_words, int* ntasks, int* ncounters) {
-    if (!ntasks || !ncounters) return fail(GPSO_E_BADARG, "gpso_debug_factor_tasks: null argument");
+    return gpso_debug_factor_tasks_cap(nb, nsm, 1 << 30, out, capacity_words, ntasks, ncounters);
+}
+extern "C" int gpso_debug_factor_tasks_cap(int nb, int nsm, int inv_cap, int* out, int64_t capacity_words, int* ntasks, int* ncounters) {
+    if (!ntasks || !ncounters || inv_cap < 0) return fail(GPSO_E_BADARG, "gpso_debug_factor_tasks: bad argument");
     std::vector<int> flat;
-    GP_TRY(make_factor_tasks(nb, nsm, flat, *ntasks, *ncounters));
+    GP_TRY(make_factor_tasks(nb, nsm, flat, *ntasks, *ncounters, inv_cap));
     if (out) {
         if (capacity_words < (int64_t)flat.size()) return fail(GPSO_E_BADARG, "gpso_debug_factor_tasks: buffer too small");
         std::copy(flat.begin(), flat.end(), out);

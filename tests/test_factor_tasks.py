@@ -78,6 +78,37 @@ def test_queue_is_topological_and_complete(nb):
     assert seen["XT"] == expect and seen["Y"] == expect
 
 
+@pytest.mark.parametrize("cap", [0, 1, 2, 4, 8])
+@pytest.mark.parametrize("nb", [4, 5, 8, 9, 16, 24, 32])
+def test_capped_inverse_levels_keep_the_queue_topological(nb, cap):
+    """What the library runs from N = 512 up: the inverse-factor merges of the levels s < cap tiles inside the queue (entered
+    as soon as their inputs are), the levels above left to the int8 engine."""
+    lib = backend.load_library()
+    nt, nc = ctypes.c_int(0), ctypes.c_int(0)
+    assert lib.gpso_debug_factor_tasks_cap(nb, 148, cap, None, 0, ctypes.byref(nt), ctypes.byref(nc)) == 0
+    buf = np.zeros(nt.value * 16, dtype=np.int32)
+    assert lib.gpso_debug_factor_tasks_cap(nb, 148, cap, buf.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), buf.size, ctypes.byref(nt), ctypes.byref(nc)) == 0
+    tasks = buf.reshape(-1, 16)
+    ctr = np.zeros(nc.value, dtype=np.int64)
+    levels_seen = set()
+    for t in tasks:
+        for k in range(3):
+            if t[6 + k] >= 0:
+                assert ctr[t[6 + k]] >= t[9 + k], (OPS[int(t[0])], t.tolist(), int(ctr[t[6 + k]]))
+        if t[13] > 0:
+            ctr[t[12]] = t[13]
+        else:
+            ctr[t[12]] += 1
+        if OPS[int(t[0])] in ("XT", "Y"):
+            levels_seen.add(int(t[4]))
+    want = {s for s in (1, 2, 4, 8, 16) if s < cap and s < nb}
+    assert levels_seen == want, (levels_seen, want)
+    # XT and Y tasks of the levels present: s * nv per pair, both kinds
+    expect = sum(s * max(0, min(nb - (2 * q * s + s), s)) for s in want for q in range(nb) if 2 * q * s < nb)
+    kinds = [OPS[int(t[0])] for t in tasks]
+    assert kinds.count("XT") == expect and kinds.count("Y") == expect
+
+
 def test_single_panel_matrix_has_no_scheduler_tasks_beyond_the_block():
     tasks, _ = task_list(1)
     assert [OPS[int(t[0])] for t in tasks] == ["DIAG", "TRANSPOSE"]
