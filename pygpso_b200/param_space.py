@@ -198,7 +198,7 @@ class LeafNode:
     def get_center_as_list(self, normed=False):
         centers = [float(c) for c in self.center_array()]
         if not normed:
-            centers = np.around(self.scaler.inverse_transform(np.array([centers])), decimals=5)[0].tolist()
+            centers = np.around(_scaler_transform(self.scaler, np.array([centers]), inverse=True), decimals=5)[0].tolist()
         return centers
 
     def get_center_as_dict(self, normed=False):
@@ -250,8 +250,26 @@ class LeafNode:
                     children=None,
                 )
             )
-        np.testing.assert_allclose(kids[1].center_array(), self.center_array())
+        if not np.allclose(kids[1].center_array(), self.center_array(), rtol=1e-7, atol=0.0):
+            np.testing.assert_allclose(kids[1].center_array(), self.center_array())  # raises with the reference's message
         return kids
+
+
+def _scaler_transform(scaler, coords, inverse):
+    """``MinMaxScaler.transform`` / ``inverse_transform`` without sklearn's per-call input validation (0.4 ms per call, two
+    calls per evaluated point): the same two float64 array operations in the same order (``X *= scale_; X += min_`` and
+    ``X -= min_; X /= scale_``, sklearn/preprocessing/_data.py), so the result is bit-identical.  Anything but a finite
+    float64 array takes sklearn's own path, with its conversions and error messages."""
+    if isinstance(coords, np.ndarray) and coords.dtype == np.float64 and coords.ndim == 2 and not scaler.clip and np.isfinite(coords).all():
+        out = np.array(coords, dtype=np.float64, order="C")
+        if inverse:
+            out -= scaler.min_
+            out /= scaler.scale_
+        else:
+            out *= scaler.scale_
+            out += scaler.min_
+        return out
+    return scaler.inverse_transform(coords) if inverse else scaler.transform(coords)
 
 
 class ParameterSpace(LeafNode):
@@ -329,12 +347,12 @@ class ParameterSpace(LeafNode):
     def normalise_coords(self, orig_coords):
         assert orig_coords.ndim == 2
         assert orig_coords.shape[1] == self.ndim
-        return self.scaler.transform(orig_coords)
+        return _scaler_transform(self.scaler, orig_coords, inverse=False)
 
     def denormalise_coords(self, normed_coords):
         assert normed_coords.ndim == 2
         assert normed_coords.shape[1] == self.ndim
-        return self.scaler.inverse_transform(normed_coords)
+        return _scaler_transform(self.scaler, normed_coords, inverse=True)
 
     # ---- persistence (same file layout as the reference: pickled nested OrderedDict, keys sorted) --------------------
     @staticmethod

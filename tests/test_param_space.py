@@ -164,3 +164,31 @@ def test_incremental_depth_index_equals_a_fresh_preorder_walk():
             got, want = space._depth_index(), fresh()
             for depth in want:
                 assert [id(n) for n in got[depth]] == [id(n) for n in want[depth]]
+
+
+def test_fast_scaler_paths_are_bit_identical_to_sklearn():
+    """normalise / denormalise skip sklearn's per-call validation: same two array operations, same bits; everything that is
+    not a finite float64 matrix still goes through sklearn itself."""
+    from pygpso_b200.param_space import _scaler_transform
+
+    rng = np.random.default_rng(0)
+    for d in (1, 2, 10, 33):
+        bounds = np.sort(rng.normal(scale=50.0, size=(d, 2)), axis=1)
+        bounds[:, 1] += 1e-3
+        space = ParameterSpace(parameter_bounds=bounds.tolist(), parameter_names=[f"p{i}" for i in range(d)])
+        for n in (1, 7, 500):
+            x = rng.normal(scale=30.0, size=(n, d))
+            u = rng.random((n, d))
+            assert np.array_equal(space.normalise_coords(x), space.scaler.transform(x))
+            assert np.array_equal(space.denormalise_coords(u), space.scaler.inverse_transform(u))
+            assert space.normalise_coords(x) is not x  # a copy, like sklearn's
+        # inputs outside the fast path: float32, integers, NaN
+        x32 = rng.random((4, d)).astype(np.float32)
+        assert np.array_equal(_scaler_transform(space.scaler, x32, inverse=True), space.scaler.inverse_transform(x32))
+        xi = np.arange(3 * d).reshape(3, d)
+        assert np.array_equal(_scaler_transform(space.scaler, xi, inverse=False), space.scaler.transform(xi))
+        xn = rng.random((3, d))
+        xn[1, 0] = np.nan
+        assert np.array_equal(space.denormalise_coords(xn), space.scaler.inverse_transform(xn), equal_nan=True)
+        with pytest.raises(ValueError):
+            space.denormalise_coords(np.full((2, d), np.inf))
